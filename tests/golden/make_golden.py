@@ -1,0 +1,186 @@
+"""Generate golden vectors by running the UNMODIFIED reference (imported read-only from /root/reference).
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Weights come from ``oracle.op3_oracle.make_params`` (deterministic from shapes+seed) and are loaded into the
+reference model with ``load_state_dict(strict=True)``; sampling noise is injected by replacing
+``op3.torch.pytorch_util.randn`` with a queue of pre-generated tensors.  Outputs are
+written as small ``.npz`` files next to this script.  Large tensors (parameter gradients) are stored as
+per-tensor (L2 norm, sum, 32 sampled entries) so fixtures stay small.
+"""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+for mod in ["matplotlib", "matplotlib.pyplot", "matplotlib.collections", "matplotlib.patches", "matplotlib.cm",
+            "matplotlib.colors", "mpl_toolkits", "mpl_toolkits.mplot3d", "imageio", "mujoco_py", "h5py", "pathos",
+            "pathos.pools", "doodad"]:
+    sys.modules.setdefault(mod, MagicMock())
+
+import op3.torch.pytorch_util as ptu                      # noqa: E402
+import op3.torch.op3_modules.op3_model as ref_model       # noqa: E402
+from op3.exp_variants.variants import stack_variant, pickplace_variant   # noqa: E402
+import exps.pickplace_exps.mpc_pickplace as ref_mpc       # noqa: E402
+
+from oracle import op3_oracle as orc                      # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+
+
+class NoiseQueue:
+    def __init__(self):
+        self.q = []
+
+    def load(self, tensors):
+        self.q = list(tensors)
+
+    def __call__(self, *size, **kw):
+        if not self.q:                       # model constructors also draw (op3_model.py:92-94); overwritten later
+            return torch.randn(*size)
+        t = self.q.pop(0)
+        assert tuple(t.shape) == tuple(size), (t.shape, size)
+        return t.clone()
+
+
+NOISE = NoiseQueue()
+ptu.randn = NOISE
+
+
+def build_reference(variant, K, action_dim, seed, dtype=torch.float32):
+    a = dict(variant["op3_args"])
+    a["K"] = K
+    m = ref_model.create_model_v2(a, a["det_repsize"], a["sto_repsize"], action_dim)
+    p = orc.make_params(action_dim, seed=seed, dtype=dtype)
+    m.load_state_dict(p, strict=True)
+    return m, p
+
+
+synth_frames, synth_actions, sample_idx = orc.synth_frames, orc.synth_actions, orc.sample_idx
+
+
+def summarize(prefix, t, out):
+    t = t.detach().double().reshape(-1)
+    idx = sample_idx(t.numel())
+    out[prefix + "/norm"] = np.float64(t.norm().item())
+    out[prefix + "/sum"] = np.float64(t.sum().item())
+    out[prefix + "/idx"] = idx.numpy()
+    out[prefix + "/val"] = t[idx].numpy()
+
+
+def train_case(name, variant, K, action_dim, B, T, schedule, full_masks):
+    m, p = build_reference(variant, K, action_dim, seed=0)
+    frames = synth_frames(B, T)
+    actions = synth_actions(B, T) if action_dim else None
+    schedule = np.array(schedule, dtype=np.float64)
+    lw = np.arange(1, len(schedule) + 1)
+    NOISE.load(orc.make_noise(B, K, 64, len(schedule) + 1))
+    out = m.forward(frames, actions, None, schedule, lw)
+    out[3].backward()
+    res = {"schedule": schedule, "loss_schedule": lw, "B": B, "K": K, "T": T, "action_dim": action_dim,
+           "total_loss": out[3].item(), "kle_loss": out[4].item(), "clog_prob": out[5].item(), "mse": out[6].item()}
+    if full_masks:
+        res["masks_list"] = out[1].detach().numpy()
+        res["final_recon"] = out[2].detach().numpy()
+    summarize("masks_list", out[1], res)
+    summarize("colors_list", out[0], res)
+    summarize("final_recon_s", out[2], res)
+    for k in ["lambdas1", "lambdas2", "samples", "deter_state"]:
+        summarize("state/" + k, out[7]["post"][k], res)
+    summarize("state/h", out[7]["post"]["extra_info"][0], res)
+    summarize("state/c", out[7]["post"]["extra_info"][1], res)
+    for k, v in m.named_parameters():
+        summarize("grad/" + k, v.grad if v.grad is not None else torch.zeros_like(v), res)
+    total_norm = torch.nn.utils.clip_grad_norm_(list(m.parameters()), 5.0)
+    res["grad_total_norm"] = float(total_norm)
+    opt = torch.optim.Adam(list(m.parameters()), lr=3e-4)
+    opt.step()
+    for k, v in m.named_parameters():
+        summarize("adam/" + k, v.detach() - p[k], res)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
+    print(name, "loss", res["total_loss"], "gnorm", res["grad_total_norm"])
+
+
+def module_case():
+    """Per-module forward goldens (decoder, refinement net, dynamics net) + refine-input pieces."""
+    m, p = build_reference(pickplace_variant, 3, 4, seed=3)
+    g = torch.Generator().manual_seed(21)
+    res = {}
+    z = torch.randn(6, 128, generator=g) * 0.7
+    logits, colors = m.decode_net(z)
+    res["dec/z"] = z.numpy()
+    summarize("dec/colors", colors, res)
+    summarize("dec/logits", logits, res)
+    a = torch.randn(6, 15, 64, 64, generator=g)
+    h = torch.randn(6, 128, generator=g) * 0.3
+    c = torch.randn(6, 128, generator=g) * 0.3
+    extra = torch.randn(6, 320, generator=g)
+    l1, l2, h2, c2 = m.refinement_net(a, h, c, extra)
+    res["ref/seed"] = 21
+    for k, v in [("l1", l1), ("l2", l2), ("h2", h2[0]), ("c2", c2[0])]:
+        res["ref/" + k] = v.detach().numpy()
+    zz = torch.randn(6, 128, generator=g) * 0.7
+    acts = synth_actions(2, 1, seed=4)[:, 0].unsqueeze(1).repeat(1, 3, 1).reshape(6, 6)
+    d, l1, l2 = m.dynamics_net(zz, acts)
+    res["dyn/z"] = zz.numpy()
+    res["dyn/actions"] = acts.numpy()
+    for k, v in [("deter", d), ("l1", l1), ("l2", l2)]:
+        res["dyn/" + k] = v.detach().numpy()
+    sa, ia, dl = m.dynamics_net.get_all_attention_values(zz, acts[:, [0, 1, 3, 4]], 3)
+    res["dyn/act_att"] = sa.detach().numpy()
+    res["dyn/pair_att"] = ia.detach().numpy()
+    res["dyn/deltas"] = dl.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "modules.npz"), **res)
+    print("modules ok")
+
+
+def mpc_case():
+    """pickplace-style MPC rollout: B=1 state from [0,0,1,0] on real-shaped synthetic frames, then Na candidate
+    actions through schedule [1] in chunks of 10 (op3_model.py:569-642) and Cost ranking (mpc_pickplace.py:50)."""
+    K, Na = 4, 24
+    m, p = build_reference(pickplace_variant, K, 4, seed=7)
+    m.eval_mode = True
+    frames = synth_frames(1, 2, seed=31)
+    acts = synth_actions(1, 2, seed=32)[:, :, [0, 1, 3, 4]]
+    sched = np.array([0, 0, 1, 0], dtype=np.float64)
+    NOISE.load(orc.make_noise(1, K, 64, len(sched) + 1, seed=40))
+    info = m.batch_internal_inference(frames, acts, None, sched)
+    state = info["state"]
+    cand = synth_actions(Na, 1, seed=33)[:, :, [0, 1, 3, 4]]
+    full_noise = orc.make_noise(Na, K, 64, 1, seed=50)[0]
+    NOISE.load([full_noise[i:i + 10] for i in range(0, Na, 10)])
+    pred = m.batch_internal_inference(None, cand, state, np.array([1.0]))
+    goal_image = synth_frames(1, 1, seed=34)[:, 0]
+    res = {"K": K, "Na": Na}
+    summarize("state/samples", state["post"]["samples"], res)
+    summarize("pred/final_recon", pred["final_recon"], res)
+    summarize("pred/sub_images", pred["sub_images"], res)
+    for core, agg in [("final_recon", "sum"), ("subimage", "min"), ("subimage", "sum")]:
+        cost = ref_mpc.Cost(None, core_type=core, compare_func="mse", post_process="raw", aggregate=agg)
+        sc, order, gidx = cost.get_action_rankings(info["state"]["post"]["samples"][0], info["sub_images"][0],
+                                                   goal_image, pred["state"]["post"]["samples"], pred["sub_images"],
+                                                   pred["final_recon"], plot_actions=0)
+        res["cost/%s_%s/sorted" % (core, agg)] = np.asarray(sc)
+        res["cost/%s_%s/order" % (core, agg)] = np.asarray(order)
+        res["cost/%s_%s/gidx" % (core, agg)] = np.asarray(gidx)
+    np.savez_compressed(os.path.join(HERE, "mpc.npz"), **res)
+    print("mpc ok", res["cost/final_recon_sum/order"][:5])
+
+
+if __name__ == "__main__":
+    train_case("stack_small", stack_variant, K=3, action_dim=0, B=2, T=2, schedule=[0, 0, 1], full_masks=True)
+    train_case("pickplace_small", pickplace_variant, K=3, action_dim=4, B=2, T=3, schedule=[0, 0, 1, 1, 0],
+               full_masks=False)
+    train_case("stack_c1", stack_variant, K=7, action_dim=0, B=8, T=2, schedule=[0, 0, 0, 0, 1], full_masks=False)
+    module_case()
+    mpc_case()
