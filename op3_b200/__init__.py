@@ -1,0 +1,32 @@
+"""op3_b200: B200-native (sm_100a) kernels behind the OP3 iterative amortized-inference step.
+
+Package layout
+  csrc/                    hand-written CUDA kernels + the C ABI (include/op3_b200.h)
+  _lib.py / _build.py      ctypes binding and in-tree nvcc build of libop3_b200.so
+  engine.py                schedule executor (forward tape + manual backward) over the C ABI
+  torch/                   mirror of the reference's op3/torch module surface (same names, kwargs, state_dict keys)
+  parallel.py              one-process-per-GPU data parallelism (NCCL gradient allreduce, MPC candidate sharding)
+"""
+__version__ = "0.1.0"
+
+_ALIASES = {
+    "op3.torch.pytorch_util": "op3_b200.torch.pytorch_util",
+    "op3.torch.modules": "op3_b200.torch.modules",
+    "op3.torch.networks": "op3_b200.torch.networks",
+    "op3.torch.conv_networks": "op3_b200.torch.conv_networks",
+    "op3.torch.op3_modules.op3_model": "op3_b200.torch.op3_modules.op3_model",
+    "op3.torch.op3_modules.op3_trainer": "op3_b200.torch.op3_modules.op3_trainer",
+    "op3.torch.op3_modules.decoder_network": "op3_b200.torch.op3_modules.decoder_network",
+    "op3.torch.op3_modules.refinement_network": "op3_b200.torch.op3_modules.refinement_network",
+    "op3.torch.op3_modules.physics_network": "op3_b200.torch.op3_modules.physics_network",
+}
+
+
+def install():
+    """Make `import op3.torch.op3_modules.op3_model` (etc.) resolve to this package so that the reference's
+    exps/train_op3/train_op3.py and MPC scripts run unchanged on top of the sm_100a kernels.  Call before the
+    reference scripts import their modules."""
+    import importlib
+    import sys
+    for ref_name, ours in _ALIASES.items():
+        sys.modules[ref_name] = importlib.import_module(ours)

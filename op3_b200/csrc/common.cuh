@@ -1,0 +1,103 @@
+// Shared device/host helpers for the op3_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/op3_b200.h"
+
+namespace op3 {
+
+// ---- error plumbing (C ABI never throws; see op3_last_error) ---------------------------------
+void set_error(const char* fmt, ...);
+#define OP3_CHECK(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      op3::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return OP3_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+#define OP3_LAUNCH_CHECK() OP3_CHECK(cudaGetLastError())
+#define OP3_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      op3::set_error(__VA_ARGS__);      \
+      return OP3_ERR_ARG;               \
+    }                                   \
+  } while (0)
+#define OP3_TRY(call)            \
+  do {                           \
+    int _rc = (call);            \
+    if (_rc != OP3_OK) return _rc; \
+  } while (0)
+
+// ---- launch accounting (bench.py reports gpu_launches from this) ------------------------------
+extern unsigned long long g_launch_count;
+#define OP3_COUNT_LAUNCH() (++op3::g_launch_count)
+
+// ---- small device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+// derivative of ELU(alpha=1) expressed through its OUTPUT a: a>0 -> 1, else a+1 (= e^x)
+__device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.f : a + 1.f; }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int bytes = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- internal kernels shared between translation units ----------------------------------------
+// gemm.cu ------------------------------------------------------------------------------------
+enum { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2 };
+// C[M,N] = act( opA(A)[M,K] * opB(B)[K,N] + bias[N] ) (+ C if accumulate)
+//   transA=0: A is row-major [M,K] (lda); transA=1: A is stored [K,M] (lda)
+//   transB=0: B is stored [K,N] (ldb);    transB=1: B is stored [N,K] (ldb)  (nn.Linear weight)
+int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, int transA, const float* B, int ldb,
+         int transB, float* C, int ldc, const float* bias, int act, int accumulate);
+// dPre[m,n] = dY[m,n] * act'(Y[m,n]) in place on dY (Y is the activation OUTPUT)
+int act_backward(cudaStream_t st, int M, int N, float* dY, int ldd, const float* Y, int ldy, int act);
+// out[n] (+)= sum_m X[m,n]
+int colsum(cudaStream_t st, int M, int N, const float* X, int ldx, float* out, int accumulate);
+// y (+)= x  (flat)
+int axpy(cudaStream_t st, long long n, const float* x, float* y);
+int fill_zero(cudaStream_t st, void* p, size_t bytes);
+
+// conv5x5.cu ---------------------------------------------------------------------------------
+struct ConvSrc {          // one group of float4 channel-chunks of the (virtual) conv input
+  const float4* ptr;      // [n_idx][nchunks][D][D] float4
+  int nchunks;
+  int div;                // n_idx = (div > 0) ? n / div : 0   (div=1 per slot-image, K per sample, 0 constant)
+};
+struct ConvInput {
+  ConvSrc src[5];
+  int nsrc;
+  int total_chunks;
+};
+enum { EPI_NONE = 0, EPI_ELU = 1, EPI_MUL_ELUGRAD = 2 };
+// out[n][cout/4][D][D] = epi( conv5x5_pad2(in, wt) + bias ); wt layout [25][cin_pad][cout] (cout fastest)
+int conv5x5_forward(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt, const float* bias,
+                    float4* out, int epi, const float4* elu_ref);
+// dW[25][cin_pad][cout] and db[cout] partial sums over all (n, pixels); scratch sized by conv5x5_wgrad_scratch_floats
+size_t conv5x5_wgrad_scratch_floats(int cin_pad, int cout);
+int conv5x5_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
+                  float* dwt /*[25][cin_pad][cout], accumulated*/, float* dbias /*[cout], accumulated*/);
+
+}  // namespace op3

@@ -1,0 +1,368 @@
+// 5x5 / stride 1 / pad 2 convolution over float4 channel-chunk ("C4") activations: [n][c/4][y][x] float4.
+// fp32 CUDA-core ("exact") path: forward (also used as dgrad with flipped/transposed weights) and wgrad.
+// Reference ops replaced: nn.Conv2d in BroadcastCNN.apply_forward (op3/torch/conv_networks.py:343-350) and
+// RefinementNetwork._apply_forward (op3/torch/op3_modules/refinement_network.py:224-231) and their autograd
+// backward.  The conv input may be gathered from several tensors (ConvInput) so that the 17-channel
+// refinement input (op3_model.py:219-229) is never materialised.
+#include "common.cuh"
+
+namespace op3 {
+
+namespace {
+
+constexpr int TR = 8;            // output rows per CTA (forward)
+constexpr int TW = 64;           // output cols per CTA
+constexpr int HW = TW + 4;       // halo width
+constexpr int FWD_IN_F4 = (TR + 4) * HW;
+
+__device__ __forceinline__ const float4* src_chunk_ptr(const ConvInput& in, int c, int n, int D) {
+  int base = 0;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    if (s < in.nsrc) {
+      int nc = in.src[s].nchunks;
+      if (c < base + nc) {
+        int idx = in.src[s].div > 0 ? n / in.src[s].div : 0;
+        return in.src[s].ptr + ((size_t)idx * nc + (c - base)) * D * D;
+      }
+      base += nc;
+    }
+  }
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int COUT, int COUT_T>
+__global__ void __launch_bounds__(128 * (COUT / COUT_T))
+conv5x5_fwd_kernel(ConvInput in, int D, const float* __restrict__ wt, const float* __restrict__ bias,
+                   float4* __restrict__ out, int epi, const float4* __restrict__ ref) {
+  constexpr int NGRP = COUT / COUT_T;
+  constexpr int NT = 128 * NGRP;
+  constexpr int W_F4 = 25 * COUT;  // float4 count of one weight chunk slab: 25 taps * 4 ci * COUT / 4
+  extern __shared__ float4 smem[];
+  float4* s_in[2] = {smem, smem + FWD_IN_F4 + W_F4};
+  float4* s_w[2] = {smem + FWD_IN_F4, smem + 2 * FWD_IN_F4 + W_F4};
+
+  const int tid = threadIdx.x;
+  const int g = tid / 128, pq = tid % 128, r = pq / 16, q = pq % 16;
+  const int tiles_x = (D + TW - 1) / TW;
+  const int tx0 = (blockIdx.x % tiles_x) * TW, ty0 = (blockIdx.x / tiles_x) * TR;
+  const int n = blockIdx.y;
+  const int cin_pad = in.total_chunks * 4;
+
+  float acc[4][COUT_T];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < COUT_T; ++c) acc[j][c] = bias ? bias[g * COUT_T + c] : 0.f;
+
+  auto load_chunk = [&](int c, int stage) {
+    const float4* src = src_chunk_ptr(in, c, n, D);
+    for (int e = tid; e < FWD_IN_F4; e += NT) {
+      int yy = e / HW, xx = e % HW;
+      int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
+      bool ok = gy >= 0 && gy < D && gx >= 0 && gx < D;
+      cp_async16(&s_in[stage][e], ok ? src + (size_t)gy * D + gx : src, ok);
+    }
+    // weights: for each tap, 4*COUT contiguous floats at wt[(tap*cin_pad + c*4)*COUT]
+    for (int e = tid; e < W_F4; e += NT) {
+      int tap = e / COUT, o = e % COUT;  // o indexes float4 within the 4*COUT floats of this tap
+      cp_async16(&s_w[stage][e], wt + ((size_t)tap * cin_pad + c * 4) * COUT + o * 4, true);
+    }
+    cp_async_commit();
+  };
+
+  const int nch = in.total_chunks;
+  load_chunk(0, 0);
+  for (int c = 0; c < nch; ++c) {
+    int stage = c & 1;
+    if (c + 1 < nch) {
+      load_chunk(c + 1, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float4* tin = s_in[stage];
+    const float* tw = reinterpret_cast<const float*>(s_w[stage]);
+#pragma unroll 1
+    for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = tin[(r + ky) * HW + q + 16 * j + kx];
+        const float* wp = tw + (size_t)((ky * 5 + kx) * 4) * COUT + g * COUT_T;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+          for (int cg = 0; cg < COUT_T / 4; ++cg) {
+            float4 w = *reinterpret_cast<const float4*>(wp + ci * COUT + cg * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = ci == 0 ? v[j].x : (ci == 1 ? v[j].y : (ci == 2 ? v[j].z : v[j].w));
+              acc[j][cg * 4 + 0] = fmaf(a, w.x, acc[j][cg * 4 + 0]);
+              acc[j][cg * 4 + 1] = fmaf(a, w.y, acc[j][cg * 4 + 1]);
+              acc[j][cg * 4 + 2] = fmaf(a, w.z, acc[j][cg * 4 + 2]);
+              acc[j][cg * 4 + 3] = fmaf(a, w.w, acc[j][cg * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int gy = ty0 + r;
+  if (gy >= D) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int gx = tx0 + q + 16 * j;
+    if (gx >= D) continue;
+#pragma unroll
+    for (int cg = 0; cg < COUT_T / 4; ++cg) {
+      size_t o = (((size_t)n * (COUT / 4) + g * (COUT_T / 4) + cg) * D + gy) * D + gx;
+      float4 v = make_float4(acc[j][cg * 4], acc[j][cg * 4 + 1], acc[j][cg * 4 + 2], acc[j][cg * 4 + 3]);
+      if (epi == EPI_ELU) {
+        v.x = elu_f(v.x); v.y = elu_f(v.y); v.z = elu_f(v.z); v.w = elu_f(v.w);
+      } else if (epi == EPI_MUL_ELUGRAD) {
+        float4 a = ref[o];
+        v.x *= elu_grad_from_out(a.x); v.y *= elu_grad_from_out(a.y);
+        v.z *= elu_grad_from_out(a.z); v.w *= elu_grad_from_out(a.w);
+      }
+      out[o] = v;
+    }
+  }
+}
+
+template <int COUT, int COUT_T>
+int launch_fwd(cudaStream_t st, int N, int D, const ConvInput& in, const float* wt, const float* bias, float4* out,
+               int epi, const float4* ref) {
+  constexpr int NT = 128 * (COUT / COUT_T);
+  size_t smem = 2 * (size_t)(FWD_IN_F4 + 25 * COUT) * sizeof(float4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_fwd_kernel<COUT, COUT_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    attr_set = true;
+  }
+  int tiles = ceil_div(D, TW) * ceil_div(D, TR);
+  dim3 grid(tiles, N);
+  conv5x5_fwd_kernel<COUT, COUT_T><<<grid, NT, smem, st>>>(in, D, wt, bias, out, epi, ref);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: dW[tap][ci][co] = sum_{n,y,x} in[n][ci][y+ky-2][x+kx-2] * dpre[n][co][y][x]
+// grid = (tile sets S, input chunks); every CTA keeps its 25*4*COUT partial in registers over a strided
+// set of (n, 4-row band) tiles, then a second kernel reduces over S in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int WR = 4;                        // rows per wgrad tile
+constexpr int WG_IN_F4 = (WR + 4) * HW;      // halo tile of one input chunk
+
+template <int COUT, int COG, int PG>
+__global__ void __launch_bounds__(20 * (COUT / COG) * PG)
+conv5x5_wgrad_kernel(ConvInput in, int N, int D, const float4* __restrict__ dpre, float* __restrict__ partial) {
+  constexpr int NCG = COUT / COG;
+  constexpr int NT = 20 * NCG * PG;
+  constexpr int DP_F4 = (COUT / 4) * WR * TW;
+  constexpr int ROWS_PER_PG = WR / PG;
+  static_assert(WR % PG == 0, "pixel groups must divide the tile rows");
+  extern __shared__ float4 smem[];
+  float4* s_in[2] = {smem, smem + WG_IN_F4 + DP_F4};
+  float4* s_dp[2] = {smem + WG_IN_F4, smem + 2 * WG_IN_F4 + DP_F4};
+
+  const int tid = threadIdx.x;
+  const int pg = tid / (20 * NCG);
+  const int rem = tid % (20 * NCG);
+  const int cog = rem / 20, ky = (rem % 20) / 4, ci = rem % 4;
+  const int c = blockIdx.y;  // input chunk
+  const int tiles_x = (D + TW - 1) / TW, tiles_y = D / WR;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const long long total_tiles = (long long)N * tiles_per_img;
+
+  float acc[5][COG];
+  float bsum[COG];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int o = 0; o < COG; ++o) acc[k][o] = 0.f;
+#pragma unroll
+  for (int o = 0; o < COG; ++o) bsum[o] = 0.f;
+
+  auto load_tile = [&](long long t, int stage) {
+    int n = (int)(t / tiles_per_img);
+    int ti = (int)(t % tiles_per_img);
+    int tx0 = (ti % tiles_x) * TW, ty0 = (ti / tiles_x) * WR;
+    const float4* src = src_chunk_ptr(in, c, n, D);
+    for (int e = tid; e < WG_IN_F4; e += NT) {
+      int yy = e / HW, xx = e % HW;
+      int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
+      bool ok = gy >= 0 && gy < D && gx >= 0 && gx < D;
+      cp_async16(&s_in[stage][e], ok ? src + (size_t)gy * D + gx : src, ok);
+    }
+    for (int e = tid; e < DP_F4; e += NT) {
+      int ch = e / (WR * TW), p = e % (WR * TW);
+      int yy = p / TW, xx = p % TW;
+      int gy = ty0 + yy, gx = tx0 + xx;
+      bool ok = gy < D && gx < D;
+      const float4* s = dpre + (((size_t)n * (COUT / 4) + ch) * D + (ok ? gy : 0)) * D + (ok ? gx : 0);
+      cp_async16(&s_dp[stage][e], s, ok);
+    }
+    cp_async_commit();
+  };
+
+  long long t = blockIdx.x;
+  int stage = 0;
+  if (t < total_tiles) load_tile(t, 0);
+  for (; t < total_tiles; t += gridDim.x, stage ^= 1) {
+    long long tn = t + gridDim.x;
+    if (tn < total_tiles) {
+      load_tile(tn, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* tin = reinterpret_cast<const float*>(s_in[stage]);
+    const float4* tdp = s_dp[stage];
+#pragma unroll 1
+    for (int rr = 0; rr < ROWS_PER_PG; ++rr) {
+      const int y = pg * ROWS_PER_PG + rr;
+      const float* row = tin + (size_t)((y + ky) * HW) * 4 + ci;
+      float iv[5];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) iv[k + 1] = row[k * 4];
+#pragma unroll 4
+      for (int x = 0; x < TW; ++x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) iv[k] = iv[k + 1];
+        iv[4] = row[(x + 4) * 4];
+        float dp[COG];
+#pragma unroll
+        for (int o4 = 0; o4 < COG / 4; ++o4) {
+          float4 d = tdp[((cog * (COG / 4) + o4) * WR + y) * TW + x];
+          dp[o4 * 4] = d.x; dp[o4 * 4 + 1] = d.y; dp[o4 * 4 + 2] = d.z; dp[o4 * 4 + 3] = d.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+          for (int o = 0; o < COG; ++o) acc[k][o] = fmaf(iv[k], dp[o], acc[k][o]);
+        if (c == 0 && ky == 0 && ci == 0) {
+#pragma unroll
+          for (int o = 0; o < COG; ++o) bsum[o] += dp[o];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // cross pixel-group reduction through smem, then one partial slab per CTA
+  float* red = reinterpret_cast<float*>(smem);  // [PG][20*NCG][5*COG + COG]
+  constexpr int PER_T = 6 * COG;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int o = 0; o < COG; ++o) red[(size_t)(pg * 20 * NCG + rem) * PER_T + k * COG + o] = acc[k][o];
+#pragma unroll
+  for (int o = 0; o < COG; ++o) red[(size_t)(pg * 20 * NCG + rem) * PER_T + 5 * COG + o] = bsum[o];
+  __syncthreads();
+  if (pg == 0) {
+    const int cin_pad = in.total_chunks * 4;
+    float* slab = partial + (size_t)blockIdx.x * (25 * cin_pad * COUT + COUT);
+    for (int e = 0; e < PER_T; ++e) {
+      float s = 0.f;
+#pragma unroll
+      for (int p = 0; p < PG; ++p) s += red[(size_t)(p * 20 * NCG + rem) * PER_T + e];
+      if (e < 5 * COG) {
+        int kx = e / COG, o = e % COG;
+        slab[((size_t)(ky * 5 + kx) * cin_pad + c * 4 + ci) * COUT + cog * COG + o] = s;
+      } else if (c == 0 && ky == 0 && ci == 0) {
+        slab[(size_t)25 * cin_pad * COUT + cog * COG + (e - 5 * COG)] = s;
+      }
+    }
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int S, int n_w, int n_b,
+                                    float* __restrict__ dwt, float* __restrict__ dbias) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int tot = n_w + n_b;
+  if (i >= tot) return;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += partial[(size_t)k * tot + i];
+  if (i < n_w) dwt[i] += s;
+  else if (dbias) dbias[i - n_w] += s;
+}
+
+int wgrad_sets(int chunks) { int s = 296 / chunks; return s < 1 ? 1 : s; }
+
+template <int COUT, int COG, int PG>
+int launch_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, float* scratch, float* dwt,
+                 float* dbias) {
+  constexpr int NT = 20 * (COUT / COG) * PG;
+  constexpr int DP_F4 = (COUT / 4) * WR * TW;
+  size_t smem = 2 * (size_t)(WG_IN_F4 + DP_F4) * sizeof(float4);
+  size_t red = (size_t)NT * 6 * COG * sizeof(float);
+  if (red > smem) smem = red;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_kernel<COUT, COG, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    attr_set = true;
+  }
+  int chunks = in.total_chunks;
+  long long total_tiles = (long long)N * ceil_div(D, TW) * (D / WR);
+  int S = wgrad_sets(chunks);
+  if (S > total_tiles) S = (int)total_tiles;
+  dim3 grid(S, chunks);
+  conv5x5_wgrad_kernel<COUT, COG, PG><<<grid, NT, smem, st>>>(in, N, D, dpre, scratch);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  int n_w = 25 * chunks * 4 * COUT, n_b = COUT;
+  wgrad_reduce_kernel<<<ceil_div(n_w + n_b, 256), 256, 0, st>>>(scratch, S, n_w, n_b, dwt, dbias);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+}  // namespace
+
+int conv5x5_forward(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt, const float* bias,
+                    float4* out, int epi, const float4* elu_ref) {
+  OP3_REQUIRE(D % TR == 0, "conv5x5: D=%d must be a multiple of %d", D, TR);
+  if (N <= 0) return OP3_OK;
+  switch (cout) {
+    case 4:  return launch_fwd<4, 4>(st, N, D, in, wt, bias, out, epi, elu_ref);
+    case 20: return launch_fwd<20, 20>(st, N, D, in, wt, bias, out, epi, elu_ref);
+    case 32: return launch_fwd<32, 16>(st, N, D, in, wt, bias, out, epi, elu_ref);
+    case 64: return launch_fwd<64, 16>(st, N, D, in, wt, bias, out, epi, elu_ref);
+    default: break;
+  }
+  set_error("conv5x5_forward: unsupported cout=%d", cout);
+  return OP3_ERR_ARG;
+}
+
+size_t conv5x5_wgrad_scratch_floats(int cin_pad, int cout) {
+  return (size_t)wgrad_sets(cin_pad / 4) * ((size_t)25 * cin_pad * cout + cout);
+}
+
+int conv5x5_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
+                  float* dwt, float* dbias) {
+  OP3_REQUIRE(D % WR == 0, "conv5x5_wgrad: D=%d must be a multiple of %d", D, WR);
+  if (N <= 0) return OP3_OK;
+  switch (cout) {
+    case 4:  return launch_wgrad<4, 4, 4>(st, N, D, in, dpre, scratch, dwt, dbias);
+    case 32: return launch_wgrad<32, 8, 4>(st, N, D, in, dpre, scratch, dwt, dbias);
+    case 64: return launch_wgrad<64, 8, 2>(st, N, D, in, dpre, scratch, dwt, dbias);
+    default: break;
+  }
+  set_error("conv5x5_wgrad: unsupported cout=%d", cout);
+  return OP3_ERR_ARG;
+}
+
+}  // namespace op3

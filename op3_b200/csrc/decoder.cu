@@ -1,0 +1,186 @@
+// K-slot spatial-broadcast decoder: replaces DecoderNetwork.forward (op3/torch/op3_modules/decoder_network.py:83-88)
+// and BroadcastCNN.forward/apply_forward (op3/torch/conv_networks.py:326-350) plus their backward.
+//   layer 1 : collapsed (class-sum GEMM + coordinate map, never materialising the (N,130,D,D) broadcast input)
+//   layer 2-5: 5x5 convs over float4 channel-chunk activations, ELU fused in the epilogue
+#include "layout.cuh"
+
+namespace op3 {
+
+namespace {
+
+__device__ __forceinline__ int border_class(int v, int D) { return v < 2 ? v : (v >= D - 2 ? 4 - (D - 1 - v) : 2); }
+
+// a1[n][c4][y][x] = ELU(T[n][cls(y,x)*32 + c4*4 ..] + cmap[c4][y][x])
+__global__ void __launch_bounds__(256) dec_l1_expand_kernel(const float* __restrict__ T, const float4* __restrict__ cmap,
+                                                            int D, float4* __restrict__ a1) {
+  const int n = blockIdx.y;
+  int i = blockIdx.x * 256 + threadIdx.x;  // over 8*D*D
+  if (i >= 8 * D * D) return;
+  int x = i % D, y = (i / D) % D, c4 = i / (D * D);
+  int cls = border_class(y, D) * 5 + border_class(x, D);
+  float4 t = *reinterpret_cast<const float4*>(T + (size_t)n * (NCLS * 32) + cls * 32 + c4 * 4);
+  float4 m = cmap[i];
+  float4 v = make_float4(elu_f(t.x + m.x), elu_f(t.y + m.y), elu_f(t.z + m.z), elu_f(t.w + m.w));
+  a1[(size_t)n * 8 * D * D + i] = v;
+}
+
+// dT[n][cls*32 + co] = sum over pixels of class cls of g1[n][co][y][x]; one CTA per (chunk, n); deterministic.
+__global__ void __launch_bounds__(256) dec_l1_class_reduce_kernel(const float4* __restrict__ g1, int D,
+                                                                  float* __restrict__ dT) {
+  __shared__ float4 wacc[8][NCLS];
+  const int c4 = blockIdx.x, n = blockIdx.y;
+  const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+  for (int i = lane; i < NCLS; i += 32) wacc[w][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  const float4* src = g1 + ((size_t)n * 8 + c4) * D * D;
+  for (int y = w; y < D; y += 8) {
+    int cy = border_class(y, D);
+    float4 mid = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = lane; x < D; x += 32) {
+      float4 v = src[(size_t)y * D + x];
+      int cx = border_class(x, D);
+      if (cx == 2) {
+        mid.x += v.x; mid.y += v.y; mid.z += v.z; mid.w += v.w;
+      } else {  // exactly one lane owns each border column of this row
+        float4 a = wacc[w][cy * 5 + cx];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        wacc[w][cy * 5 + cx] = a;
+      }
+    }
+    mid.x = warp_sum(mid.x); mid.y = warp_sum(mid.y); mid.z = warp_sum(mid.z); mid.w = warp_sum(mid.w);
+    if (lane == 0) {
+      float4 a = wacc[w][cy * 5 + 2];
+      a.x += mid.x; a.y += mid.y; a.z += mid.z; a.w += mid.w;
+      wacc[w][cy * 5 + 2] = a;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < NCLS) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 8; ++k) {
+      float4 a = wacc[k][threadIdx.x];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    *reinterpret_cast<float4*>(dT + (size_t)n * (NCLS * 32) + threadIdx.x * 32 + c4 * 4) = s;
+  }
+}
+
+// dcmap[i] += sum_n g1[n][i]   (i over 8*D*D float4)
+__global__ void __launch_bounds__(256) dec_l1_dcmap_kernel(const float4* __restrict__ g1, int N, int D,
+                                                           float4* __restrict__ dcmap) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  int tot = 8 * D * D;
+  if (i >= tot) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int n = 0; n < N; ++n) {
+    float4 v = g1[(size_t)n * tot + i];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  float4 o = dcmap[i];
+  o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+  dcmap[i] = o;
+}
+
+struct DecActs {
+  float* T;        // [N][800]
+  float4* a[4];    // a1..a4: [N][8][D][D] float4
+};
+inline DecActs dec_acts(const Op3Dims* d, int N, float* base) {
+  DecActs A;
+  size_t plane = (size_t)N * 32 * d->D * d->D;
+  A.T = base;
+  size_t o = ((size_t)N * NCLS * 32 + 3) & ~(size_t)3;
+  for (int i = 0; i < 4; ++i) A.a[i] = reinterpret_cast<float4*>(base + o + i * plane);
+  return A;
+}
+
+inline ConvInput single_src(const float4* p, int chunks) {
+  ConvInput in{};
+  in.src[0].ptr = p; in.src[0].nchunks = chunks; in.src[0].div = 1;
+  in.nsrc = 1; in.total_chunks = chunks;
+  return in;
+}
+
+}  // namespace
+}  // namespace op3
+
+using namespace op3;
+
+extern "C" size_t op3_decoder_acts_floats(const Op3Dims* d, int N) {
+  if (validate_dims(d) != OP3_OK) return 0;
+  return (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) + 4 * (size_t)N * 32 * d->D * d->D;
+}
+
+extern "C" size_t op3_decoder_scratch_floats(const Op3Dims* d, int N) {
+  if (validate_dims(d) != OP3_OK) return 0;
+  return 2 * (size_t)N * 32 * d->D * d->D + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) +
+         conv5x5_wgrad_scratch_floats(32, 32);
+}
+
+extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const float* z, float* acts, float* out,
+                               void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(prep && z && acts && out && N > 0, "op3_decoder_fwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PrepLayout L = prep_layout(d);
+  const int R = d->Rd + d->Rs, D = d->D;
+  DecActs A = dec_acts(d, N, acts);
+  // T[n][cls*32+co] = b[co] + sum_c z[n][c] * Wsum[cls*32+co][c]
+  OP3_TRY(gemm(st, N, NCLS * 32, R, z, R, 0, prep + L.wsum, R, 1, A.T, NCLS * 32, prep + L.biasT, ACT_NONE, 0));
+  dim3 grid(ceil_div(8 * D * D, 256), N);
+  dec_l1_expand_kernel<<<grid, 256, 0, st>>>(A.T, reinterpret_cast<const float4*>(prep + L.cmap), D, A.a[0]);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  // layers 2-4 are the implicit-GEMM hot spot (M = N*D*D pixels, N = 32, K = 800); layer 5 has 4 outputs
+  for (int i = 0; i < 3; ++i)
+    OP3_TRY(conv5x5_forward(st, N, D, single_src(A.a[i], 8), 32, prep + L.dec_wf[i], prep + L.dec_bf[i], A.a[i + 1],
+                            EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_forward(st, N, D, single_src(A.a[3], 8), 4, prep + L.dec_wf[3], prep + L.dec_bf[3],
+                          reinterpret_cast<float4*>(out), EPI_NONE, nullptr));
+  return OP3_OK;
+}
+
+extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const float* z, const float* acts,
+                               const float* d_out, float* scratch, float* dz, int accumulate_dz, float* pg,
+                               void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(prep && z && acts && d_out && scratch && dz && N > 0, "op3_decoder_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PrepLayout L = prep_layout(d);
+  const int R = d->Rd + d->Rs, D = d->D;
+  DecActs A = dec_acts(d, N, const_cast<float*>(acts));
+  const size_t plane = (size_t)N * 32 * D * D;
+  float4* gbuf[2] = {reinterpret_cast<float4*>(scratch), reinterpret_cast<float4*>(scratch + plane)};
+  float* dT = scratch + 2 * plane;
+  float* wscr = dT + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3);
+
+  // layer 5 (32 -> 4, no activation): g5 = d_out
+  const float4* g = reinterpret_cast<const float4*>(d_out);
+  int gch = 1;  // chunks of g
+  for (int i = 3; i >= 0; --i) {  // conv layer i+2, input a[i], output gradient g (dPre of that layer)
+    const int cout = i == 3 ? 4 : 32;
+    if (pg) OP3_TRY(conv5x5_wgrad(st, N, D, single_src(A.a[i], 8), cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i]));
+    float4* gn = gbuf[i & 1];
+    // dgrad: conv over g with flipped/transposed weights, times ELU'(a[i]) -> dPre of the layer below
+    OP3_TRY(conv5x5_forward(st, N, D, single_src(g, gch), 32, prep + L.dec_wd[i], nullptr, gn, EPI_MUL_ELUGRAD, A.a[i]));
+    g = gn;
+    gch = 8;
+  }
+  // layer 1: g = dPre1 [N][8][D][D]
+  dim3 grid(8, N);
+  dec_l1_class_reduce_kernel<<<grid, 256, 0, st>>>(g, D, dT);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  OP3_TRY(gemm(st, N, R, NCLS * 32, dT, NCLS * 32, 0, prep + L.wsum, R, 0, dz, R, nullptr, ACT_NONE, accumulate_dz ? 1 : 0));
+  if (pg) {
+    // d Wsum[cls*32+co][c] += sum_n dT[n][.] z[n][c] ; d biasT += column sums of dT ; d cmap += sum_n g
+    OP3_TRY(gemm(st, NCLS * 32, R, N, dT, NCLS * 32, 1, z, R, 0, pg + L.wsum, R, nullptr, ACT_NONE, 1));
+    OP3_TRY(colsum(st, N, NCLS * 32, dT, NCLS * 32, pg + L.biasT, 1));
+    dec_l1_dcmap_kernel<<<ceil_div(8 * D * D, 256), 256, 0, st>>>(g, N, D, reinterpret_cast<float4*>(pg + L.cmap));
+    OP3_COUNT_LAUNCH();
+    OP3_LAUNCH_CHECK();
+  }
+  return OP3_OK;
+}

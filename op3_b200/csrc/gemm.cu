@@ -1,0 +1,162 @@
+// Batched small-GEMM + elementwise helpers (fp32 CUDA-core path) used by the refinement head and the
+// pairwise dynamics network.  These are < 1 % of the step FLOPs; shapes are
+// M = B*K or B*K*(K-1) rows, widths 1..576.
+#include "common.cuh"
+
+namespace op3 {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                   const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                   int ldc, const float* __restrict__ bias, int act, int accumulate) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // A tile: BM x BK
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int e = tid + r * 256;
+      int mm, kk;
+      if (TA == 0) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < K) v = TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int e = tid + r * 256;
+      int nn, kk;
+      if (TB == 0) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
+      int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < K) v = TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (accumulate) v += C[(size_t)gm * ldc + gn];
+      if (act == ACT_ELU) v = elu_f(v);
+      else if (act == ACT_SIGMOID) v = sigmoid_f(v);
+      C[(size_t)gm * ldc + gn] = v;
+    }
+  }
+}
+
+__global__ void act_backward_kernel(int M, int N, float* __restrict__ dY, int ldd, const float* __restrict__ Y,
+                                    int ldy, int act) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  int m = (int)(i / N), n = (int)(i % N);
+  float y = Y[(size_t)m * ldy + n];
+  float g = act == ACT_ELU ? elu_grad_from_out(y) : (act == ACT_SIGMOID ? y * (1.f - y) : 1.f);
+  dY[(size_t)m * ldd + n] *= g;
+}
+
+// one block per 32 columns; 8 warps stride over rows; deterministic order
+__global__ void __launch_bounds__(256) colsum_kernel(int M, int N, const float* __restrict__ X, int ldx,
+                                                     float* __restrict__ out, int accumulate) {
+  __shared__ float part[8][33];
+  int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+  int n = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (n < N)
+    for (int m = w; m < M; m += 8) s += X[(size_t)m * ldx + n];
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+__global__ void axpy_kernel(long long n, const float* __restrict__ x, float* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
+}  // namespace
+
+int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, int transA, const float* B, int ldb,
+         int transB, float* C, int ldc, const float* bias, int act, int accumulate) {
+  if (M <= 0 || N <= 0) return OP3_OK;
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  if (transA == 0 && transB == 0) gemm_kernel<0, 0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
+  else if (transA == 0 && transB == 1) gemm_kernel<0, 1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
+  else if (transA == 1 && transB == 0) gemm_kernel<1, 0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
+  else gemm_kernel<1, 1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+int act_backward(cudaStream_t st, int M, int N, float* dY, int ldd, const float* Y, int ldy, int act) {
+  if (act == ACT_NONE || M <= 0 || N <= 0) return OP3_OK;
+  long long n = (long long)M * N;
+  act_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(M, N, dY, ldd, Y, ldy, act);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+int colsum(cudaStream_t st, int M, int N, const float* X, int ldx, float* out, int accumulate) {
+  if (N <= 0) return OP3_OK;
+  colsum_kernel<<<ceil_div(N, 32), 256, 0, st>>>(M, N, X, ldx, out, accumulate);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+int axpy(cudaStream_t st, long long n, const float* x, float* y) {
+  if (n <= 0) return OP3_OK;
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, y);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+int fill_zero(cudaStream_t st, void* p, size_t bytes) {
+  if (bytes == 0) return OP3_OK;
+  OP3_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+  return OP3_OK;
+}
+
+}  // namespace op3

@@ -1,0 +1,469 @@
+// Fused per-pixel mask-softmax over K + Gaussian-mixture log-likelihood + KL + refinement-input kernel family.
+// Replaces: F.softmax(mask_logits, dim=1) (op3_model.py:306); _gaussian_prob (:123-126); get_loss (:313-327);
+// kl_divergence_prior_post (:137-145); and in refine (:209-229) posterior_mask, leave_out_ll, the autograd.grad
+// outputs x_hat_grad / mask_grad (closed forms) and the four LayerNorm2D
+// (op3/torch/modules.py:48-69: per-sample mean / UNBIASED std over (C,H,W), (x-mean)/(std+1e-5), per-channel affine).
+//
+// HBM-bound.  One thread owns one pixel of one sample and keeps its K slot float4s in registers (coalesced 16-byte
+// loads, slot-major planes), LN statistics are reduced warp-shuffle -> smem -> per-tile fp64 partials (fixed order,
+// run-to-run deterministic) with sums centred on the value at pixel 0 to avoid cancellation.
+#include "layout.cuh"
+
+namespace op3 {
+
+namespace {
+
+constexpr int MIX_THREADS = 256;
+constexpr int STATS_PPT = 4;  // pixels per thread in the statistics pass
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int KMAX>
+struct Pixel {
+  float4 v[KMAX];   // (r,g,b,logit) per slot
+  float m[KMAX];    // softmax mask
+  float p[KMAX];    // gaussian colour likelihood
+  float x0, x1, x2; // target pixel
+  float P;          // mixture likelihood
+  float sp;         // sum_k p_k
+  float gP;         // d clog / d P = (-1/B)/(P+1e-12)
+
+  __device__ __forceinline__ void load(const float* dec, const float* img, int b, int K, int DD, int pix) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) v[k] = ldg4(dec + ((size_t)(b * K + k) * DD + pix) * 4);
+    if (img) { x0 = __ldg(img + pix); x1 = __ldg(img + DD + pix); x2 = __ldg(img + 2 * DD + pix); }
+    else { x0 = x1 = x2 = 0.f; }
+  }
+  __device__ __forceinline__ void compute(int K, float invB) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) mx = fmaxf(mx, v[k].w);
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) { m[k] = expf(v[k].w - mx); se += m[k]; }
+    P = 0.f; sp = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        m[k] = m[k] / se;
+        float d0 = v[k].x - x0, d1 = v[k].y - x1, d2 = v[k].z - x2;
+        float S = d0 * d0 + d1 * d1 + d2 * d2;
+        p[k] = expf(-S / 0.06f) / 0.24805f;          // op3_model.py:126 (ch*2*sigma^2 = 0.06, sqrt(sigma^6)*248.05)
+        P += m[k] * p[k];
+        sp += p[k];
+      }
+    gP = (-invB) / (P + 1e-12f);
+  }
+  __device__ __forceinline__ float mask_grad(int k) const { return gP * p[k]; }
+  __device__ __forceinline__ float leave_out(int k) const { return P - m[k] * p[k]; }
+  __device__ __forceinline__ float post_mask(int k) const { return p[k] / (sp + 1e-8f); }
+  // x_hat_grad = d clog / d colors = -gP * m * p * (c - x) / 0.03
+  __device__ __forceinline__ float xh_coef(int k) const { return -gP * m[k] * p[k] / 0.03f; }
+};
+
+// stats buffer layout (in floats; the fp64 regions are 8-byte aligned because every count below is even)
+struct StatsLayout {
+  int tiles, nq;
+  size_t shifts;    // [B][3K+1] floats (padded to even)
+  size_t ln;        // [B][K][3][2] + [B][2] floats: (mean, 1/(std+eps))
+  size_t partial;   // [B][tiles][nq] doubles
+  size_t gpart;     // [B*tiles][12] doubles (LN2D parameter-gradient partials of the backward pass)
+  size_t total;
+};
+__host__ __device__ inline StatsLayout stats_layout(int B, int K, int D) {
+  StatsLayout L;
+  L.tiles = (D * D + MIX_THREADS * STATS_PPT - 1) / (MIX_THREADS * STATS_PPT);
+  L.nq = 6 * K + 4;
+  size_t o = 0;
+  L.shifts = o; o += (size_t)B * (3 * K + 1); o = (o + 1) & ~(size_t)1;
+  L.ln = o; o += (size_t)B * K * 6 + (size_t)B * 2; o = (o + 1) & ~(size_t)1;
+  L.partial = o; o += 2 * (size_t)B * L.tiles * L.nq;
+  L.gpart = o; o += 2 * (size_t)B * L.tiles * STATS_PPT * 12;
+  L.total = o;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass A: masks / colours / final_recon outputs + centred LN statistics + loss partials
+// ---------------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(MIX_THREADS)
+mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long mse_bstride, int B, int K, int D,
+                 int want_stats) {
+  const int DD = D * D;
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+  const float invB = 1.f / (float)B;
+  const float* img = io.image ? io.image + (size_t)b * io.image_bstride : nullptr;
+  StatsLayout L = stats_layout(B, K, D);
+  __shared__ float s_shift[3 * 16 + 1];
+  __shared__ float s_red[MIX_THREADS / 32][6 * 16 + 4];
+
+  Pixel<KMAX> px;
+  if (want_stats) {
+    if (tid == 0) {  // centring references: the quantities at pixel 0 of this sample
+      px.load(io.dec_out, img, b, K, DD, 0);
+      px.compute(K, invB);
+      for (int k = 0; k < K; ++k) {
+        s_shift[3 * k] = px.mask_grad(k);
+        s_shift[3 * k + 1] = px.leave_out(k);
+        s_shift[3 * k + 2] = px.xh_coef(k) * (px.v[k].x - px.x0);
+      }
+      s_shift[3 * K] = px.P;
+      if (tile == 0)
+        for (int i = 0; i < 3 * K + 1; ++i) io.stats[L.shifts + (size_t)b * (3 * K + 1) + i] = s_shift[i];
+    }
+    __syncthreads();
+  }
+
+  float acc[6 * KMAX];
+  float accP = 0.f, accP2 = 0.f, accLog = 0.f, accSq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6 * KMAX; ++i) acc[i] = 0.f;
+
+#pragma unroll 1
+  for (int it = 0; it < STATS_PPT; ++it) {
+    int pix = (tile * STATS_PPT + it) * MIX_THREADS + tid;
+    if (pix >= DD) break;
+    px.load(io.dec_out, img, b, K, DD, pix);
+    px.compute(K, invB);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        if (io.mask) io.mask[(size_t)(b * K + k) * DD + pix] = px.m[k];
+        if (io.colors) {
+          float* c = io.colors + (size_t)(b * K + k) * 3 * DD + pix;
+          c[0] = px.v[k].x; c[DD] = px.v[k].y; c[2 * DD] = px.v[k].z;
+        }
+        r0 += px.v[k].x * px.m[k]; r1 += px.v[k].y * px.m[k]; r2 += px.v[k].z * px.m[k];
+        if (want_stats) {
+          float d = px.mask_grad(k) - s_shift[3 * k];
+          acc[6 * k] += d; acc[6 * k + 1] += d * d;
+          d = px.leave_out(k) - s_shift[3 * k + 1];
+          acc[6 * k + 2] += d; acc[6 * k + 3] += d * d;
+          float cf = px.xh_coef(k), sh = s_shift[3 * k + 2];
+          float e0 = cf * (px.v[k].x - px.x0) - sh, e1 = cf * (px.v[k].y - px.x1) - sh, e2 = cf * (px.v[k].z - px.x2) - sh;
+          acc[6 * k + 4] += e0 + e1 + e2; acc[6 * k + 5] += e0 * e0 + e1 * e1 + e2 * e2;
+        }
+      }
+    if (io.final_recon) {
+      float* fr = io.final_recon + (size_t)b * 3 * DD + pix;
+      fr[0] = r0; fr[DD] = r1; fr[2 * DD] = r2;
+    }
+    if (want_stats) {
+      float d = px.P - s_shift[3 * K];
+      accP += d; accP2 += d * d;
+      accLog += -logf(px.P + 1e-12f);
+      if (mse_image) {
+        const float* mi = mse_image + (size_t)b * mse_bstride;
+        float q0 = r0 - __ldg(mi + pix), q1 = r1 - __ldg(mi + DD + pix), q2 = r2 - __ldg(mi + 2 * DD + pix);
+        accSq += q0 * q0 + q1 * q1 + q2 * q2;
+      }
+    }
+  }
+  if (!want_stats) return;
+
+  // warp shuffle -> smem -> fp64 partial per (sample, tile)
+#pragma unroll
+  for (int i = 0; i < 6 * KMAX; ++i)
+    if (i < 6 * K) {
+      float s = warp_sum(acc[i]);
+      if (lane == 0) s_red[warp][i] = s;
+    }
+  {
+    float s0 = warp_sum(accP), s1 = warp_sum(accP2), s2 = warp_sum(accLog), s3 = warp_sum(accSq);
+    if (lane == 0) { s_red[warp][6 * K] = s0; s_red[warp][6 * K + 1] = s1; s_red[warp][6 * K + 2] = s2; s_red[warp][6 * K + 3] = s3; }
+  }
+  __syncthreads();
+  if (tid < L.nq) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < MIX_THREADS / 32; ++w) s += (double)s_red[w][tid];
+    reinterpret_cast<double*>(io.stats + L.partial)[((size_t)b * L.tiles + tile) * L.nq + tid] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// finalize: LN statistics per (b,k,group), loss scalars, KL (single CTA; O(B*K*Rs) work)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_std(float x) { return sqrtf(logf(1.f + expf(fminf(x, 80.f))) + 1e-5f); }
+
+__global__ void __launch_bounds__(256) mix_finalize_kernel(Op3MixtureIO io, int B, int K, int D, int Rs, float beta,
+                                                           int want_mse) {
+  StatsLayout L = stats_layout(B, K, D);
+  const double* part = reinterpret_cast<const double*>(io.stats + L.partial);
+  const int tid = threadIdx.x;
+  const double n1 = (double)D * D;
+  __shared__ double s_red[256];
+  // LN statistics
+  for (int i = tid; i < B * (3 * K + 1); i += 256) {
+    int b = i / (3 * K + 1), q = i % (3 * K + 1);
+    int k = q / 3, g = q % 3;   // for q == 3K: the P group
+    int qi = q == 3 * K ? 6 * K : 6 * k + 2 * g;
+    double s = 0.0, s2 = 0.0;
+    for (int t = 0; t < L.tiles; ++t) {
+      s += part[((size_t)b * L.tiles + t) * L.nq + qi];
+      s2 += part[((size_t)b * L.tiles + t) * L.nq + qi + 1];
+    }
+    double n = (q != 3 * K && g == 2) ? 3.0 * n1 : n1;
+    double mean = (double)io.stats[L.shifts + i] + s / n;
+    double var = (s2 - s * s / n) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    float stdv = (float)sqrt(var);
+    size_t o = q == 3 * K ? L.ln + (size_t)B * K * 6 + (size_t)b * 2 : L.ln + ((size_t)(b * K + k) * 3 + g) * 2;
+    io.stats[o] = (float)mean;
+    io.stats[o + 1] = 1.f / (stdv + 1e-5f);
+  }
+  // clog and squared reconstruction error
+  double cl = 0.0, sq = 0.0;
+  for (int i = tid; i < B * L.tiles; i += 256) {
+    cl += part[(size_t)i * L.nq + 6 * K + 2];
+    sq += part[(size_t)i * L.nq + 6 * K + 3];
+  }
+  // KL(post || prior), diagonal Gaussians
+  double kl = 0.0;
+  for (int i = tid; i < B * K * Rs; i += 256) {
+    float sq_ = softplus_std(io.post_l2[i]), spv = softplus_std(io.prior_l2[i]);
+    float dm = io.post_l1[i] - io.prior_l1[i];
+    kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
+  }
+  double vals[3] = {cl, kl, sq};
+  double outv[3];
+  for (int j = 0; j < 3; ++j) {
+    s_red[tid] = vals[j];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) s_red[tid] += s_red[tid + o];
+      __syncthreads();
+    }
+    outv[j] = s_red[0];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float clog = (float)(outv[0] / B), klv = (float)(outv[1] / B);
+    io.losses[0] = clog;
+    io.losses[1] = klv;
+    io.losses[2] = clog + beta * klv;
+    io.losses[3] = want_mse ? (float)(outv[2] / ((double)B * 3.0 * n1)) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass B: refinement-input chunks (LayerNorm2D applied) + the gradient seed d total / d dec_out
+// ---------------------------------------------------------------------------------------------------------
+struct Ln2dParams { float g[6]; float b[6]; };  // groups: 0 mask_grad, 1 P, 2 leave_out, 3..5 x_hat rgb
+
+template <int KMAX>
+__global__ void __launch_bounds__(MIX_THREADS)
+mix_emit_kernel(Op3MixtureIO io, const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ g2,
+                const float* __restrict__ g3, const float* __restrict__ b0, const float* __restrict__ b1,
+                const float* __restrict__ b2, const float* __restrict__ b3, int B, int K, int D) {
+  const int DD = D * D;
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * MIX_THREADS + threadIdx.x;
+  if (pix >= DD) return;
+  const float invB = 1.f / (float)B;
+  StatsLayout L = stats_layout(B, K, D);
+  const float* img = io.image + (size_t)b * io.image_bstride;
+  Pixel<KMAX> px;
+  px.load(io.dec_out, img, b, K, DD, pix);
+  px.compute(K, invB);
+  const float ga0 = __ldg(g0), be0 = __ldg(b0), ga1 = __ldg(g1), be1 = __ldg(b1), ga2 = __ldg(g2), be2 = __ldg(b2);
+  const float ga3x = __ldg(g3), ga3y = __ldg(g3 + 1), ga3z = __ldg(g3 + 2);
+  const float be3x = __ldg(b3), be3y = __ldg(b3 + 1), be3z = __ldg(b3 + 2);
+  const float gPP = px.gP * px.P;  // sum_j m_j * mask_grad_j
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) {
+      const float* ln = io.stats + L.ln + (size_t)(b * K + k) * 6;
+      size_t o = ((size_t)(b * K + k) * DD + pix);
+      float mg = px.mask_grad(k), lo = px.leave_out(k), cf = px.xh_coef(k);
+      float xh0 = cf * (px.v[k].x - px.x0), xh1 = cf * (px.v[k].y - px.x1), xh2 = cf * (px.v[k].z - px.x2);
+      float4 o1 = make_float4(px.m[k], px.post_mask(k), (mg - ln[0]) * ln[1] * ga0 + be0, (lo - ln[2]) * ln[3] * ga2 + be2);
+      float4 o2 = make_float4((xh0 - ln[4]) * ln[5] * ga3x + be3x, (xh1 - ln[4]) * ln[5] * ga3y + be3y,
+                              (xh2 - ln[4]) * ln[5] * ga3z + be3z, 0.f);
+      reinterpret_cast<float4*>(io.mix1)[o] = o1;
+      reinterpret_cast<float4*>(io.mix2)[o] = o2;
+      if (io.seed) reinterpret_cast<float4*>(io.seed)[o] = make_float4(xh0, xh1, xh2, px.m[k] * (mg - gPP));
+    }
+  const float* lnP = io.stats + L.ln + (size_t)B * K * 6 + (size_t)b * 2;
+  reinterpret_cast<float4*>(io.smp)[(size_t)b * DD + pix] =
+      make_float4(px.x0, px.x1, px.x2, (px.P - lnP[0]) * lnP[1] * ga1 + be1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward w.r.t. dec_out (+ LayerNorm2D gamma/beta gradient partials)
+// ---------------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(MIX_THREADS)
+mix_bwd_kernel(Op3MixtureIO io, float w_clog, const float4* __restrict__ d_in, float4* __restrict__ d_dec,
+               double* __restrict__ gpart, int B, int K, int D) {
+  const int DD = D * D;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+  const int pix = blockIdx.x * MIX_THREADS + tid;
+  const bool live = pix < DD;
+  const float invB = 1.f / (float)B;
+  StatsLayout L = stats_layout(B, K, D);
+  float lg[12];  // dgamma0,dbeta0, dgamma1,dbeta1, dgamma2,dbeta2, dgamma3 rgb, dbeta3 rgb
+#pragma unroll
+  for (int i = 0; i < 12; ++i) lg[i] = 0.f;
+  if (live) {
+    const float* img = io.image + (size_t)b * io.image_bstride;
+    Pixel<KMAX> px;
+    px.load(io.dec_out, img, b, K, DD, pix);
+    px.compute(K, invB);
+    const float Sp = px.sp + 1e-8f;
+    float gm[KMAX], dpm[KMAX];
+    float4 u0[KMAX];
+    float sum_mg = 0.f, sum_dpm_p = 0.f;
+    const float* lnP = io.stats + L.ln + (size_t)B * K * 6 + (size_t)b * 2;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        float4 u1 = make_float4(0.f, 0.f, 0.f, 0.f), u2 = u1, u3 = u1;
+        u0[k] = u1;
+        if (d_in) {
+          size_t base = (size_t)(b * K + k) * 5 * DD + pix;
+          u0[k] = d_in[base]; u1 = d_in[base + DD]; u2 = d_in[base + 2 * (size_t)DD]; u3 = d_in[base + 3 * (size_t)DD];
+          const float* ln = io.stats + L.ln + (size_t)(b * K + k) * 6;
+          float cf = px.xh_coef(k);
+          lg[0] += u1.z * (px.mask_grad(k) - ln[0]) * ln[1]; lg[1] += u1.z;
+          lg[2] += u3.w * (px.P - lnP[0]) * lnP[1];          lg[3] += u3.w;
+          lg[4] += u1.w * (px.leave_out(k) - ln[2]) * ln[3]; lg[5] += u1.w;
+          lg[6] += u2.x * (cf * (px.v[k].x - px.x0) - ln[4]) * ln[5]; lg[9] += u2.x;
+          lg[7] += u2.y * (cf * (px.v[k].y - px.x1) - ln[4]) * ln[5]; lg[10] += u2.y;
+          lg[8] += u2.z * (cf * (px.v[k].z - px.x2) - ln[4]) * ln[5]; lg[11] += u2.z;
+        }
+        gm[k] = u1.x + w_clog * px.mask_grad(k);
+        dpm[k] = u1.y;
+        sum_mg += px.m[k] * gm[k];
+        sum_dpm_p += dpm[k] * px.p[k];
+      }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        float dp = dpm[k] / Sp - sum_dpm_p / (Sp * Sp);        // through posterior_mask = p/(sum p + 1e-8)
+        float cc = w_clog * px.xh_coef(k) - dp * px.p[k] / 0.03f;
+        float4 o;
+        o.x = u0[k].x + cc * (px.v[k].x - px.x0);
+        o.y = u0[k].y + cc * (px.v[k].y - px.x1);
+        o.z = u0[k].z + cc * (px.v[k].z - px.x2);
+        o.w = u0[k].w + px.m[k] * (gm[k] - sum_mg);
+        d_dec[(size_t)(b * K + k) * DD + pix] = o;
+      }
+  }
+  if (d_in && gpart) {
+    __shared__ float s_red[MIX_THREADS / 32][12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      float s = warp_sum(lg[i]);
+      if (lane == 0) s_red[warp][i] = s;
+    }
+    __syncthreads();
+    if (tid < 12) {
+      double s = 0.0;
+      for (int w = 0; w < MIX_THREADS / 32; ++w) s += (double)s_red[w][tid];
+      gpart[((size_t)b * gridDim.x + blockIdx.x) * 12 + tid] = s;
+    }
+  }
+}
+
+__global__ void mix_bwd_reduce_kernel(const double* __restrict__ gpart, int nblocks, Op3Params grads) {
+  int i = threadIdx.x;
+  if (i >= 12) return;
+  double s = 0.0;
+  for (int k = 0; k < nblocks; ++k) s += gpart[(size_t)k * 12 + i];
+  float v = (float)s;
+  switch (i) {
+    case 0: grads.ln2d_gamma[0][0] += v; break;
+    case 1: grads.ln2d_beta[0][0] += v; break;
+    case 2: grads.ln2d_gamma[1][0] += v; break;
+    case 3: grads.ln2d_beta[1][0] += v; break;
+    case 4: grads.ln2d_gamma[2][0] += v; break;
+    case 5: grads.ln2d_beta[2][0] += v; break;
+    case 6: case 7: case 8: grads.ln2d_gamma[3][i - 6] += v; break;
+    default: grads.ln2d_beta[3][i - 9] += v; break;
+  }
+}
+
+}  // namespace
+}  // namespace op3
+
+using namespace op3;
+
+extern "C" size_t op3_mixture_stats_floats(const Op3Dims* d) {
+  if (validate_dims(d) != OP3_OK) return 0;
+  return stats_layout(d->B, d->K, d->D).total;
+}
+
+extern "C" size_t op3_mixture_bwd_scratch_floats(const Op3Dims* d) { (void)d; return 0; }
+
+// `want_loss`: bit 0 = compute LN statistics + losses (needed for loss and/or refine inputs); bit 1 = losses[3] is the
+// reconstruction mse against io->mse_image.
+extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3MixtureIO* io, int want_loss, void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(io && io->dec_out, "op3_mixture_fwd: NULL io");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->B, K = d->K, D = d->D;
+  const bool emit = io->mix1 != nullptr;
+  const int want_stats = (want_loss & 1) || emit;
+  if (want_stats)
+    OP3_REQUIRE(io->image && io->stats && io->losses && io->post_l1 && io->post_l2 && io->prior_l1 && io->prior_l2,
+                "op3_mixture_fwd: statistics requested but image/stats/losses/lambda pointers missing");
+  if (emit) OP3_REQUIRE(p && io->mix2 && io->smp, "op3_mixture_fwd: refine inputs requested but mix2/smp/params missing");
+  StatsLayout L = stats_layout(B, K, D);
+  dim3 gs(L.tiles, B);
+#define OP3_MIX_STATS(KM) mix_stats_kernel<KM><<<gs, MIX_THREADS, 0, st>>>(*io, io->mse_image, io->mse_image_bstride, B, K, D, want_stats)
+  if (K <= 4) OP3_MIX_STATS(4); else if (K <= 8) OP3_MIX_STATS(8); else OP3_MIX_STATS(16);
+#undef OP3_MIX_STATS
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  if (!want_stats) return OP3_OK;
+  mix_finalize_kernel<<<1, 256, 0, st>>>(*io, B, K, D, d->Rs, d->beta, io->mse_image != nullptr);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  if (emit) {
+    dim3 ge(ceil_div(D * D, MIX_THREADS), B);
+#define OP3_MIX_EMIT(KM)                                                                                         \
+  mix_emit_kernel<KM><<<ge, MIX_THREADS, 0, st>>>(*io, p->ln2d_gamma[0], p->ln2d_gamma[1], p->ln2d_gamma[2],    \
+                                                  p->ln2d_gamma[3], p->ln2d_beta[0], p->ln2d_beta[1],           \
+                                                  p->ln2d_beta[2], p->ln2d_beta[3], B, K, D)
+    if (K <= 4) OP3_MIX_EMIT(4); else if (K <= 8) OP3_MIX_EMIT(8); else OP3_MIX_EMIT(16);
+#undef OP3_MIX_EMIT
+    OP3_COUNT_LAUNCH();
+    OP3_LAUNCH_CHECK();
+  }
+  return OP3_OK;
+}
+
+extern "C" int op3_mixture_bwd(const Op3Dims* d, const Op3MixtureIO* io, float w_clog, const float* d_in,
+                               float* d_dec_out, const Op3Params* grads, float* scratch, void* stream) {
+  (void)scratch;
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(io && io->dec_out && io->image && io->stats && d_dec_out, "op3_mixture_bwd: NULL argument");
+  OP3_REQUIRE(!d_in || grads, "op3_mixture_bwd: grads required when d_in is given");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->B, K = d->K, D = d->D;
+  StatsLayout L = stats_layout(B, K, D);
+  dim3 g(ceil_div(D * D, MIX_THREADS), B);
+  OP3_REQUIRE((size_t)g.x * B * 12 <= (size_t)B * L.tiles * STATS_PPT * 12, "op3_mixture_bwd: partial buffer too small");
+  double* gpart = reinterpret_cast<double*>(io->stats + L.gpart);
+#define OP3_MIX_BWD(KM)                                                                                  \
+  mix_bwd_kernel<KM><<<g, MIX_THREADS, 0, st>>>(*io, w_clog, reinterpret_cast<const float4*>(d_in),       \
+                                                reinterpret_cast<float4*>(d_dec_out), gpart, B, K, D)
+  if (K <= 4) OP3_MIX_BWD(4); else if (K <= 8) OP3_MIX_BWD(8); else OP3_MIX_BWD(16);
+#undef OP3_MIX_BWD
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  if (d_in) {
+    mix_bwd_reduce_kernel<<<1, 32, 0, st>>>(gpart, (int)(g.x * B), *grads);
+    OP3_COUNT_LAUNCH();
+    OP3_LAUNCH_CHECK();
+  }
+  return OP3_OK;
+}

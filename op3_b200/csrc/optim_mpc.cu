@@ -1,0 +1,164 @@
+// Trainer-step and MPC helper kernels.
+//  * op3_adam_clip replaces torch.nn.utils.clip_grad_norm_(params, 5.0) + optim.Adam.step (op3/torch/op3_modules/
+//    op3_trainer.py:136,188-189) with one pass over flat parameter / gradient / moment buffers.
+//  * op3_mpc_cost replaces Cost.image_mse + min over K (exps/stack_exps/mpc_stack.py:103-127,160-184,225-228).
+#include "common.cuh"
+
+namespace op3 {
+namespace {
+
+constexpr int NORM_BLOCKS = 512;
+
+__global__ void __launch_bounds__(256) sqnorm_kernel(long long n, const float* __restrict__ g, float scale,
+                                                     double* __restrict__ partial) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float v = g[i] * scale;
+    s += (double)v * (double)v;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, float scale, float lr,
+                                                   float b1, float b2, float eps, float bc1, float bc2_sqrt, float max_norm,
+                                                   const double* __restrict__ partial, int nparts, float* __restrict__ norm_out) {
+  __shared__ float s_coef;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += partial[i];
+    float total = (float)sqrt(t);
+    float coef = max_norm / (total + 1e-6f);
+    s_coef = coef < 1.f ? coef : 1.f;
+    if (blockIdx.x == 0) norm_out[0] = total;
+  }
+  __syncthreads();
+  const float coef = s_coef * scale;
+  const float step = lr / bc1;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float gi = g[i] * coef;
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);          // torch: exp_avg.lerp_(grad, 1 - beta1)
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step * (mi / denom);
+  }
+}
+
+// sums[(a*Kp+k)*G + g] = sum over (3,D,D) of (goal_g - pred_{a,k})^2 ; one CTA per (a,k); fixed-order reduction
+template <int GMAX>
+__global__ void __launch_bounds__(256) mpc_sqerr_kernel(int G, int n_el, const float* __restrict__ pred,
+                                                        const float* __restrict__ goal, double* __restrict__ sums) {
+  __shared__ double red[256];
+  const float* pp = pred + (size_t)blockIdx.x * n_el;
+  float acc[GMAX];
+#pragma unroll
+  for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
+  for (int i = threadIdx.x; i < n_el; i += 256) {
+    float pv = pp[i];
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g)
+      if (g < G) {
+        float dlt = __ldg(goal + (size_t)g * n_el + i) - pv;
+        acc[g] = fmaf(dlt, dlt, acc[g]);
+      }
+  }
+  for (int g = 0; g < G; ++g) {
+    double mine = 0.0;
+#pragma unroll
+    for (int q = 0; q < GMAX; ++q)
+      if (q == g) mine = (double)acc[q];
+    red[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[(size_t)blockIdx.x * G + g] = red[0];
+    __syncthreads();
+  }
+}
+
+__global__ void mpc_min_kernel(int Na, int Kp, int G, int n_el, const double* __restrict__ sums, float* __restrict__ cost,
+                               int* __restrict__ argk) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Na * G) return;
+  int a = i % Na, g = i / Na;
+  float best = 0.f;
+  int bk = 0;
+  for (int k = 0; k < Kp; ++k) {
+    float c = (float)(sums[((size_t)a * Kp + k) * G + g] / (double)n_el);
+    if (k == 0 || c < best) { best = c; bk = k; }   // ties -> lowest k, like torch.min
+  }
+  cost[(size_t)g * Na + a] = best;
+  if (argk) argk[(size_t)g * Na + a] = bk;
+}
+
+__global__ void sub_images_kernel(long long n_slots, int DD, const float* __restrict__ colors, const float* __restrict__ mask,
+                                  float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots * 3 * DD) return;
+  long long s = i / (3LL * DD);
+  int pix = (int)(i % DD);
+  out[i] = colors[i] * mask[s * DD + pix];
+}
+
+}  // namespace
+}  // namespace op3
+
+using namespace op3;
+
+extern "C" int op3_adam_clip(long long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step,
+                             float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                             float* scratch, void* stream) {
+  OP3_REQUIRE(n > 0 && params && grads && exp_avg && exp_avg_sq && scratch && step >= 1, "op3_adam_clip: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partial = reinterpret_cast<double*>(scratch + 2);  // scratch[0] = norm; doubles 8-byte aligned at +2 floats
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > NORM_BLOCKS) blocks = NORM_BLOCKS;
+  sqnorm_kernel<<<blocks, 256, 0, st>>>(n, grads, grad_scale, partial);
+  OP3_COUNT_LAUNCH();
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  int ab = (int)((n + 255) / 256);
+  if (ab > 1184) ab = 1184;
+  adam_kernel<<<ab, 256, 0, st>>>(n, params, grads, exp_avg, exp_avg_sq, grad_scale, lr, beta1, beta2, eps, bc1, bc2s,
+                                  max_norm, partial, blocks, scratch);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+extern "C" int op3_mpc_cost(int Na, int Kp, int G, int D, const float* pred, const float* goal, float* cost, int* argk,
+                            void* stream) {
+  OP3_REQUIRE(Na > 0 && Kp > 0 && G > 0 && G <= 16 && D > 0 && pred && goal && cost, "op3_mpc_cost: bad argument (G<=16)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_el = 3 * D * D;
+  double* sums = nullptr;
+  OP3_CHECK(cudaMallocAsync((void**)&sums, (size_t)Na * Kp * G * sizeof(double), st));  // stream-ordered temp, freed below
+  if (G <= 4) mpc_sqerr_kernel<4><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
+  else mpc_sqerr_kernel<16><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
+  OP3_COUNT_LAUNCH();
+  mpc_min_kernel<<<ceil_div(Na * G, 256), 256, 0, st>>>(Na, Kp, G, n_el, sums, cost, argk);
+  OP3_COUNT_LAUNCH();
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(sums, st);
+  OP3_CHECK(e);
+  return OP3_OK;
+}
+
+extern "C" int op3_sub_images(long long n_slots, int D, const float* colors, const float* mask, float* out, void* stream) {
+  OP3_REQUIRE(n_slots > 0 && D > 0 && colors && mask && out, "op3_sub_images: bad argument");
+  long long tot = n_slots * 3 * D * D;
+  sub_images_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_slots, D * D, colors, mask, out);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}

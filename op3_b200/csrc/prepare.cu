@@ -1,0 +1,200 @@
+// Derived weights (op3_prepare) and folding of their gradients back to PyTorch layouts (op3_finalize_grads).
+//
+// Decoder layer 1 (conv_networks.py:326-335 feeds a spatially CONSTANT latent plus two coordinate planes into a
+// 5x5/pad-2 conv) collapses to:  pre1[n,co,y,x] = b[co] + sum_c z[n,c]*Wsum[cls(y,x)][co][c] + cmap[co][y][x]
+// where the valid-tap set only depends on one of 25 border classes (hard part 2).
+#include "layout.cuh"
+
+namespace op3 {
+
+namespace {
+
+__host__ __device__ inline bool tap_valid(int cls_1d, int k) {
+  int lo = 2 - cls_1d; if (lo < 0) lo = 0;
+  int hi = 6 - cls_1d; if (hi > 4) hi = 4;
+  return k >= lo && k <= hi;
+}
+
+__device__ __forceinline__ double lin_coord(int i, int D) {  // np.linspace(-1, 1, D)[i]
+  if (i == D - 1) return 1.0;
+  return -1.0 + (double)i * (2.0 / (double)(D - 1));
+}
+
+// W [cout][cin][5][5] -> wf [25][cin_pad][cout] and wd [25][cout][cin_pad] (flipped taps), mode 1 = refinement L1 perm
+__global__ void prep_conv_kernel(const float* __restrict__ W, int cout, int cin, int cin_pad, int mode,
+                                 float* __restrict__ wf, float* __restrict__ wd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int tot = 25 * cin_pad * cout;
+  if (i >= tot) return;
+  int co = i % cout, cip = (i / cout) % cin_pad, tap = i / (cout * cin_pad);
+  int ci = mode == 1 ? ref_l1_channel(cip) : cip;
+  float v = (ci >= 0 && ci < cin) ? W[((size_t)co * cin + ci) * 25 + tap] : 0.f;
+  wf[i] = v;
+  wd[((size_t)(24 - tap) * cout + co) * cin_pad + cip] = v;
+}
+
+__global__ void prep_wsum_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int R,
+                                 float* __restrict__ wsum, float* __restrict__ biasT) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int tot = NCLS * 32 * R;
+  if (i < NCLS * 32) biasT[i] = b1[i % 32];
+  if (i >= tot) return;
+  int c = i % R, co = (i / R) % 32, cls = i / (R * 32);
+  int cy = cls / 5, cx = cls % 5;
+  const float* w = W1 + ((size_t)co * (R + 2) + c) * 25;
+  float s = 0.f;
+  for (int ky = 0; ky < 5; ++ky)
+    for (int kx = 0; kx < 5; ++kx)
+      if (tap_valid(cy, ky) && tap_valid(cx, kx)) s += w[ky * 5 + kx];
+  wsum[i] = s;
+}
+
+__global__ void prep_cmap_kernel(const float* __restrict__ W1, int R, int D, float* __restrict__ cmap,
+                                 float* __restrict__ coords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D * D) {
+    int y = i / D, x = i % D;
+    reinterpret_cast<float4*>(coords)[i] = make_float4((float)lin_coord(x, D), (float)lin_coord(y, D), 0.f, 0.f);
+  }
+  if (i >= 32 * D * D) return;
+  int x = i % D, y = (i / D) % D, co = i / (D * D);
+  const float* wx = W1 + ((size_t)co * (R + 2) + R) * 25;
+  const float* wy = wx + 25;
+  float s = 0.f;
+  for (int ky = 0; ky < 5; ++ky) {
+    int yy = y + ky - 2;
+    if (yy < 0 || yy >= D) continue;
+    float cyv = (float)lin_coord(yy, D);
+    for (int kx = 0; kx < 5; ++kx) {
+      int xx = x + kx - 2;
+      if (xx < 0 || xx >= D) continue;
+      s = fmaf(wx[ky * 5 + kx], (float)lin_coord(xx, D), s);
+      s = fmaf(wy[ky * 5 + kx], cyv, s);
+    }
+  }
+  cmap[(((size_t)(co / 4) * D + y) * D + x) * 4 + (co % 4)] = s;
+}
+
+// ---- gradient folding ------------------------------------------------------------------------------------
+__global__ void fin_conv_kernel(const float* __restrict__ dwf, const float* __restrict__ dbf, int cout, int cin,
+                                int cin_pad, int mode, float* __restrict__ dW, float* __restrict__ db) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cout && db) db[i] += dbf[i];
+  int tot = 25 * cin_pad * cout;
+  if (i >= tot) return;
+  int co = i % cout, cip = (i / cout) % cin_pad, tap = i / (cout * cin_pad);
+  int ci = mode == 1 ? ref_l1_channel(cip) : cip;
+  if (ci >= 0 && ci < cin) dW[((size_t)co * cin + ci) * 25 + tap] += dwf[i];
+}
+
+__global__ void fin_wsum_kernel(const float* __restrict__ dwsum, const float* __restrict__ dbT, int R,
+                                float* __restrict__ dW1, float* __restrict__ db1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 32) {
+    float s = 0.f;
+    for (int cls = 0; cls < NCLS; ++cls) s += dbT[cls * 32 + i];
+    db1[i] += s;
+  }
+  int tot = 32 * R * 25;
+  if (i >= tot) return;
+  int tap = i % 25, c = (i / 25) % R, co = i / (25 * R);
+  int ky = tap / 5, kx = tap % 5;
+  float s = 0.f;
+  for (int cls = 0; cls < NCLS; ++cls)
+    if (tap_valid(cls / 5, ky) && tap_valid(cls % 5, kx)) s += dwsum[((size_t)cls * 32 + co) * R + c];
+  dW1[((size_t)co * (R + 2) + c) * 25 + tap] += s;
+}
+
+// one block per (co, coord channel, tap): deterministic tree reduction over D*D pixels
+__global__ void __launch_bounds__(256) fin_cmap_kernel(const float* __restrict__ dcmap, int R, int D,
+                                                       float* __restrict__ dW1) {
+  __shared__ float red[256];
+  int b = blockIdx.x;
+  int tap = b % 25, cc = (b / 25) % 2, co = b / 50;
+  int ky = tap / 5, kx = tap % 5;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < D * D; p += 256) {
+    int y = p / D, x = p % D;
+    int yy = y + ky - 2, xx = x + kx - 2;
+    if (yy < 0 || yy >= D || xx < 0 || xx >= D) continue;
+    float cv = cc == 0 ? (float)lin_coord(xx, D) : (float)lin_coord(yy, D);
+    s = fmaf(dcmap[(((size_t)(co / 4) * D + y) * D + x) * 4 + (co % 4)], cv, s);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dW1[((size_t)co * (R + 2) + R + cc) * 25 + tap] += red[0];
+}
+
+}  // namespace
+}  // namespace op3
+
+using namespace op3;
+
+extern "C" size_t op3_prepared_floats(const Op3Dims* d) {
+  if (validate_dims(d) != OP3_OK) return 0;
+  return prep_layout(d).total;
+}
+
+extern "C" int op3_prepare(const Op3Dims* d, const Op3Params* p, float* prep, void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(p && prep, "op3_prepare: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PrepLayout L = prep_layout(d);
+  const int R = d->Rd + d->Rs, D = d->D;
+  prep_wsum_kernel<<<ceil_div(NCLS * 32 * R, 256), 256, 0, st>>>(p->dec_conv_w[0], p->dec_conv_b[0], R, prep + L.wsum,
+                                                                prep + L.biasT);
+  OP3_COUNT_LAUNCH();
+  prep_cmap_kernel<<<ceil_div(32 * D * D, 256), 256, 0, st>>>(p->dec_conv_w[0], R, D, prep + L.cmap, prep + L.coords);
+  OP3_COUNT_LAUNCH();
+  const int dec_cout[4] = {32, 32, 32, 4};
+  for (int i = 0; i < 4; ++i) {
+    prep_conv_kernel<<<ceil_div(25 * 32 * dec_cout[i], 256), 256, 0, st>>>(p->dec_conv_w[i + 1], dec_cout[i], 32, 32, 0,
+                                                                           prep + L.dec_wf[i], prep + L.dec_wd[i]);
+    OP3_COUNT_LAUNCH();
+    OP3_CHECK(cudaMemcpyAsync(prep + L.dec_bf[i], p->dec_conv_b[i + 1], dec_cout[i] * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+  }
+  const int ref_cin[3] = {17, 32, 32}, ref_pad[3] = {REF_CIN_PAD, 32, 32}, ref_cout[3] = {32, 32, d->Rs};
+  for (int i = 0; i < 3; ++i) {
+    prep_conv_kernel<<<ceil_div(25 * ref_pad[i] * ref_cout[i], 256), 256, 0, st>>>(
+        p->ref_conv_w[i], ref_cout[i], ref_cin[i], ref_pad[i], i == 0 ? 1 : 0, prep + L.ref_wf[i], prep + L.ref_wd[i]);
+    OP3_COUNT_LAUNCH();
+    OP3_CHECK(cudaMemcpyAsync(prep + L.ref_bf[i], p->ref_conv_b[i], ref_cout[i] * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+  }
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+extern "C" int op3_finalize_grads(const Op3Dims* d, const float* pg, const Op3Params* g, void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(pg && g, "op3_finalize_grads: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PrepLayout L = prep_layout(d);
+  const int R = d->Rd + d->Rs, D = d->D;
+  fin_wsum_kernel<<<ceil_div(32 * R * 25, 256), 256, 0, st>>>(pg + L.wsum, pg + L.biasT, R, g->dec_conv_w[0],
+                                                             g->dec_conv_b[0]);
+  OP3_COUNT_LAUNCH();
+  fin_cmap_kernel<<<32 * 2 * 25, 256, 0, st>>>(pg + L.cmap, R, D, g->dec_conv_w[0]);
+  OP3_COUNT_LAUNCH();
+  const int dec_cout[4] = {32, 32, 32, 4};
+  for (int i = 0; i < 4; ++i) {
+    fin_conv_kernel<<<ceil_div(25 * 32 * dec_cout[i], 256), 256, 0, st>>>(pg + L.dec_wf[i], pg + L.dec_bf[i], dec_cout[i],
+                                                                          32, 32, 0, g->dec_conv_w[i + 1],
+                                                                          g->dec_conv_b[i + 1]);
+    OP3_COUNT_LAUNCH();
+  }
+  const int ref_cin[3] = {17, 32, 32}, ref_pad[3] = {REF_CIN_PAD, 32, 32}, ref_cout[3] = {32, 32, d->Rs};
+  for (int i = 0; i < 3; ++i) {
+    fin_conv_kernel<<<ceil_div(25 * ref_pad[i] * ref_cout[i], 256), 256, 0, st>>>(
+        pg + L.ref_wf[i], pg + L.ref_bf[i], ref_cout[i], ref_cin[i], ref_pad[i], i == 0 ? 1 : 0, g->ref_conv_w[i],
+        g->ref_conv_b[i]);
+    OP3_COUNT_LAUNCH();
+  }
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}

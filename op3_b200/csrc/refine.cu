@@ -1,0 +1,402 @@
+// Refinement network + latent-state helpers.
+// Replaces RefinementNetwork.forward (op3/torch/op3_modules/refinement_network.py:189-219: conv x3 + ELU, AvgPool2d(D),
+// FC+ELU, LSTM cell, two linear heads), the LayerNorm of the lambda gradients and extra_input assembly of
+// OP3Model.refine (op3_model.py:232-249), get_samples / _softplus_to_std (:130-153) and their backward.
+#include "layout.cuh"
+
+namespace op3 {
+
+namespace {
+
+constexpr int LSTM = OP3_LSTM, HID = OP3_HID;
+
+__device__ __forceinline__ float sp_std(float x) { return sqrtf(logf(1.f + expf(fminf(x, 80.f))) + 1e-5f); }
+// d std / d x for std = sqrt(softplus(min(x,80)) + 1e-5)
+__device__ __forceinline__ float sp_std_grad(float x, float stdv) { return x < 80.f ? sigmoid_f(x) / (2.f * stdv) : 0.f; }
+
+__global__ void sample_kernel(int N, int R, int Rd, int Rs, const float* __restrict__ l1, const float* __restrict__ l2,
+                              const float* __restrict__ eps, const float* __restrict__ deter_src, float* __restrict__ z) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (deter_src && i < N * Rd) z[(size_t)(i / Rd) * R + (i % Rd)] = deter_src[(size_t)(i / Rd) * R + (i % Rd)];
+  if (i >= N * Rs) return;
+  int n = i / Rs, j = i % Rs;
+  z[(size_t)n * R + Rd + j] = eps[i] * sp_std(l2[i]) + l1[i];
+}
+
+// see op3_state_bwd in op3_b200.h (no __restrict__: dprior may alias dl when the prior IS the posterior)
+__global__ void state_bwd_kernel(int N, int R, int Rd, int Rs, const float* l1, const float* l2, const float* eps,
+                                 const float* prior1, const float* prior2, const float* dz, float w_kl, float* dl1,
+                                 float* dl2, float* dprior1, float* dprior2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Rs) return;
+  int n = i / Rs, j = i % Rs;
+  float s2 = sp_std(l2[i]);
+  float ds2 = sp_std_grad(l2[i], s2);
+  float dsmp = dz ? dz[(size_t)n * R + Rd + j] : 0.f;
+  float g1 = dsmp, g2 = dsmp * eps[i] * ds2;
+  if (w_kl != 0.f) {
+    float p2 = prior2[i];
+    float s1 = sp_std(p2);
+    float dm = l1[i] - prior1[i];
+    float inv1 = 1.f / (s1 * s1);
+    g1 += w_kl * dm * inv1;
+    g2 += w_kl * (-1.f / s2 + s2 * inv1) * ds2;
+    if (dprior1) {
+      float a = dprior1[i] + w_kl * (-dm * inv1);
+      dprior1[i] = a;
+      float b = dprior2[i] + w_kl * (1.f / s1 - (s2 * s2 + dm * dm) * inv1 / s1) * sp_std_grad(p2, s1);
+      dprior2[i] = b;
+    }
+  }
+  dl1[i] += g1;
+  dl2[i] += g2;
+}
+
+// One warp per slot row.  Builds columns [128, 448) of the LSTM input X: LN(g_l1) | LN(g_l2) | l1 | l2 | samples
+// (op3_model.py:232-248) where g_l = d total / d lambda (decoder path through samples + beta/B * dKL).
+__global__ void __launch_bounds__(128) refine_extras_kernel(int N, int R, int Rd, int Rs, Op3RefineIO io, float w_kl,
+                                                            const float* __restrict__ sc1, const float* __restrict__ ce1,
+                                                            const float* __restrict__ sc2, const float* __restrict__ ce2,
+                                                            float* __restrict__ X, int ldx, float* __restrict__ xn) {
+  const int lane = threadIdx.x % 32;
+  const int n = blockIdx.x * 4 + threadIdx.x / 32;
+  if (n >= N) return;
+  float g1[2], g2[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    int j = lane + 32 * t;
+    size_t i = (size_t)n * Rs + j;
+    float l2v = io.l2[i], l1v = io.l1[i];
+    float s2 = sp_std(l2v), ds2 = sp_std_grad(l2v, s2);
+    float dsmp = io.dz[(size_t)n * R + Rd + j];
+    float a = dsmp, b = dsmp * io.eps[i] * ds2;
+    if (!io.prior_is_post && w_kl != 0.f) {
+      float s1 = sp_std(io.prior2[i]);
+      float dm = l1v - io.prior1[i];
+      a += w_kl * dm / (s1 * s1);
+      b += w_kl * (-1.f / s2 + s2 / (s1 * s1)) * ds2;
+    }
+    g1[t] = a; g2[t] = b;
+    X[(size_t)n * ldx + HID + 2 * Rs + j] = l1v;
+    X[(size_t)n * ldx + HID + 3 * Rs + j] = l2v;
+    X[(size_t)n * ldx + HID + 4 * Rs + j] = io.z[(size_t)n * R + Rd + j];
+  }
+  // LayerNorm over Rs=64 (modules.py:19-46): mean, unbiased std, (x-mean)/(std+1e-6)*scale+center
+  float m1 = warp_sum(g1[0] + g1[1]) / 64.f, m2 = warp_sum(g2[0] + g2[1]) / 64.f;
+  float v1 = warp_sum((g1[0] - m1) * (g1[0] - m1) + (g1[1] - m1) * (g1[1] - m1)) / 63.f;
+  float v2 = warp_sum((g2[0] - m2) * (g2[0] - m2) + (g2[1] - m2) * (g2[1] - m2)) / 63.f;
+  float i1 = 1.f / (sqrtf(v1) + 1e-6f), i2 = 1.f / (sqrtf(v2) + 1e-6f);
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    int j = lane + 32 * t;
+    float a = (g1[t] - m1) * i1, b = (g2[t] - m2) * i2;
+    xn[(size_t)n * 2 * Rs + j] = a;
+    xn[(size_t)n * 2 * Rs + Rs + j] = b;
+    X[(size_t)n * ldx + HID + j] = a * sc1[j] + ce1[j];
+    X[(size_t)n * ldx + HID + Rs + j] = b * sc2[j] + ce2[j];
+  }
+}
+
+// pooled[n][co] = mean_{y,x} r3[n][co/4][y][x][co%4]; one CTA per (chunk, n); fixed-order tree
+__global__ void __launch_bounds__(256) avgpool_kernel(const float4* __restrict__ r3, int chunks, int DD,
+                                                      float* __restrict__ pooled) {
+  __shared__ float4 red[256];
+  const int c4 = blockIdx.x, n = blockIdx.y;
+  const float4* src = r3 + ((size_t)n * chunks + c4) * DD;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = threadIdx.x; p < DD; p += 256) {
+    float4 v = src[p];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      float4 a = red[threadIdx.x], b = red[threadIdx.x + o];
+      red[threadIdx.x] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float inv = 1.f / (float)DD;
+    float4 a = red[0];
+    *reinterpret_cast<float4*>(pooled + (size_t)n * chunks * 4 + c4 * 4) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+}
+
+// g3[n][c4][p] = dpooled[n][c4*4..] / DD * ELU'(r3)
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dpooled, const float4* __restrict__ r3,
+                                                          int chunks, int DD, float4* __restrict__ g3) {
+  const int n = blockIdx.y;
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= chunks * DD) return;
+  int c4 = i / DD;
+  float inv = 1.f / (float)DD;
+  float4 d = *reinterpret_cast<const float4*>(dpooled + (size_t)n * chunks * 4 + c4 * 4);
+  float4 a = r3[(size_t)n * chunks * DD + i];
+  g3[(size_t)n * chunks * DD + i] = make_float4(d.x * inv * elu_grad_from_out(a.x), d.y * inv * elu_grad_from_out(a.y),
+                                                d.z * inv * elu_grad_from_out(a.z), d.w * inv * elu_grad_from_out(a.w));
+}
+
+__global__ void lstm_fwd_kernel(int N, const float* __restrict__ gates, const float* __restrict__ c, float* __restrict__ h2,
+                                float* __restrict__ c2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * LSTM) return;
+  int n = i / LSTM, j = i % LSTM;
+  const float* g = gates + (size_t)n * 4 * LSTM;
+  float gi = sigmoid_f(g[j]), gf = sigmoid_f(g[LSTM + j]), gg = tanhf(g[2 * LSTM + j]), go = sigmoid_f(g[3 * LSTM + j]);
+  float cn = gf * c[i] + gi * gg;
+  c2[i] = cn;
+  h2[i] = go * tanhf(cn);
+}
+
+// dgates from (dh2, dc2); also dc_prev (+=)
+__global__ void lstm_bwd_kernel(int N, const float* __restrict__ gates, const float* __restrict__ c,
+                                const float* __restrict__ dh2, const float* __restrict__ dc2, float* __restrict__ dgates,
+                                float* __restrict__ dc_prev) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * LSTM) return;
+  int n = i / LSTM, j = i % LSTM;
+  const float* g = gates + (size_t)n * 4 * LSTM;
+  float gi = sigmoid_f(g[j]), gf = sigmoid_f(g[LSTM + j]), gg = tanhf(g[2 * LSTM + j]), go = sigmoid_f(g[3 * LSTM + j]);
+  float cp = c[i];
+  float cn = gf * cp + gi * gg;
+  float tc = tanhf(cn);
+  float dh = dh2 ? dh2[i] : 0.f;
+  float dcn = (dc2 ? dc2[i] : 0.f) + dh * go * (1.f - tc * tc);
+  float* dg = dgates + (size_t)n * 4 * LSTM;
+  dg[j] = dcn * gg * gi * (1.f - gi);
+  dg[LSTM + j] = dcn * cp * gf * (1.f - gf);
+  dg[2 * LSTM + j] = dcn * gi * (1.f - gg * gg);
+  dg[3 * LSTM + j] = dh * tc * go * (1.f - go);
+  if (dc_prev) dc_prev[i] += dcn * gf;
+}
+
+// out[n] += sum_m X[m][n] * Y[m][n]   (Y == nullptr -> plain column sum); deterministic
+__global__ void __launch_bounds__(256) colsum_prod_kernel(int M, int N, const float* __restrict__ X, int ldx,
+                                                          const float* __restrict__ Y, int ldy, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+  int n = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (n < N)
+    for (int m = w; m < M; m += 8) s += X[(size_t)m * ldx + n] * (Y ? Y[(size_t)m * ldy + n] : 1.f);
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    out[n] += t;
+  }
+}
+
+// dst[m][0..n) (+)= src[m][0..n)  with row strides
+__global__ void add_cols_kernel(int M, int N, const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  int m = i / N, n = i % N;
+  dst[(size_t)m * ldd + n] += src[(size_t)m * lds + n];
+}
+
+struct RefActs {
+  float4 *r1, *r2, *r3;
+  float *pooled, *X, *gates, *xn;
+};
+inline RefActs ref_acts(const Op3Dims* d, float* base) {
+  RefActs A;
+  const size_t N = (size_t)d->B * d->K, DD = (size_t)d->D * d->D;
+  size_t o = 0;
+  A.r1 = reinterpret_cast<float4*>(base + o); o += N * 32 * DD;
+  A.r2 = reinterpret_cast<float4*>(base + o); o += N * 32 * DD;
+  A.r3 = reinterpret_cast<float4*>(base + o); o += N * d->Rs * DD;
+  A.pooled = base + o; o += N * d->Rs;
+  A.X = base + o; o += N * (HID + 5 * d->Rs);
+  A.gates = base + o; o += N * 4 * LSTM;
+  A.xn = base + o; o += N * 2 * d->Rs;
+  return A;
+}
+inline size_t ref_acts_floats(const Op3Dims* d) {
+  const size_t N = (size_t)d->B * d->K, DD = (size_t)d->D * d->D;
+  return N * (64 + d->Rs) * DD + N * (d->Rs + HID + 5 * d->Rs + 4 * LSTM + 2 * d->Rs);
+}
+
+inline ConvInput refine_l1_input(const Op3Dims* d, const Op3RefineIO* io, const float* prep, const PrepLayout& L) {
+  ConvInput in{};
+  in.src[0] = {reinterpret_cast<const float4*>(io->dec_out), 1, 1};
+  in.src[1] = {reinterpret_cast<const float4*>(io->mix1), 1, 1};
+  in.src[2] = {reinterpret_cast<const float4*>(io->mix2), 1, 1};
+  in.src[3] = {reinterpret_cast<const float4*>(io->smp), 1, d->K};
+  in.src[4] = {reinterpret_cast<const float4*>(prep + L.coords), 1, 0};
+  in.nsrc = 5; in.total_chunks = 5;
+  return in;
+}
+inline ConvInput one_src(const float4* p, int chunks) {
+  ConvInput in{};
+  in.src[0] = {p, chunks, 1};
+  in.nsrc = 1; in.total_chunks = chunks;
+  return in;
+}
+
+}  // namespace
+}  // namespace op3
+
+using namespace op3;
+
+extern "C" int op3_sample_fwd(const Op3Dims* d, int N, const float* l1, const float* l2, const float* eps,
+                              const float* deter_src, float* z, void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(l1 && l2 && eps && z && N > 0, "op3_sample_fwd: bad argument");
+  int tot = N * (d->Rs > d->Rd ? d->Rs : d->Rd);
+  sample_kernel<<<ceil_div(tot, 256), 256, 0, (cudaStream_t)stream>>>(N, d->Rd + d->Rs, d->Rd, d->Rs, l1, l2, eps, deter_src, z);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+extern "C" int op3_state_bwd(const Op3Dims* d, int N, const float* l1, const float* l2, const float* eps,
+                             const float* prior1, const float* prior2, const float* dz, float w_kl, float* dl1,
+                             float* dl2, float* dprior1, float* dprior2, void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(l1 && l2 && eps && dl1 && dl2 && N > 0, "op3_state_bwd: bad argument");
+  OP3_REQUIRE(w_kl == 0.f || (prior1 && prior2), "op3_state_bwd: prior required when w_kl != 0");
+  OP3_REQUIRE((dprior1 == nullptr) == (dprior2 == nullptr), "op3_state_bwd: dprior1/dprior2 must both be given");
+  state_bwd_kernel<<<ceil_div(N * d->Rs, 256), 256, 0, (cudaStream_t)stream>>>(N, d->Rd + d->Rs, d->Rd, d->Rs, l1, l2, eps,
+                                                                            prior1, prior2, dz, w_kl, dl1, dl2, dprior1,
+                                                                            dprior2);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+extern "C" size_t op3_refine_acts_floats(const Op3Dims* d) {
+  if (validate_dims(d) != OP3_OK) return 0;
+  return ref_acts_floats(d);
+}
+
+extern "C" size_t op3_refine_scratch_floats(const Op3Dims* d) {
+  if (validate_dims(d) != OP3_OK) return 0;
+  const size_t N = (size_t)d->B * d->K, DD = (size_t)d->D * d->D;
+  size_t w = conv5x5_wgrad_scratch_floats(32, d->Rs);
+  size_t w2 = conv5x5_wgrad_scratch_floats(32, 32);
+  if (w2 > w) w = w2;
+  return N * (d->Rs + 64) * DD + N * (4 * LSTM + HID + 5 * d->Rs + LSTM + HID + d->Rs) + w;
+}
+
+extern "C" int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float* prep, const Op3RefineIO* io,
+                              void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(p && prep && io && io->dec_out && io->mix1 && io->mix2 && io->smp && io->dz && io->z && io->l1 && io->l2 &&
+                  io->eps && io->prior1 && io->prior2 && io->h && io->c && io->acts && io->l1_out && io->l2_out && io->h_out && io->c_out,
+              "op3_refine_fwd: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = d->B * d->K, D = d->D, DD = D * D, Rs = d->Rs, R = d->Rd + d->Rs;
+  const int XW = HID + 5 * Rs;
+  PrepLayout L = prep_layout(d);
+  RefActs A = ref_acts(d, io->acts);
+  // conv stack 17(20) -> 32 -> 32 -> Rs, ELU each (refinement_network.py:195)
+  OP3_TRY(conv5x5_forward(st, N, D, refine_l1_input(d, io, prep, L), 32, prep + L.ref_wf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_forward(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_forward(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr));
+  avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  // X = [ ELU(fc(pooled)) | LN(g_l1) | LN(g_l2) | l1 | l2 | samples ]
+  OP3_TRY(gemm(st, N, HID, Rs, A.pooled, Rs, 0, p->ref_fc.w, Rs, 1, A.X, XW, p->ref_fc.b, ACT_ELU, 0));
+  refine_extras_kernel<<<ceil_div(N, 4), 128, 0, st>>>(N, R, d->Rd, Rs, *io, d->beta / (float)d->B, p->ln1d_scale[0],
+                                                     p->ln1d_center[0], p->ln1d_scale[1], p->ln1d_center[1], A.X, XW, A.xn);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  // LSTM cell, gate order i,f,g,o
+  OP3_TRY(gemm(st, N, 4 * LSTM, XW, A.X, XW, 0, p->lstm_w_ih, XW, 1, A.gates, 4 * LSTM, p->lstm_b_ih, ACT_NONE, 0));
+  OP3_TRY(gemm(st, N, 4 * LSTM, LSTM, io->h, LSTM, 0, p->lstm_w_hh, LSTM, 1, A.gates, 4 * LSTM, p->lstm_b_hh, ACT_NONE, 1));
+  lstm_fwd_kernel<<<ceil_div(N * LSTM, 256), 256, 0, st>>>(N, A.gates, io->c, io->h_out, io->c_out);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  OP3_TRY(gemm(st, N, Rs, LSTM, io->h_out, LSTM, 0, p->ref_last_fc.w, LSTM, 1, io->l1_out, Rs, p->ref_last_fc.b, ACT_NONE, 0));
+  OP3_TRY(gemm(st, N, Rs, LSTM, io->h_out, LSTM, 0, p->ref_last_fc2.w, LSTM, 1, io->l2_out, Rs, p->ref_last_fc2.b, ACT_NONE, 0));
+  return OP3_OK;
+}
+
+extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float* prep, const Op3RefineIO* io,
+                              const float* d_l1n, const float* d_l2n, const float* d_h, const float* d_c, float* d_in,
+                              float* dl1, float* dl2,
+                              float* dz_acc, float* dh, float* dc, const Op3Params* g, float* pg, float* scratch,
+                              void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(p && prep && io && io->acts && io->h && io->c && io->h_out && d_in && dl1 && dl2 && dz_acc && dh && dc && g &&
+                  pg && scratch,
+              "op3_refine_bwd: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = d->B * d->K, D = d->D, DD = D * D, Rs = d->Rs, R = d->Rd + d->Rs;
+  const int XW = HID + 5 * Rs;
+  PrepLayout L = prep_layout(d);
+  RefActs A = ref_acts(d, io->acts);
+  // scratch carve-up
+  size_t o = 0;
+  float4* g3 = reinterpret_cast<float4*>(scratch + o); o += (size_t)N * Rs * DD;
+  float4* g2 = reinterpret_cast<float4*>(scratch + o); o += (size_t)N * 32 * DD;
+  float4* g1 = reinterpret_cast<float4*>(scratch + o); o += (size_t)N * 32 * DD;
+  float* dgates = scratch + o; o += (size_t)N * 4 * LSTM;
+  float* dX = scratch + o; o += (size_t)N * XW;
+  float* dh2 = scratch + o; o += (size_t)N * LSTM;
+  float* dfc = scratch + o; o += (size_t)N * HID;   // (unused separately: dX[:, :HID] is used in place)
+  float* dpool = scratch + o; o += (size_t)N * Rs;
+  float* wscr = scratch + o;
+  (void)dfc;
+
+  // heads: lam = h2 W^T + b
+  OP3_CHECK(cudaMemsetAsync(dh2, 0, (size_t)N * LSTM * sizeof(float), st));
+  if (d_h) OP3_TRY(axpy(st, (long long)N * LSTM, d_h, dh2));
+  if (d_l1n) {
+    OP3_TRY(gemm(st, N, LSTM, Rs, d_l1n, Rs, 0, p->ref_last_fc.w, LSTM, 0, dh2, LSTM, nullptr, ACT_NONE, 1));
+    OP3_TRY(gemm(st, Rs, LSTM, N, d_l1n, Rs, 1, io->h_out, LSTM, 0, g->ref_last_fc.w, LSTM, nullptr, ACT_NONE, 1));
+    OP3_TRY(colsum(st, N, Rs, d_l1n, Rs, g->ref_last_fc.b, 1));
+  }
+  if (d_l2n) {
+    OP3_TRY(gemm(st, N, LSTM, Rs, d_l2n, Rs, 0, p->ref_last_fc2.w, LSTM, 0, dh2, LSTM, nullptr, ACT_NONE, 1));
+    OP3_TRY(gemm(st, Rs, LSTM, N, d_l2n, Rs, 1, io->h_out, LSTM, 0, g->ref_last_fc2.w, LSTM, nullptr, ACT_NONE, 1));
+    OP3_TRY(colsum(st, N, Rs, d_l2n, Rs, g->ref_last_fc2.b, 1));
+  }
+  // LSTM cell
+  lstm_bwd_kernel<<<ceil_div(N * LSTM, 256), 256, 0, st>>>(N, A.gates, io->c, dh2, d_c, dgates, dc);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  OP3_TRY(gemm(st, N, XW, 4 * LSTM, dgates, 4 * LSTM, 0, p->lstm_w_ih, XW, 0, dX, XW, nullptr, ACT_NONE, 0));
+  OP3_TRY(gemm(st, N, LSTM, 4 * LSTM, dgates, 4 * LSTM, 0, p->lstm_w_hh, LSTM, 0, dh, LSTM, nullptr, ACT_NONE, 1));
+  OP3_TRY(gemm(st, 4 * LSTM, XW, N, dgates, 4 * LSTM, 1, A.X, XW, 0, g->lstm_w_ih, XW, nullptr, ACT_NONE, 1));
+  OP3_TRY(gemm(st, 4 * LSTM, LSTM, N, dgates, 4 * LSTM, 1, io->h, LSTM, 0, g->lstm_w_hh, LSTM, nullptr, ACT_NONE, 1));
+  OP3_TRY(colsum(st, N, 4 * LSTM, dgates, 4 * LSTM, g->lstm_b_ih, 1));
+  OP3_TRY(colsum(st, N, 4 * LSTM, dgates, 4 * LSTM, g->lstm_b_hh, 1));
+  // extras: LN1d parameter gradients and the direct paths into the previous state's lambdas / samples
+  for (int j = 0; j < 2; ++j) {
+    colsum_prod_kernel<<<ceil_div(Rs, 32), 256, 0, st>>>(N, Rs, dX + HID + j * Rs, XW, A.xn + j * Rs, 2 * Rs, g->ln1d_scale[j]);
+    OP3_COUNT_LAUNCH();
+    colsum_prod_kernel<<<ceil_div(Rs, 32), 256, 0, st>>>(N, Rs, dX + HID + j * Rs, XW, nullptr, 0, g->ln1d_center[j]);
+    OP3_COUNT_LAUNCH();
+  }
+  add_cols_kernel<<<ceil_div(N * Rs, 256), 256, 0, st>>>(N, Rs, dX + HID + 2 * Rs, XW, dl1, Rs);
+  OP3_COUNT_LAUNCH();
+  add_cols_kernel<<<ceil_div(N * Rs, 256), 256, 0, st>>>(N, Rs, dX + HID + 3 * Rs, XW, dl2, Rs);
+  OP3_COUNT_LAUNCH();
+  add_cols_kernel<<<ceil_div(N * Rs, 256), 256, 0, st>>>(N, Rs, dX + HID + 4 * Rs, XW, dz_acc + d->Rd, R);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  // FC (+ELU) on the pooled features
+  OP3_TRY(act_backward(st, N, HID, dX, XW, A.X, XW, ACT_ELU));
+  OP3_TRY(gemm(st, N, Rs, HID, dX, XW, 0, p->ref_fc.w, Rs, 0, dpool, Rs, nullptr, ACT_NONE, 0));
+  OP3_TRY(gemm(st, HID, Rs, N, dX, XW, 1, A.pooled, Rs, 0, g->ref_fc.w, Rs, nullptr, ACT_NONE, 1));
+  OP3_TRY(colsum(st, N, HID, dX, XW, g->ref_fc.b, 1));
+  // conv stack
+  avgpool_bwd_kernel<<<dim3(ceil_div(Rs / 4 * DD, 256), N), 256, 0, st>>>(dpool, A.r3, Rs / 4, DD, g3);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  OP3_TRY(conv5x5_wgrad(st, N, D, one_src(A.r2, 8), Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2]));
+  OP3_TRY(conv5x5_forward(st, N, D, one_src(g3, Rs / 4), 32, prep + L.ref_wd[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2));
+  OP3_TRY(conv5x5_wgrad(st, N, D, one_src(A.r1, 8), 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1]));
+  OP3_TRY(conv5x5_forward(st, N, D, one_src(g2, 8), 32, prep + L.ref_wd[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1));
+  OP3_TRY(conv5x5_wgrad(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0]));
+  OP3_TRY(conv5x5_forward(st, N, D, one_src(g1, 8), REF_CIN_PAD, prep + L.ref_wd[0], nullptr, reinterpret_cast<float4*>(d_in),
+                          EPI_NONE, nullptr));
+  return OP3_OK;
+}

@@ -177,7 +177,27 @@ def mpc_case():
     print("mpc ok", res["cost/final_recon_sum/order"][:5])
 
 
+def schedule_case():
+    """TrainingScheduler outputs (op3_trainer.py:36-111) for every schedule type under a fixed numpy seed."""
+    from op3.torch.op3_modules.op3_trainer import TrainingScheduler as Ref
+    cases = []
+    for kind in ["single_step_physics", "multi_step_physics", "curriculum", "rprp_curriculum", "static_iodine", "rprp",
+                 "next_step", "random_alternating"]:
+        for epoch in [0, 49, 100, 101, 135, 160, 400]:
+            for is_train in [True, False]:
+                for max_T in [None, 3, 5]:
+                    np.random.seed(3)
+                    r = Ref(4, kind, max_T, 5)
+                    cases.append((kind, epoch, is_train, max_T, r.get_schedule(epoch, is_train), r.should_save_model(epoch)))
+    arr = np.empty(len(cases), dtype=object)
+    for i, c in enumerate(cases):
+        arr[i] = c
+    np.savez_compressed(os.path.join(HERE, "schedules.npz"), cases=arr)
+    print("schedules", len(cases))
+
+
 if __name__ == "__main__":
+    schedule_case()
     train_case("stack_small", stack_variant, K=3, action_dim=0, B=2, T=2, schedule=[0, 0, 1], full_masks=True)
     train_case("pickplace_small", pickplace_variant, K=3, action_dim=4, B=2, T=3, schedule=[0, 0, 1, 1, 0],
                full_masks=False)

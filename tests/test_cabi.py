@@ -1,0 +1,80 @@
+"""CPU: the C-ABI library loads and exports every symbol include/op3_b200.h declares (no compute calls), the Python
+binding declares the same set, and the host-side scheduler logic mirrors the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "op3_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(op3_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from op3_b200 import _build, _lib
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = _header_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "libop3_b200.so does not export %s" % name
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES and the header disagree"
+    bound = _lib.load()
+    assert b"sm_100a" in bound.op3_version()
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    from op3_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _lib.load()
+
+
+def test_size_queries_do_not_need_a_gpu():
+    from op3_b200 import _lib
+    lib = _lib.load()
+    d = _lib.Op3Dims(B=8, K=7, D=64, Rd=64, Rs=64, A=0, beta=0.01)
+    N = 56
+    assert lib.op3_decoder_acts_floats(ctypes.byref(d), N) == N * (800 + 4 * 32 * 64 * 64)
+    assert lib.op3_prepared_floats(ctypes.byref(d)) > 25 * 32 * 128
+    bad = _lib.Op3Dims(B=8, K=7, D=60, Rd=64, Rs=64, A=0, beta=0.01)
+    assert lib.op3_prepared_floats(ctypes.byref(bad)) == 0
+    assert b"multiple of 8" in lib.op3_last_error()
+
+
+def test_state_dict_keys_match_reference_layout():
+    """73 / 85 entries with the reference key names, incl. the `inital_deter_state` typo."""
+    from oracle import op3_oracle as orc
+    from op3_b200.torch.op3_modules.op3_model import create_model_v2
+    for action_dim, n in ((0, 73), (4, 85)):
+        v = dict(refinement_model_type="size_dependent_conv", decoder_model_type="reg", dynamics_model_type="reg_ac32",
+                 K=4, extra_args=dict(beta=1e-2, deterministic_sampling=False))
+        m = create_model_v2(v, 64, 64, action_dim)
+        sd = m.state_dict()
+        shapes = dict(orc.param_shapes(action_dim))
+        assert len(sd) == n and set(sd) == set(shapes)
+        for k, t in sd.items():
+            assert tuple(t.shape) == tuple(shapes[k]), k
+        assert "inital_deter_state" in sd
+        assert sum(p.numel() for p in m.parameters()) == (876305 if action_dim == 0 else 938930)
+
+
+def test_training_scheduler_matches_reference_fixture(golden_dir):
+    from op3_b200.torch.op3_modules.op3_trainer import TrainingScheduler
+    fx = np.load(os.path.join(golden_dir, "schedules.npz"), allow_pickle=True)
+    cases = fx["cases"]
+    for kind, epoch, is_train, max_T, expect, save in cases:
+        np.random.seed(3)
+        s = TrainingScheduler(4, kind, max_T, 5)
+        got = s.get_schedule(int(epoch), bool(is_train))
+        assert np.array_equal(got, expect), (kind, epoch, is_train, max_T)
+        assert s.should_save_model(int(epoch)) == save
+        assert np.array_equal(s.get_loss_schedule(got), np.arange(1, len(got) + 1))
