@@ -87,6 +87,14 @@ const char* op3_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long op3_launch_count(void);
 
+/* Optional timing of kernel families with CUDA events on the launch stream (used by bench.py for the roofline
+ * numbers).  Families: 0 = conv5x5 forward/dgrad, 1 = conv5x5 wgrad, 2 = mixture kernels, 3 = small GEMMs.
+ * collect() synchronises on the recorded events and returns, per family, the summed milliseconds, the summed
+ * algorithmic work (FLOPs, or bytes for family 2) and the number of timed calls; it also resets the recorder. */
+#define OP3_PROFILE_FAMILIES 4
+int op3_profile_enable(int on);
+int op3_profile_collect(double* ms, double* work, long long* launches);
+
 /* ---- derived weights -------------------------------------------------------------------------------------
  * Re-laid-out / algebraically collapsed copies of the conv weights (tap-major layouts for forward and dgrad, the
  * 25 border-class sums + coordinate map of decoder layer 1).  Must be refreshed after every optimizer step.

@@ -1,5 +1,6 @@
 // Library-wide state of the C ABI: version, thread-local error string, launch counter.
 #include <stdarg.h>
+#include <vector>
 #include "common.cuh"
 
 namespace op3 {
@@ -11,7 +12,45 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// ---- profiling -------------------------------------------------------------------------------------------
+bool g_profile_on = false;
+namespace {
+struct ProfEntry { cudaEvent_t a, b; int kid; double work; };
+std::vector<ProfEntry> g_entries;
+std::vector<cudaEvent_t> g_pool;
+cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void profile_begin(cudaStream_t st, int kid, double work) {
+  ProfEntry en{get_event(), get_event(), kid, work};
+  cudaEventRecord(en.a, st);
+  g_entries.push_back(en);
+}
+void profile_end(cudaStream_t st) { if (!g_entries.empty()) cudaEventRecord(g_entries.back().b, st); }
 }  // namespace op3
+
+extern "C" int op3_profile_enable(int on) {
+  for (auto& e : op3::g_entries) { op3::g_pool.push_back(e.a); op3::g_pool.push_back(e.b); }
+  op3::g_entries.clear();
+  op3::g_profile_on = on != 0;
+  return OP3_OK;
+}
+
+extern "C" int op3_profile_collect(double* ms, double* work, long long* launches) {
+  for (int i = 0; i < op3::KID_COUNT; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+  for (auto& e : op3::g_entries) {
+    OP3_CHECK(cudaEventSynchronize(e.b));
+    float t = 0.f;
+    OP3_CHECK(cudaEventElapsedTime(&t, e.a, e.b));
+    ms[e.kid] += t; work[e.kid] += e.work; launches[e.kid] += 1;
+    op3::g_pool.push_back(e.a); op3::g_pool.push_back(e.b);
+  }
+  op3::g_entries.clear();
+  return OP3_OK;
+}
 
 extern "C" const char* op3_version(void) { return "op3_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* op3_last_error(void) { return op3::g_err; }

@@ -36,6 +36,17 @@ void set_error(const char* fmt, ...);
 extern unsigned long long g_launch_count;
 #define OP3_COUNT_LAUNCH() (++op3::g_launch_count)
 
+// ---- optional per-kernel-family timing (op3_profile_enable / op3_profile_collect), CUDA events on the launch stream
+enum { KID_CONV_FWD = 0, KID_CONV_WGRAD = 1, KID_MIXTURE = 2, KID_GEMM = 3, KID_COUNT = 4 };
+extern bool g_profile_on;
+void profile_begin(cudaStream_t st, int kid, double work);
+void profile_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(cudaStream_t s, int kid, double work) : st(s), on(g_profile_on) { if (on) profile_begin(st, kid, work); }
+  ~ProfScope() { if (on) profile_end(st); }
+};
+
 // ---- small device helpers -------------------------------------------------------------------
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 // derivative of ELU(alpha=1) expressed through its OUTPUT a: a>0 -> 1, else a+1 (= e^x)
@@ -90,6 +101,7 @@ struct ConvInput {
   ConvSrc src[5];
   int nsrc;
   int total_chunks;
+  int real_cin;           // channels that carry data (0 = 4*total_chunks); only used for FLOP accounting
 };
 enum { EPI_NONE = 0, EPI_ELU = 1, EPI_MUL_ELUGRAD = 2 };
 // out[n][cout/4][D][D] = epi( conv5x5_pad2(in, wt) + bias ); wt layout [25][cin_pad][cout] (cout fastest)

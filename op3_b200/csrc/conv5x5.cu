@@ -336,6 +336,8 @@ int conv5x5_forward(cudaStream_t st, int N, int D, const ConvInput& in, int cout
                     float4* out, int epi, const float4* elu_ref) {
   OP3_REQUIRE(D % TR == 0, "conv5x5: D=%d must be a multiple of %d", D, TR);
   if (N <= 0) return OP3_OK;
+  const int cin_real = in.real_cin ? in.real_cin : in.total_chunks * 4;
+  ProfScope prof(st, KID_CONV_FWD, 2.0 * 25 * cin_real * (cout == 20 ? 17 : cout) * (double)N * D * D);
   switch (cout) {
     case 4:  return launch_fwd<4, 4>(st, N, D, in, wt, bias, out, epi, elu_ref);
     case 20: return launch_fwd<20, 20>(st, N, D, in, wt, bias, out, epi, elu_ref);
@@ -355,6 +357,8 @@ int conv5x5_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, int cout, 
                   float* dwt, float* dbias) {
   OP3_REQUIRE(D % WR == 0, "conv5x5_wgrad: D=%d must be a multiple of %d", D, WR);
   if (N <= 0) return OP3_OK;
+  const int cin_real = in.real_cin ? in.real_cin : in.total_chunks * 4;
+  ProfScope prof(st, KID_CONV_WGRAD, 2.0 * 25 * cin_real * cout * (double)N * D * D);
   switch (cout) {
     case 4:  return launch_wgrad<4, 4, 4>(st, N, D, in, dpre, scratch, dwt, dbias);
     case 32: return launch_wgrad<32, 8, 4>(st, N, D, in, dpre, scratch, dwt, dbias);

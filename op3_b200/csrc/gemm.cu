@@ -118,6 +118,7 @@ __global__ void axpy_kernel(long long n, const float* __restrict__ x, float* __r
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, int transA, const float* B, int ldb,
          int transB, float* C, int ldc, const float* bias, int act, int accumulate) {
   if (M <= 0 || N <= 0) return OP3_OK;
+  ProfScope prof(st, KID_GEMM, 2.0 * M * N * K);
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
   if (transA == 0 && transB == 0) gemm_kernel<0, 0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
   else if (transA == 0 && transB == 1) gemm_kernel<0, 1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);

@@ -417,6 +417,8 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
                 "op3_mixture_fwd: statistics requested but image/stats/losses/lambda pointers missing");
   if (emit) OP3_REQUIRE(p && io->mix2 && io->smp, "op3_mixture_fwd: refine inputs requested but mix2/smp/params missing");
   StatsLayout L = stats_layout(B, K, D);
+  // algorithmic bytes: full forward (11K+4)*4 per pixel-sample, outputs-only (8K+3... see DESIGN.md)
+  ProfScope prof(st, KID_MIXTURE, (emit ? (11.0 * K + 4) : (8.0 * K + 6)) * 4.0 * B * D * D);
   dim3 gs(L.tiles, B);
 #define OP3_MIX_STATS(KM) mix_stats_kernel<KM><<<gs, MIX_THREADS, 0, st>>>(*io, io->mse_image, io->mse_image_bstride, B, K, D, want_stats)
   if (K <= 4) OP3_MIX_STATS(4); else if (K <= 8) OP3_MIX_STATS(8); else OP3_MIX_STATS(16);
@@ -450,6 +452,7 @@ extern "C" int op3_mixture_bwd(const Op3Dims* d, const Op3MixtureIO* io, float w
   cudaStream_t st = (cudaStream_t)stream;
   const int B = d->B, K = d->K, D = d->D;
   StatsLayout L = stats_layout(B, K, D);
+  ProfScope prof(st, KID_MIXTURE, (14.0 * K + 3) * 4.0 * B * D * D);
   dim3 g(ceil_div(D * D, MIX_THREADS), B);
   OP3_REQUIRE((size_t)g.x * B * 12 <= (size_t)B * L.tiles * STATS_PPT * 12, "op3_mixture_bwd: partial buffer too small");
   double* gpart = reinterpret_cast<double*>(io->stats + L.gpart);

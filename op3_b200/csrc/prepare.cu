@@ -145,13 +145,18 @@ extern "C" int op3_prepare(const Op3Dims* d, const Op3Params* p, float* prep, vo
   cudaStream_t st = (cudaStream_t)stream;
   PrepLayout L = prep_layout(d);
   const int R = d->Rd + d->Rs, D = d->D;
-  prep_wsum_kernel<<<ceil_div(NCLS * 32 * R, 256), 256, 0, st>>>(p->dec_conv_w[0], p->dec_conv_b[0], R, prep + L.wsum,
-                                                                prep + L.biasT);
-  OP3_COUNT_LAUNCH();
-  prep_cmap_kernel<<<ceil_div(32 * D * D, 256), 256, 0, st>>>(p->dec_conv_w[0], R, D, prep + L.cmap, prep + L.coords);
-  OP3_COUNT_LAUNCH();
+  // a standalone DecoderNetwork / RefinementNetwork only owns its own weights: NULL groups are skipped
+  const bool has_dec = p->dec_conv_w[0] != nullptr, has_ref = p->ref_conv_w[0] != nullptr;
+  OP3_REQUIRE(has_dec || has_ref, "op3_prepare: neither decoder nor refinement weights given");
   const int dec_cout[4] = {32, 32, 32, 4};
-  for (int i = 0; i < 4; ++i) {
+  if (has_dec) {
+    prep_wsum_kernel<<<ceil_div(NCLS * 32 * R, 256), 256, 0, st>>>(p->dec_conv_w[0], p->dec_conv_b[0], R, prep + L.wsum,
+                                                                  prep + L.biasT);
+    OP3_COUNT_LAUNCH();
+    prep_cmap_kernel<<<ceil_div(32 * D * D, 256), 256, 0, st>>>(p->dec_conv_w[0], R, D, prep + L.cmap, prep + L.coords);
+    OP3_COUNT_LAUNCH();
+  }
+  for (int i = 0; i < 4 && has_dec; ++i) {
     prep_conv_kernel<<<ceil_div(25 * 32 * dec_cout[i], 256), 256, 0, st>>>(p->dec_conv_w[i + 1], dec_cout[i], 32, 32, 0,
                                                                            prep + L.dec_wf[i], prep + L.dec_wd[i]);
     OP3_COUNT_LAUNCH();
@@ -159,7 +164,7 @@ extern "C" int op3_prepare(const Op3Dims* d, const Op3Params* p, float* prep, vo
                               cudaMemcpyDeviceToDevice, st));
   }
   const int ref_cin[3] = {17, 32, 32}, ref_pad[3] = {REF_CIN_PAD, 32, 32}, ref_cout[3] = {32, 32, d->Rs};
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 3 && has_ref; ++i) {
     prep_conv_kernel<<<ceil_div(25 * ref_pad[i] * ref_cout[i], 256), 256, 0, st>>>(
         p->ref_conv_w[i], ref_cout[i], ref_cin[i], ref_pad[i], i == 0 ? 1 : 0, prep + L.ref_wf[i], prep + L.ref_wd[i]);
     OP3_COUNT_LAUNCH();

@@ -228,7 +228,7 @@ inline ConvInput refine_l1_input(const Op3Dims* d, const Op3RefineIO* io, const 
   in.src[2] = {reinterpret_cast<const float4*>(io->mix2), 1, 1};
   in.src[3] = {reinterpret_cast<const float4*>(io->smp), 1, d->K};
   in.src[4] = {reinterpret_cast<const float4*>(prep + L.coords), 1, 0};
-  in.nsrc = 5; in.total_chunks = 5;
+  in.nsrc = 5; in.total_chunks = 5; in.real_cin = 17;
   return in;
 }
 inline ConvInput one_src(const float4* p, int chunks) {

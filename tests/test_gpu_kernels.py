@@ -125,8 +125,9 @@ def test_dynamics_backward_matches_autograd():
         d_oz[:, :64] = up[0].cuda()
         dz = torch.empty(N, R, device="cuda")
         scratch = torch.empty(lib.op3_dynamics_scratch_floats(C.byref(d)), device="cuda")
-        check(lib.op3_dynamics_bwd(C.byref(d), C.byref(ps), ptr(zc), ptr(ac), ptr(A), ptr(d_oz), ptr(up[1].cuda()),
-                                   ptr(up[2].cuda()), ptr(dz), C.byref(gs), ptr(scratch), st))
+        u1, u2 = up[1].cuda(), up[2].cuda()      # keep alive: the call is asynchronous
+        check(lib.op3_dynamics_bwd(C.byref(d), C.byref(ps), ptr(zc), ptr(ac), ptr(A), ptr(d_oz), ptr(u1), ptr(u2), ptr(dz),
+                                   C.byref(gs), ptr(scratch), st))
         assert rel_l2(dz, zr.grad) <= 2e-5
         views = dict(zip(eng._names, eng.grad_views(gflat)))
         ref = {k: v.grad for k, v in q.items()}

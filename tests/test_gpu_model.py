@@ -97,7 +97,7 @@ def test_fused_clip_adam_matches_oracle():
     B, K, T = cfg["B"], cfg["K"], cfg["T"]
     with NoiseInjector(orc.make_noise(B, K, 64, 4)):
         out2 = m.forward(orc.synth_frames(B, T).cuda(), None, None, np.array([0., 0., 1.]), np.arange(1, 4))
-    q = {k: v.detach().cpu() for k, v in m.named_parameters()}
+    q = {k: v.detach().cpu().requires_grad_(True) for k, v in m.named_parameters()}
     o2 = orc.run_schedule(q, orc.synth_frames(B, T), None, [0, 0, 1], np.arange(1, 4), orc.make_noise(B, K, 64, 4), K)
     assert abs(out2[3].item() - o2["total_loss"].item()) <= 2e-5 * abs(o2["total_loss"].item())
 
