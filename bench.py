@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "fp32"), choices=["fp32", "tf32x3", "tf32"],
+                    help="arithmetic of the 5x5 convolutions (see op3_set_precision)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -194,6 +196,8 @@ def main():
     from op3_b200.torch.op3_modules.op3_trainer import OP3Trainer, TrainingScheduler
     from oracle import op3_oracle as orc       # weights only (deterministic synthetic init); not on the timed path
     lib = _lib.load()
+    import op3_b200
+    op3_b200.set_precision(args.precision)
     torch.manual_seed(1234 + rank)
     model = create_model_v2(dict(VARIANT, K=K), 64, 64, A)
     model.load_state_dict(orc.make_params(A, seed=0, generic=False))
@@ -279,11 +283,12 @@ def main():
     line = {
         "metric": "train_sequences_per_sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split on tcgen05)", "tf32": "tf32"}[args.precision],
+        "data": "synthetic", "config": dict(CONFIG, precision=args.precision),
         "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(B_PER_GPU * T * 3 * D * D + B_PER_GPU * T * 4 * 4), "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": fam[dom] + " (fp32 CUDA-core kernel; tcgen05 path pending)",
+        "roofline": {"bound": "tensor", "kernel": fam[dom] + (" (fp32 CUDA cores)" if (args.precision == "fp32" or dom == 1) else " (tcgen05 kind::tf32, %s)" % args.precision),
                      "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                      "traffic": None, "avg_launch_ms": pms[dom] / max(pn[dom], 1),
                      "share_of_step": pms[dom] / ms_total,

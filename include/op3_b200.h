@@ -87,6 +87,14 @@ const char* op3_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long op3_launch_count(void);
 
+/* Arithmetic of the 5x5 convolutions (decoder layers 2-5, refinement conv stack, forward and dgrad):
+ *   0 = fp32 CUDA-core kernels (exact mode, bit-faithful fp32 products),
+ *   1 = tcgen05 3xTF32 operand splitting (fp32-grade; parity mode),
+ *   2 = tcgen05 1xTF32 (speed mode; operands truncated to 19 bits).
+ * Process-wide; call op3_prepare again after changing it (the derived weights depend on the mode). */
+int op3_set_precision(int mode);
+int op3_get_precision(void);
+
 /* Optional timing of kernel families with CUDA events on the launch stream (used by bench.py for the roofline
  * numbers).  Families: 0 = conv5x5 forward/dgrad, 1 = conv5x5 wgrad, 2 = mixture kernels, 3 = small GEMMs.
  * collect() synchronises on the recorded events and returns, per family, the summed milliseconds, the summed

@@ -22,6 +22,22 @@ _ALIASES = {
 }
 
 
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+
+
+def set_precision(name):
+    """Arithmetic of the 5x5 convolutions: 'fp32' (CUDA cores, exact), 'tf32x3' (tcgen05, fp32-grade operand
+    splitting) or 'tf32' (tcgen05, 1xTF32 speed mode).  Process-wide; derived weights are rebuilt on the next call."""
+    from . import _lib
+    _lib.check(_lib.load().op3_set_precision(PRECISIONS[name]), "op3_set_precision")
+
+
+def get_precision():
+    from . import _lib
+    mode = _lib.load().op3_get_precision()
+    return [k for k, v in PRECISIONS.items() if v == mode][0]
+
+
 def install():
     """Make `import op3.torch.op3_modules.op3_model` (etc.) resolve to this package so that the reference's
     exps/train_op3/train_op3.py and MPC scripts run unchanged on top of the sm_100a kernels.  Call before the

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <vector>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace op3 {
 static thread_local char g_err[1024] = "";
@@ -51,6 +52,14 @@ extern "C" int op3_profile_collect(double* ms, double* work, long long* launches
   op3::g_entries.clear();
   return OP3_OK;
 }
+
+static int g_precision = OP3_PREC_FP32;
+extern "C" int op3_set_precision(int mode) {
+  if (mode < 0 || mode > 2) { op3::set_error("op3_set_precision: mode %d not in {0 fp32, 1 tf32x3, 2 tf32}", mode); return OP3_ERR_ARG; }
+  g_precision = mode;
+  return OP3_OK;
+}
+extern "C" int op3_get_precision(void) { return g_precision; }
 
 extern "C" const char* op3_version(void) { return "op3_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* op3_last_error(void) { return op3::g_err; }

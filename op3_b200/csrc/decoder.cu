@@ -135,10 +135,10 @@ extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const
   OP3_LAUNCH_CHECK();
   // layers 2-4 are the implicit-GEMM hot spot (M = N*D*D pixels, N = 32, K = 800); layer 5 has 4 outputs
   for (int i = 0; i < 3; ++i)
-    OP3_TRY(conv5x5_forward(st, N, D, single_src(A.a[i], 8), 32, prep + L.dec_wf[i], prep + L.dec_bf[i], A.a[i + 1],
-                            EPI_ELU, nullptr));
-  OP3_TRY(conv5x5_forward(st, N, D, single_src(A.a[3], 8), 4, prep + L.dec_wf[3], prep + L.dec_bf[3],
-                          reinterpret_cast<float4*>(out), EPI_NONE, nullptr));
+    OP3_TRY(conv5x5_auto(st, N, D, single_src(A.a[i], 8), 32, prep + L.dec_wf[i], prep + L.dec_tf[i], prep + L.dec_bf[i],
+                         A.a[i + 1], EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, single_src(A.a[3], 8), 4, prep + L.dec_wf[3], prep + L.dec_tf[3], prep + L.dec_bf[3],
+                       reinterpret_cast<float4*>(out), EPI_NONE, nullptr));
   return OP3_OK;
 }
 
@@ -164,7 +164,8 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
     if (pg) OP3_TRY(conv5x5_wgrad(st, N, D, single_src(A.a[i], 8), cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i]));
     float4* gn = gbuf[i & 1];
     // dgrad: conv over g with flipped/transposed weights, times ELU'(a[i]) -> dPre of the layer below
-    OP3_TRY(conv5x5_forward(st, N, D, single_src(g, gch), 32, prep + L.dec_wd[i], nullptr, gn, EPI_MUL_ELUGRAD, A.a[i]));
+    OP3_TRY(conv5x5_auto(st, N, D, single_src(g, gch), 32, prep + L.dec_wd[i], prep + L.dec_td[i], nullptr, gn,
+                         EPI_MUL_ELUGRAD, A.a[i]));
     g = gn;
     gch = 8;
   }

@@ -1,6 +1,7 @@
 // Layout of the "prepared" (derived-weight) buffer and of its gradient twin.  See op3_prepare in op3_b200.h.
 #pragma once
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace op3 {
 
@@ -18,6 +19,8 @@ struct PrepLayout {
   size_t ref_bf[3];  // refinement conv biases                                  (grad twin: d bias)
   size_t ref_wd[3];  // refinement dgrad [25][32][20], [25][32][32], [25][Rs][32]
   size_t coords;     // [D][D] float4 (x, y, 0, 0)
+  // tcgen05 weight slabs (conv5x5_tc.cu): [K group][tap][k-chunk][row][4], forward and dgrad orientation
+  size_t dec_tf[4], dec_td[4], ref_tf[3], ref_td[3];
   size_t total;
 };
 
@@ -39,6 +42,10 @@ inline PrepLayout prep_layout(const Op3Dims* d) {
   for (int i = 0; i < 3; ++i) L.ref_bf[i] = take(ref_cout[i]);
   for (int i = 0; i < 3; ++i) L.ref_wd[i] = take((size_t)25 * ref_cout[i] * ref_cin[i]);
   L.coords = take((size_t)4 * D * D);
+  for (int i = 0; i < 4; ++i) L.dec_tf[i] = take(conv5x5_tc_weight_floats(32, dec_cout[i]));
+  for (int i = 0; i < 4; ++i) L.dec_td[i] = take(conv5x5_tc_weight_floats(dec_cout[i], 32));
+  for (int i = 0; i < 3; ++i) L.ref_tf[i] = take(conv5x5_tc_weight_floats(ref_cin[i], ref_cout[i]));
+  for (int i = 0; i < 3; ++i) L.ref_td[i] = take(conv5x5_tc_weight_floats(ref_cout[i], ref_cin[i]));
   L.total = o;
   return L;
 }

@@ -75,6 +75,38 @@ __global__ void prep_cmap_kernel(const float* __restrict__ W1, int R, int D, flo
   cmap[(((size_t)(co / 4) * D + y) * D + x) * 4 + (co % 4)] = s;
 }
 
+// tcgen05 weight slab: element (g, tap, kc, row, e) of [groups][25][2][NB][4]; GEMM input channel = g*8+kc*4+e.
+//   transposed = 0 (forward): value = W[co][ci][tap];  transposed = 1 (dgrad): value = W[ci_g][co_g][24-tap] where the
+//   GEMM input channels are the layer's outputs.  mode 1 applies the refinement-L1 channel permutation to the layer's
+//   INPUT channel index.  split3: rows [0,nout) = rn_tf32(w), rows [nout,2nout) = rn_tf32(w - rn_tf32(w)).
+__global__ void prep_tc_kernel(const float* __restrict__ W, int cout_src, int cin_src, int mode, int transposed, int groups,
+                               int nout, int split3, int co_base, float* __restrict__ slab) {
+  const int NB = split3 ? 2 * nout : nout;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int tot = groups * 25 * 2 * NB * 4;
+  if (i >= tot) return;
+  int e = i % 4, row = (i / 4) % NB, kc = (i / (4 * NB)) % 2, tap = (i / (8 * NB)) % 25, g = i / (200 * NB);
+  int k_in = g * 8 + kc * 4 + e;                 // GEMM K channel
+  int n_out = (row % nout) + co_base;            // GEMM N channel
+  float w = 0.f;
+  if (!transposed) {
+    int ci = mode == 1 ? ref_l1_channel(k_in) : k_in;
+    if (ci >= 0 && ci < cin_src && n_out < cout_src) w = W[((size_t)n_out * cin_src + ci) * 25 + tap];
+  } else {
+    int ci = mode == 1 ? ref_l1_channel(n_out) : n_out;   // layer input channel = GEMM output
+    if (ci >= 0 && ci < cin_src && k_in < cout_src) w = W[((size_t)k_in * cin_src + ci) * 25 + (24 - tap)];
+  }
+  // the tensor core truncates to tf32: store round-to-nearest values so that truncation is a no-op (see conv5x5_tc.cu)
+  float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+  if (split3) {
+    float lo = w - hi;
+    w = row < nout ? hi : __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+  } else {
+    w = hi;
+  }
+  slab[i] = w;
+}
+
 // ---- gradient folding ------------------------------------------------------------------------------------
 __global__ void fin_conv_kernel(const float* __restrict__ dwf, const float* __restrict__ dbf, int cout, int cin,
                                 int cin_pad, int mode, float* __restrict__ dW, float* __restrict__ db) {
@@ -170,6 +202,33 @@ extern "C" int op3_prepare(const Op3Dims* d, const Op3Params* p, float* prep, vo
     OP3_COUNT_LAUNCH();
     OP3_CHECK(cudaMemcpyAsync(prep + L.ref_bf[i], p->ref_conv_b[i], ref_cout[i] * sizeof(float),
                               cudaMemcpyDeviceToDevice, st));
+  }
+  // tcgen05 slabs for the current precision mode
+  const int prec = op3_get_precision();
+  if (prec != OP3_PREC_FP32) {
+    const int s3 = prec == OP3_PREC_TF32X3;
+    auto build = [&](const float* W, int cout_src, int cin_src, int mode, int transposed, int gemm_cin_pad, int gemm_cout,
+                     float* slab) {
+      const int groups = (gemm_cin_pad / 4 + 1) / 2;
+      const int nout_full = tc_nout(gemm_cout);
+      const int halves = (s3 && nout_full == 64) ? 2 : 1;          // see conv5x5_tc_forward
+      const int nout = halves == 2 ? 32 : nout_full;
+      const int NB = s3 ? 2 * nout : nout;
+      const int per = groups * 25 * 2 * NB * 4;
+      for (int h = 0; h < halves; ++h) {
+        prep_tc_kernel<<<ceil_div(per, 256), 256, 0, st>>>(W, cout_src, cin_src, mode, transposed, groups, nout, s3, 32 * h,
+                                                          slab + (size_t)h * per);
+        OP3_COUNT_LAUNCH();
+      }
+    };
+    for (int i = 0; i < 4 && has_dec; ++i) {
+      build(p->dec_conv_w[i + 1], dec_cout[i], 32, 0, 0, 32, dec_cout[i], prep + L.dec_tf[i]);
+      build(p->dec_conv_w[i + 1], dec_cout[i], 32, 0, 1, dec_cout[i], 32, prep + L.dec_td[i]);
+    }
+    for (int i = 0; i < 3 && has_ref; ++i) {
+      build(p->ref_conv_w[i], ref_cout[i], ref_cin[i], i == 0 ? 1 : 0, 0, ref_pad[i], ref_cout[i], prep + L.ref_tf[i]);
+      build(p->ref_conv_w[i], ref_cout[i], ref_cin[i], i == 0 ? 1 : 0, 1, ref_cout[i], ref_pad[i], prep + L.ref_td[i]);
+    }
   }
   OP3_LAUNCH_CHECK();
   return OP3_OK;

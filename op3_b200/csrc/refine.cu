@@ -295,9 +295,9 @@ extern "C" int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float*
   PrepLayout L = prep_layout(d);
   RefActs A = ref_acts(d, io->acts);
   // conv stack 17(20) -> 32 -> 32 -> Rs, ELU each (refinement_network.py:195)
-  OP3_TRY(conv5x5_forward(st, N, D, refine_l1_input(d, io, prep, L), 32, prep + L.ref_wf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr));
-  OP3_TRY(conv5x5_forward(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr));
-  OP3_TRY(conv5x5_forward(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr));
   avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
@@ -392,11 +392,11 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   OP3_TRY(conv5x5_wgrad(st, N, D, one_src(A.r2, 8), Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2]));
-  OP3_TRY(conv5x5_forward(st, N, D, one_src(g3, Rs / 4), 32, prep + L.ref_wd[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(g3, Rs / 4), 32, prep + L.ref_wd[2], prep + L.ref_td[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2));
   OP3_TRY(conv5x5_wgrad(st, N, D, one_src(A.r1, 8), 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1]));
-  OP3_TRY(conv5x5_forward(st, N, D, one_src(g2, 8), 32, prep + L.ref_wd[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(g2, 8), 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1));
   OP3_TRY(conv5x5_wgrad(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0]));
-  OP3_TRY(conv5x5_forward(st, N, D, one_src(g1, 8), REF_CIN_PAD, prep + L.ref_wd[0], nullptr, reinterpret_cast<float4*>(d_in),
-                          EPI_NONE, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(g1, 8), REF_CIN_PAD, prep + L.ref_wd[0], prep + L.ref_td[0], nullptr,
+                       reinterpret_cast<float4*>(d_in), EPI_NONE, nullptr));
   return OP3_OK;
 }

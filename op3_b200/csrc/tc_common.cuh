@@ -1,0 +1,116 @@
+// tcgen05 / TMEM / mbarrier helpers (inline PTX for sm_100a).  Conventions verified by tests/probes/probe_tcgen05.cu:
+//  * K-major, no-swizzle smem operand: rows of 16 bytes (4 tf32), 8-row core matrices contiguous (SBO = 8 x 16 B),
+//    the two 16-byte K-chunks of one K=8 MMA are LBO apart; the descriptor start address may point at any 16-byte row;
+//  * kind::tf32 TRUNCATES fp32 operands to 19 bits;
+//  * a single thread can issue one M=128 x K=8 MMA every ~48 cycles for N <= 64 (operand-fetch floor), N/4 beyond.
+#pragma once
+#include "common.cuh"
+
+namespace op3 {
+
+#define OP3_PREC_FP32 0      /* CUDA-core fp32 kernels (exact mode)          */
+#define OP3_PREC_TF32X3 1    /* tcgen05 3xTF32 split (fp32-grade, parity)    */
+#define OP3_PREC_TF32 2      /* tcgen05 1xTF32 (speed mode)                  */
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_lo(float x) { return x - tf32_hi(x); }
+// round to nearest tf32 (ties away from zero in magnitude); result has its low 13 mantissa bits clear
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo16 & 0x3FFF) << 16;
+  d |= (uint64_t)(sbo16 & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version 1 (Blackwell); layout_type 0 = no swizzle, base_offset 0
+  return d;
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  unsigned long long spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1ull << 28)) __trap();
+  }
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(COLS) : "memory");
+}
+// 32 lanes x 16 consecutive columns: thread i of the warp receives lane (taddr.lane + i), columns [col, col+16)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ const float4* tc_src_chunk_ptr(const ConvInput& in, int c, int n, int D) {
+  int base = 0;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    if (s < in.nsrc) {
+      int nc = in.src[s].nchunks;
+      if (c < base + nc) {
+        int idx = in.src[s].div > 0 ? n / in.src[s].div : 0;
+        return in.src[s].ptr + ((size_t)idx * nc + (c - base)) * D * D;
+      }
+      base += nc;
+    }
+  }
+  return nullptr;
+}
+
+// conv5x5_tc.cu
+int tc_nout(int cout);
+size_t conv5x5_tc_weight_floats(int cin_pad, int cout);
+int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float* wt,
+                       const float* bias, float4* out, int epi, const float4* elu_ref);
+
+int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
+                 const float* bias, float4* out, int epi, const float4* elu_ref);
+
+}  // namespace op3

@@ -185,7 +185,8 @@ class Engine:
         return self._pstruct
 
     def _version_key(self):
-        return (self._flat.data_ptr(), sum(p._version for _, p in self._named_params()), self.manual_version)
+        return (self._flat.data_ptr(), sum(p._version for _, p in self._named_params()), self.manual_version,
+                self.lib.op3_get_precision())
 
     def prepared(self, stream):
         """Derived weights (op3_prepare), refreshed whenever the parameters changed."""

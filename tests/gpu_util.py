@@ -50,13 +50,13 @@ def max_abs(a, b):
     return (a.detach().double().cpu() - b.detach().double().cpu()).abs().max().item()
 
 
-def compare_grads(ours, ref, total_norm, rtol, report=None):
+def compare_grads(ours, ref, total_norm, rtol, report=None, floor=1e-6):
     """Per-tensor relative L2 error with an absolute floor tied to the global gradient norm.  Returns worst."""
     worst = ("", 0.0)
     for k, g in ref.items():
         mine = ours[k]
         err = (mine.detach().double().cpu() - g.double()).norm().item()
-        scale = max(g.double().norm().item(), 1e-6 * total_norm)
+        scale = max(g.double().norm().item(), floor * total_norm)
         r = err / scale
         if report is not None:
             report.append("%-60s rel %.3e  |ref| %.3e" % (k, r, g.norm().item()))
