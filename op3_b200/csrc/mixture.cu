@@ -14,7 +14,7 @@ namespace op3 {
 namespace {
 
 constexpr int MIX_THREADS = 256;
-constexpr int STATS_PPT = 4;  // pixels per thread in the statistics pass
+constexpr int STATS_PPT = 2;  // pixels per thread in the statistics pass
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -67,10 +67,11 @@ struct Pixel {
 // stats buffer layout (in floats; the fp64 regions are 8-byte aligned because every count below is even)
 struct StatsLayout {
   int tiles, nq;
-  size_t shifts;    // [B][3K+1] floats (padded to even)
-  size_t ln;        // [B][K][3][2] + [B][2] floats: (mean, 1/(std+eps))
-  size_t partial;   // [B][tiles][nq] doubles
-  size_t gpart;     // [B*tiles][12] doubles (LN2D parameter-gradient partials of the backward pass)
+  size_t ln;        // [B][K][3][2] + [B][2] floats: (mean, 1/(std+eps)) per LayerNorm2D group
+  size_t partial;   // [B][tiles][nq] doubles: raw sum / sum of squares per group, -log P sum, squared recon error
+  size_t sample;    // [B][3] doubles: per-sample clog, kl, squared error (+ 2 floats of counter at the end)
+  size_t counter;   // 1 unsigned (last-block-done reduction of the loss scalars)
+  size_t gpart;     // [B*blocks][12] doubles (LN2D parameter-gradient partials of the backward pass)
   size_t total;
 };
 __host__ __device__ inline StatsLayout stats_layout(int B, int K, int D) {
@@ -78,16 +79,19 @@ __host__ __device__ inline StatsLayout stats_layout(int B, int K, int D) {
   L.tiles = (D * D + MIX_THREADS * STATS_PPT - 1) / (MIX_THREADS * STATS_PPT);
   L.nq = 6 * K + 4;
   size_t o = 0;
-  L.shifts = o; o += (size_t)B * (3 * K + 1); o = (o + 1) & ~(size_t)1;
   L.ln = o; o += (size_t)B * K * 6 + (size_t)B * 2; o = (o + 1) & ~(size_t)1;
   L.partial = o; o += 2 * (size_t)B * L.tiles * L.nq;
-  L.gpart = o; o += 2 * (size_t)B * L.tiles * STATS_PPT * 12;
+  L.sample = o; o += 2 * (size_t)B * 3;
+  L.counter = o; o += 2;
+  L.gpart = o; o += 2 * (size_t)B * ((D * D + MIX_THREADS - 1) / MIX_THREADS) * 12;
   L.total = o;
   return L;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// pass A: masks / colours / final_recon outputs + centred LN statistics + loss partials
+// pass A: masks / colours / final_recon outputs + LN statistics + loss partials.
+// Every thread centres its sums on the values of ITS first pixel (fp32, no cancellation), converts them to raw fp64
+// sums (sum x = S1 + n s, sum x^2 = S2 + 2 s S1 + n s^2) and the block reduces those in a fixed order.
 // ---------------------------------------------------------------------------------------------------------
 template <int KMAX>
 __global__ void __launch_bounds__(MIX_THREADS)
@@ -99,28 +103,13 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
   const float invB = 1.f / (float)B;
   const float* img = io.image ? io.image + (size_t)b * io.image_bstride : nullptr;
   StatsLayout L = stats_layout(B, K, D);
-  __shared__ float s_shift[3 * 16 + 1];
-  __shared__ float s_red[MIX_THREADS / 32][6 * 16 + 4];
+  __shared__ double s_red[MIX_THREADS / 32][6 * 16 + 4];
+  if (want_stats && tile == 0 && b == 0 && tid == 0) *reinterpret_cast<unsigned*>(io.stats + L.counter) = 0u;
 
   Pixel<KMAX> px;
-  if (want_stats) {
-    if (tid == 0) {  // centring references: the quantities at pixel 0 of this sample
-      px.load(io.dec_out, img, b, K, DD, 0);
-      px.compute(K, invB);
-      for (int k = 0; k < K; ++k) {
-        s_shift[3 * k] = px.mask_grad(k);
-        s_shift[3 * k + 1] = px.leave_out(k);
-        s_shift[3 * k + 2] = px.xh_coef(k) * (px.v[k].x - px.x0);
-      }
-      s_shift[3 * K] = px.P;
-      if (tile == 0)
-        for (int i = 0; i < 3 * K + 1; ++i) io.stats[L.shifts + (size_t)b * (3 * K + 1) + i] = s_shift[i];
-    }
-    __syncthreads();
-  }
-
-  float acc[6 * KMAX];
-  float accP = 0.f, accP2 = 0.f, accLog = 0.f, accSq = 0.f;
+  float acc[6 * KMAX], shift[3 * KMAX];
+  float accP = 0.f, accP2 = 0.f, shiftP = 0.f, accLog = 0.f, accSq = 0.f;
+  int npix = 0;
 #pragma unroll
   for (int i = 0; i < 6 * KMAX; ++i) acc[i] = 0.f;
 
@@ -141,12 +130,15 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
         }
         r0 += px.v[k].x * px.m[k]; r1 += px.v[k].y * px.m[k]; r2 += px.v[k].z * px.m[k];
         if (want_stats) {
-          float d = px.mask_grad(k) - s_shift[3 * k];
+          float mg = px.mask_grad(k), lo = px.leave_out(k), cf = px.xh_coef(k);
+          float x0 = cf * (px.v[k].x - px.x0), x1 = cf * (px.v[k].y - px.x1), x2 = cf * (px.v[k].z - px.x2);
+          if (npix == 0) { shift[3 * k] = mg; shift[3 * k + 1] = lo; shift[3 * k + 2] = x0; }
+          float d = mg - shift[3 * k];
           acc[6 * k] += d; acc[6 * k + 1] += d * d;
-          d = px.leave_out(k) - s_shift[3 * k + 1];
+          d = lo - shift[3 * k + 1];
           acc[6 * k + 2] += d; acc[6 * k + 3] += d * d;
-          float cf = px.xh_coef(k), sh = s_shift[3 * k + 2];
-          float e0 = cf * (px.v[k].x - px.x0) - sh, e1 = cf * (px.v[k].y - px.x1) - sh, e2 = cf * (px.v[k].z - px.x2) - sh;
+          float sh = shift[3 * k + 2];
+          float e0 = x0 - sh, e1 = x1 - sh, e2 = x2 - sh;
           acc[6 * k + 4] += e0 + e1 + e2; acc[6 * k + 5] += e0 * e0 + e1 * e1 + e2 * e2;
         }
       }
@@ -155,7 +147,8 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
       fr[0] = r0; fr[DD] = r1; fr[2 * DD] = r2;
     }
     if (want_stats) {
-      float d = px.P - s_shift[3 * K];
+      if (npix == 0) shiftP = px.P;
+      float d = px.P - shiftP;
       accP += d; accP2 += d * d;
       accLog += -logf(px.P + 1e-12f);
       if (mse_image) {
@@ -164,99 +157,108 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
         accSq += q0 * q0 + q1 * q1 + q2 * q2;
       }
     }
+    ++npix;
   }
   if (!want_stats) return;
 
-  // warp shuffle -> smem -> fp64 partial per (sample, tile)
+  // raw fp64 sums -> warp shuffle -> smem -> per-(sample, tile) partial
+  const double n1 = (double)npix, n3 = 3.0 * npix;
 #pragma unroll
-  for (int i = 0; i < 6 * KMAX; ++i)
-    if (i < 6 * K) {
-      float s = warp_sum(acc[i]);
-      if (lane == 0) s_red[warp][i] = s;
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        double sft = npix ? (double)shift[3 * k + g] : 0.0, nn = g == 2 ? n3 : n1;
+        double S1 = acc[6 * k + 2 * g], S2 = acc[6 * k + 2 * g + 1];
+        double sx = warp_sum_d(S1 + nn * sft), sxx = warp_sum_d(S2 + 2.0 * sft * S1 + nn * sft * sft);
+        if (lane == 0) { s_red[warp][6 * k + 2 * g] = sx; s_red[warp][6 * k + 2 * g + 1] = sxx; }
+      }
     }
   {
-    float s0 = warp_sum(accP), s1 = warp_sum(accP2), s2 = warp_sum(accLog), s3 = warp_sum(accSq);
+    double sft = npix ? (double)shiftP : 0.0;
+    double s0 = warp_sum_d((double)accP + n1 * sft), s1 = warp_sum_d((double)accP2 + 2.0 * sft * accP + n1 * sft * sft);
+    double s2 = warp_sum_d((double)accLog), s3 = warp_sum_d((double)accSq);
     if (lane == 0) { s_red[warp][6 * K] = s0; s_red[warp][6 * K + 1] = s1; s_red[warp][6 * K + 2] = s2; s_red[warp][6 * K + 3] = s3; }
   }
   __syncthreads();
   if (tid < L.nq) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < MIX_THREADS / 32; ++w) s += (double)s_red[w][tid];
+    for (int w = 0; w < MIX_THREADS / 32; ++w) s += s_red[w][tid];
     reinterpret_cast<double*>(io.stats + L.partial)[((size_t)b * L.tiles + tile) * L.nq + tid] = s;
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// finalize: LN statistics per (b,k,group), loss scalars, KL (single CTA; O(B*K*Rs) work)
-// ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float softplus_std(float x) { return sqrtf(logf(1.f + expf(fminf(x, 80.f))) + 1e-5f); }
 
-__global__ void __launch_bounds__(256) mix_finalize_kernel(Op3MixtureIO io, int B, int K, int D, int Rs, float beta,
-                                                           int want_mse) {
+// LN statistics of sample b, group q in [0, 3K] (q = 3K: the pixel-likelihood group): (mean, 1/(std + 1e-5)), unbiased std
+__device__ __forceinline__ float2 ln_stat_from_partials(const double* part, const StatsLayout& L, int b, int K, int q, int DD) {
+  int k = q / 3, g = q % 3;
+  int qi = q == 3 * K ? 6 * K : 6 * k + 2 * g;
+  double s = 0.0, s2 = 0.0;
+  for (int t = 0; t < L.tiles; ++t) {
+    s += part[((size_t)b * L.tiles + t) * L.nq + qi];
+    s2 += part[((size_t)b * L.tiles + t) * L.nq + qi + 1];
+  }
+  double n = (q != 3 * K && g == 2) ? 3.0 * DD : (double)DD;
+  double mean = s / n;
+  double var = (s2 - s * s / n) / (n - 1.0);
+  if (var < 0.0) var = 0.0;
+  return make_float2((float)mean, 1.f / ((float)sqrt(var) + 1e-5f));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// loss scalars: one CTA per sample (clog, squared recon error from the partials; KL over K*Rs elements), the last CTA
+// to finish sums the per-sample values in a fixed order.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mix_loss_kernel(Op3MixtureIO io, int B, int K, int D, int Rs, float beta, int want_mse) {
   StatsLayout L = stats_layout(B, K, D);
   const double* part = reinterpret_cast<const double*>(io.stats + L.partial);
-  const int tid = threadIdx.x;
-  const double n1 = (double)D * D;
-  __shared__ double s_red[256];
-  // LN statistics
-  for (int i = tid; i < B * (3 * K + 1); i += 256) {
-    int b = i / (3 * K + 1), q = i % (3 * K + 1);
-    int k = q / 3, g = q % 3;   // for q == 3K: the P group
-    int qi = q == 3 * K ? 6 * K : 6 * k + 2 * g;
-    double s = 0.0, s2 = 0.0;
-    for (int t = 0; t < L.tiles; ++t) {
-      s += part[((size_t)b * L.tiles + t) * L.nq + qi];
-      s2 += part[((size_t)b * L.tiles + t) * L.nq + qi + 1];
-    }
-    double n = (q != 3 * K && g == 2) ? 3.0 * n1 : n1;
-    double mean = (double)io.stats[L.shifts + i] + s / n;
-    double var = (s2 - s * s / n) / (n - 1.0);
-    if (var < 0.0) var = 0.0;
-    float stdv = (float)sqrt(var);
-    size_t o = q == 3 * K ? L.ln + (size_t)B * K * 6 + (size_t)b * 2 : L.ln + ((size_t)(b * K + k) * 3 + g) * 2;
-    io.stats[o] = (float)mean;
-    io.stats[o + 1] = 1.f / (stdv + 1e-5f);
-  }
-  // clog and squared reconstruction error
-  double cl = 0.0, sq = 0.0;
-  for (int i = tid; i < B * L.tiles; i += 256) {
-    cl += part[(size_t)i * L.nq + 6 * K + 2];
-    sq += part[(size_t)i * L.nq + 6 * K + 3];
-  }
-  // KL(post || prior), diagonal Gaussians
+  double* samp = reinterpret_cast<double*>(io.stats + L.sample);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ double s_red[128];
+  __shared__ bool s_last;
   double kl = 0.0;
-  for (int i = tid; i < B * K * Rs; i += 256) {
-    float sq_ = softplus_std(io.post_l2[i]), spv = softplus_std(io.prior_l2[i]);
-    float dm = io.post_l1[i] - io.prior_l1[i];
+  for (int i = tid; i < K * Rs; i += 128) {
+    size_t o = (size_t)b * K * Rs + i;
+    float sq_ = softplus_std(io.post_l2[o]), spv = softplus_std(io.prior_l2[o]);
+    float dm = io.post_l1[o] - io.prior_l1[o];
     kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
   }
-  double vals[3] = {cl, kl, sq};
-  double outv[3];
-  for (int j = 0; j < 3; ++j) {
-    s_red[tid] = vals[j];
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) s_red[tid] += s_red[tid + o];
-      __syncthreads();
-    }
-    outv[j] = s_red[0];
+  s_red[tid] = kl;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) s_red[tid] += s_red[tid + o];
     __syncthreads();
   }
   if (tid == 0) {
-    float clog = (float)(outv[0] / B), klv = (float)(outv[1] / B);
+    double cl = 0.0, sq = 0.0;
+    for (int t = 0; t < L.tiles; ++t) {
+      cl += part[((size_t)b * L.tiles + t) * L.nq + 6 * K + 2];
+      sq += part[((size_t)b * L.tiles + t) * L.nq + 6 * K + 3];
+    }
+    samp[b * 3] = cl; samp[b * 3 + 1] = s_red[0]; samp[b * 3 + 2] = sq;
+    __threadfence();
+    unsigned done = atomicAdd(reinterpret_cast<unsigned*>(io.stats + L.counter), 1u);
+    s_last = done == (unsigned)B - 1;
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    __threadfence();
+    double cl = 0.0, klv = 0.0, sq = 0.0;
+    for (int i = 0; i < B; ++i) { cl += samp[i * 3]; klv += samp[i * 3 + 1]; sq += samp[i * 3 + 2]; }
+    float clog = (float)(cl / B), klf = (float)(klv / B);
     io.losses[0] = clog;
-    io.losses[1] = klv;
-    io.losses[2] = clog + beta * klv;
-    io.losses[3] = want_mse ? (float)(outv[2] / ((double)B * 3.0 * n1)) : 0.f;
+    io.losses[1] = klf;
+    io.losses[2] = clog + beta * klf;
+    io.losses[3] = want_mse ? (float)(sq / ((double)B * 3.0 * D * D)) : 0.f;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// pass B: refinement-input chunks (LayerNorm2D applied) + the gradient seed d total / d dec_out
+// pass B: refinement-input chunks (LayerNorm2D applied) + the gradient seed d total / d dec_out.
+// Each CTA derives the LayerNorm statistics of its sample from the fp64 partials (3K+1 tiny reductions).
 // ---------------------------------------------------------------------------------------------------------
-struct Ln2dParams { float g[6]; float b[6]; };  // groups: 0 mask_grad, 1 P, 2 leave_out, 3..5 x_hat rgb
-
 template <int KMAX>
 __global__ void __launch_bounds__(MIX_THREADS)
 mix_emit_kernel(Op3MixtureIO io, const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ g2,
@@ -265,9 +267,20 @@ mix_emit_kernel(Op3MixtureIO io, const float* __restrict__ g0, const float* __re
   const int DD = D * D;
   const int b = blockIdx.y;
   const int pix = blockIdx.x * MIX_THREADS + threadIdx.x;
-  if (pix >= DD) return;
   const float invB = 1.f / (float)B;
   StatsLayout L = stats_layout(B, K, D);
+  __shared__ float2 s_ln[3 * 16 + 1];
+  if (threadIdx.x < 3 * K + 1) {
+    float2 st = ln_stat_from_partials(reinterpret_cast<const double*>(io.stats + L.partial), L, b, K, threadIdx.x, DD);
+    s_ln[threadIdx.x] = st;
+    if (blockIdx.x == 0) {     // keep them for the backward pass
+      int q = threadIdx.x;
+      size_t o = q == 3 * K ? L.ln + (size_t)B * K * 6 + (size_t)b * 2 : L.ln + ((size_t)(b * K + q / 3) * 3 + q % 3) * 2;
+      io.stats[o] = st.x; io.stats[o + 1] = st.y;
+    }
+  }
+  __syncthreads();
+  if (pix >= DD) return;
   const float* img = io.image + (size_t)b * io.image_bstride;
   Pixel<KMAX> px;
   px.load(io.dec_out, img, b, K, DD, pix);
@@ -279,20 +292,20 @@ mix_emit_kernel(Op3MixtureIO io, const float* __restrict__ g0, const float* __re
 #pragma unroll
   for (int k = 0; k < KMAX; ++k)
     if (k < K) {
-      const float* ln = io.stats + L.ln + (size_t)(b * K + k) * 6;
+      const float2 l0 = s_ln[3 * k], l1 = s_ln[3 * k + 1], l2 = s_ln[3 * k + 2];
       size_t o = ((size_t)(b * K + k) * DD + pix);
       float mg = px.mask_grad(k), lo = px.leave_out(k), cf = px.xh_coef(k);
       float xh0 = cf * (px.v[k].x - px.x0), xh1 = cf * (px.v[k].y - px.x1), xh2 = cf * (px.v[k].z - px.x2);
-      float4 o1 = make_float4(px.m[k], px.post_mask(k), (mg - ln[0]) * ln[1] * ga0 + be0, (lo - ln[2]) * ln[3] * ga2 + be2);
-      float4 o2 = make_float4((xh0 - ln[4]) * ln[5] * ga3x + be3x, (xh1 - ln[4]) * ln[5] * ga3y + be3y,
-                              (xh2 - ln[4]) * ln[5] * ga3z + be3z, 0.f);
+      float4 o1 = make_float4(px.m[k], px.post_mask(k), (mg - l0.x) * l0.y * ga0 + be0, (lo - l1.x) * l1.y * ga2 + be2);
+      float4 o2 = make_float4((xh0 - l2.x) * l2.y * ga3x + be3x, (xh1 - l2.x) * l2.y * ga3y + be3y,
+                              (xh2 - l2.x) * l2.y * ga3z + be3z, 0.f);
       reinterpret_cast<float4*>(io.mix1)[o] = o1;
       reinterpret_cast<float4*>(io.mix2)[o] = o2;
       if (io.seed) reinterpret_cast<float4*>(io.seed)[o] = make_float4(xh0, xh1, xh2, px.m[k] * (mg - gPP));
     }
-  const float* lnP = io.stats + L.ln + (size_t)B * K * 6 + (size_t)b * 2;
+  const float2 lP = s_ln[3 * K];
   reinterpret_cast<float4*>(io.smp)[(size_t)b * DD + pix] =
-      make_float4(px.x0, px.x1, px.x2, (px.P - lnP[0]) * lnP[1] * ga1 + be1);
+      make_float4(px.x0, px.x1, px.x2, (px.P - lP.x) * lP.y * ga1 + be1);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -373,11 +386,13 @@ mix_bwd_kernel(Op3MixtureIO io, float w_clog, const float4* __restrict__ d_in, f
   }
 }
 
-__global__ void mix_bwd_reduce_kernel(const double* __restrict__ gpart, int nblocks, Op3Params grads) {
-  int i = threadIdx.x;
-  if (i >= 12) return;
+// one warp per quantity (12 warps); lanes stride over the per-CTA partials, fixed shuffle tree => deterministic
+__global__ void __launch_bounds__(384) mix_bwd_reduce_kernel(const double* __restrict__ gpart, int nblocks, Op3Params grads) {
+  const int i = threadIdx.x / 32, lane = threadIdx.x % 32;
   double s = 0.0;
-  for (int k = 0; k < nblocks; ++k) s += gpart[(size_t)k * 12 + i];
+  for (int k = lane; k < nblocks; k += 32) s += gpart[(size_t)k * 12 + i];
+  s = warp_sum_d(s);
+  if (lane != 0) return;
   float v = (float)s;
   switch (i) {
     case 0: grads.ln2d_gamma[0][0] += v; break;
@@ -426,9 +441,6 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   if (!want_stats) return OP3_OK;
-  mix_finalize_kernel<<<1, 256, 0, st>>>(*io, B, K, D, d->Rs, d->beta, io->mse_image != nullptr);
-  OP3_COUNT_LAUNCH();
-  OP3_LAUNCH_CHECK();
   if (emit) {
     dim3 ge(ceil_div(D * D, MIX_THREADS), B);
 #define OP3_MIX_EMIT(KM)                                                                                         \
@@ -440,6 +452,9 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
     OP3_COUNT_LAUNCH();
     OP3_LAUNCH_CHECK();
   }
+  mix_loss_kernel<<<B, 128, 0, st>>>(*io, B, K, D, d->Rs, d->beta, io->mse_image != nullptr);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
   return OP3_OK;
 }
 
@@ -454,7 +469,6 @@ extern "C" int op3_mixture_bwd(const Op3Dims* d, const Op3MixtureIO* io, float w
   StatsLayout L = stats_layout(B, K, D);
   ProfScope prof(st, KID_MIXTURE, (14.0 * K + 3) * 4.0 * B * D * D);
   dim3 g(ceil_div(D * D, MIX_THREADS), B);
-  OP3_REQUIRE((size_t)g.x * B * 12 <= (size_t)B * L.tiles * STATS_PPT * 12, "op3_mixture_bwd: partial buffer too small");
   double* gpart = reinterpret_cast<double*>(io->stats + L.gpart);
 #define OP3_MIX_BWD(KM)                                                                                  \
   mix_bwd_kernel<KM><<<g, MIX_THREADS, 0, st>>>(*io, w_clog, reinterpret_cast<const float4*>(d_in),       \
@@ -464,7 +478,7 @@ extern "C" int op3_mixture_bwd(const Op3Dims* d, const Op3MixtureIO* io, float w
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   if (d_in) {
-    mix_bwd_reduce_kernel<<<1, 32, 0, st>>>(gpart, (int)(g.x * B), *grads);
+    mix_bwd_reduce_kernel<<<1, 384, 0, st>>>(gpart, (int)(g.x * B), *grads);
     OP3_COUNT_LAUNCH();
     OP3_LAUNCH_CHECK();
   }
