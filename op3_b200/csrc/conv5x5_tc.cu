@@ -7,13 +7,19 @@
 //   operand of tap (ky,kx) is the SAME buffer with the descriptor start address advanced by (ky*(D+4)+kx)*16 bytes
 //   (verified on B200 by tests/probes/probe_tcgen05.cu): no im2col copy is ever made; the 4 pad columns of each
 //   row produce garbage outputs that the epilogue drops.
-// * Accumulators live in TMEM (one 128-lane x N-column block per tile); one elected thread issues all MMAs.
-// * kind::tf32 truncates fp32 operands to their top 19 bits (measured).  PRECISION 3xTF32 ("parity mode") therefore
-//   needs only ONE extra operand copy: a_lo = a - trunc(a), produced in shared memory by the loader threads, and
-//   weights pre-split on the host side of the kernel (op3_prepare):  D += a*[w_hi;w_lo] (one MMA, N = 2*cout, the two
-//   halves are summed in the epilogue) ; D[:, :cout] += a_lo*w_hi.   1xTF32 ("speed mode") issues a*w only.
-// * Loader threads use cp.async (zero-fill for the conv padding / image borders), make their writes visible to the
-//   async proxy (fence.proxy.async) and hand stages to the MMA thread through mbarriers; tcgen05.commit hands them back.
+// * Persistent, warp-specialised: one CTA per SM loops over (image, tile-group) work items.
+//     warps 0-7  epilogue   TMEM -> registers -> bias/ELU (or x ELU' for dgrad) -> coalesced float4 stores; two warps
+//                           per TMEM lane quadrant alternate over the tiles of an item
+//     warp  8    MMA issuer one elected thread issues every tcgen05.mma; tcgen05.commit releases smem stages and
+//                           publishes accumulators
+//     warps 9-12 loaders    cp.async (zero fill = conv padding) -> round to tf32 in place -> fence.proxy.async -> mbarrier
+//   Accumulators are double buffered in TMEM (2 x G tiles x N columns <= 512) so the epilogue of item i overlaps the
+//   MMAs of item i+1; operand stages form an NSTAGE ring that runs across item boundaries.
+// * kind::tf32 truncates fp32 operands to their top 19 bits (measured), which biases products; all operands are
+//   therefore rounded to nearest tf32 before the tensor core sees them (weights in op3_prepare, activations by the
+//   loaders).  3xTF32 ("parity mode"): a_hi*[w_hi;w_lo] is ONE MMA with N = 2*cout (the halves are summed in the
+//   epilogue), a_lo*w_hi a second one.  1xTF32 ("speed mode") issues a_hi*w_hi only.  Narrow-N MMAs are operand-fetch
+//   bound (~48 cycles for any N <= 64, measured), so the N = 2*cout stacking is free.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -21,175 +27,198 @@ namespace op3 {
 
 namespace {
 
-constexpr int TC_THREADS = 160;        // warps 0-3: loaders + epilogue (TMEM lane quadrants), warp 4: MMA issuer
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_THREADS = 128;
+constexpr int TC_THREADS = (LOAD_WARP0 + 4) * 32;
 
 template <int NOUT, bool SPLIT3>
 struct TcCfg {
-  static constexpr int GMAX = SPLIT3 ? 4 : 8;                    // max tiles per CTA (runtime G <= GMAX)
-  static constexpr int NB = SPLIT3 ? 2 * NOUT : NOUT;            // B rows per tap slab
-  static constexpr int ACC = NB;                                 // TMEM columns per tile
+  static constexpr int NB = SPLIT3 ? 2 * NOUT : NOUT;            // B rows per tap slab = TMEM columns per tile
+  static constexpr int GMAX = 256 / NB;                          // tiles per item: two accumulator buffers in 512 columns
   static constexpr int NSTAGE = SPLIT3 ? 2 : (NOUT == 64 ? 2 : 3);
-  static constexpr int TMEM_COLS = (GMAX * ACC <= 32) ? 32 : (GMAX * ACC <= 64) ? 64 : (GMAX * ACC <= 128) ? 128 : (GMAX * ACC <= 256) ? 256 : 512;
-  static_assert(GMAX * ACC <= 512, "accumulators exceed TMEM");
+  static_assert(GMAX >= 1 && 2 * GMAX * NB <= 512, "accumulators exceed TMEM");
 };
 
 template <int NOUT, bool SPLIT3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv5x5_tc_kernel(ConvInput in, int D, int G, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
-                  float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
+conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ wt, const float* __restrict__ bias,
+                  int cout_real, float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
                   const float4* __restrict__ ref) {
   using Cfg = TcCfg<NOUT, SPLIT3>;
-  constexpr int NB = Cfg::NB, ACC = Cfg::ACC;
+  constexpr int NB = Cfg::NB, NSTAGE = Cfg::NSTAGE;
   const int P = D + 4;                                   // padded row pitch
   const int PH = 128 * G + 4 * P + 4;                    // halo pixels of one group
   const int tiles_img = (D * P + 127) / 128;
   const int groups_img = (tiles_img + G - 1) / G;
-  const int n = blockIdx.x / groups_img, grp = blockIdx.x % groups_img;
-  const int tile0 = grp * G;
-  const int ntile = min(G, tiles_img - tile0);
-  const int q0 = tile0 * 128;                            // first padded-linear output pixel of this group
+  const int n_items = N * groups_img;
   const int ngroups = (in.total_chunks + 1) / 2;         // K groups of 8 channels
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
-  // ---- shared memory carve-up: per stage [A raw | A lo (3x) | W slab]
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int a_bytes = 2 * PH * 16;
   const int w_bytes = 25 * 2 * NB * 16;
   const int stage_bytes = a_bytes * (SPLIT3 ? 2 : 1) + w_bytes;
-  constexpr int NSTAGE = Cfg::NSTAGE;
-  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], accum_bar;
+  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[NOUT];
 
+  if (tid < NOUT) s_bias[tid] = (bias != nullptr && tid < cout_real) ? bias[tid] : 0.f;
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS * 32); }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
+  if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 4) {
+  if (warp >= LOAD_WARP0) {
     // ===================== loaders =====================
-    for (int cg = 0; cg < ngroups; ++cg) {
-      const int s = cg % NSTAGE;
-      if (cg >= NSTAGE) mbar_wait(&empty_bar[s], ((cg / NSTAGE) - 1) & 1);
-      uint8_t* st = smem_raw + (size_t)s * stage_bytes;
-      float4* a_raw = reinterpret_cast<float4*>(st);
-      float4* a_lo = reinterpret_cast<float4*>(st + a_bytes);
-      float4* w_s = reinterpret_cast<float4*>(st + a_bytes * (SPLIT3 ? 2 : 1));
-      // weights: contiguous slab of this K group
-      const float4* wsrc = reinterpret_cast<const float4*>(wt) + (size_t)cg * (25 * 2 * NB);
-      for (int e = tid; e < 25 * 2 * NB; e += 128) cp_async16(&w_s[e], &wsrc[e], true);
-      // activations: 2 k-chunks x PH halo pixels
-      for (int kc = 0; kc < 2; ++kc) {
-        const int c = cg * 2 + kc;
-        const float4* src = c < in.total_chunks ? tc_src_chunk_ptr(in, c, n, D) : nullptr;
-        for (int h = tid; h < PH; h += 128) {
-          int q = q0 + h;
+    const int lt = tid - LOAD_WARP0 * 32;
+    int it = 0;                                          // running stage counter across items
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int n = item / groups_img, grp = item % groups_img;
+      const int q0 = grp * G * 128;
+      for (int cg = 0; cg < ngroups; ++cg, ++it) {
+        const int s = it % NSTAGE;
+        if (it >= NSTAGE) mbar_wait(&empty_bar[s], ((it / NSTAGE) - 1) & 1);
+        uint8_t* st = smem_raw + (size_t)s * stage_bytes;
+        float4* a_raw = reinterpret_cast<float4*>(st);
+        float4* a_lo = reinterpret_cast<float4*>(st + a_bytes);
+        float4* w_s = reinterpret_cast<float4*>(st + a_bytes * (SPLIT3 ? 2 : 1));
+        const float4* wsrc = reinterpret_cast<const float4*>(wt) + (size_t)cg * (25 * 2 * NB);
+        for (int e = lt; e < 25 * 2 * NB; e += LOAD_THREADS) cp_async16(&w_s[e], &wsrc[e], true);
+        for (int kc = 0; kc < 2; ++kc) {
+          const int c = cg * 2 + kc;
+          const float4* src = c < in.total_chunks ? tc_src_chunk_ptr(in, c, n, D) : nullptr;
+          int q = q0 + lt;
           int iy = q / P - 2, ix = q % P - 2;
-          bool ok = src != nullptr && iy >= 0 && iy < D && ix >= 0 && ix < D;
-          cp_async16(&a_raw[kc * PH + h], ok ? src + (size_t)iy * D + ix : reinterpret_cast<const float4*>(wt), ok);
+          for (int h = lt; h < PH; h += LOAD_THREADS) {
+            bool ok = src != nullptr && iy >= 0 && iy < D && ix >= 0 && ix < D;
+            cp_async16(&a_raw[kc * PH + h], ok ? src + (size_t)iy * D + ix : reinterpret_cast<const float4*>(wt), ok);
+            ix += LOAD_THREADS;                          // advance LOAD_THREADS pixels in padded-linear space
+            while (ix >= P - 2) { ix -= P; ++iy; }
+          }
         }
+        cp_async_commit();
+        cp_async_wait<0>();
+        // round the granules this thread loaded itself to tf32 (and split off a_lo in 3xTF32 mode)
+        for (int kc = 0; kc < 2; ++kc)
+          for (int h = lt; h < PH; h += LOAD_THREADS) {
+            float4 v = a_raw[kc * PH + h];
+            float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+            a_raw[kc * PH + h] = hi;
+            if (SPLIT3)
+              a_lo[kc * PH + h] = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+          }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[s]);
       }
-      cp_async_commit();
-      cp_async_wait<0>();
-      // The tensor core TRUNCATES fp32 operands to tf32, which biases every product towards zero.  Each loader thread
-      // therefore rounds the granules it loaded itself to nearest tf32 in place (a_hi) and, in 3xTF32 mode, also
-      // stores a_lo = rn_tf32(a - a_hi); both are exactly representable, so the hardware truncation becomes a no-op.
-      for (int kc = 0; kc < 2; ++kc)
-        for (int h = tid; h < PH; h += 128) {
-          float4 v = a_raw[kc * PH + h];
-          float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-          a_raw[kc * PH + h] = hi;
-          if (SPLIT3)
-            a_lo[kc * PH + h] = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
-        }
-      fence_proxy_async();
-      mbar_arrive(&full_bar[s]);
     }
-    // ===================== epilogue =====================
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    for (int t = 0; t < ntile; ++t) {
-      const int p = q0 + 128 * t + warp * 32 + lane;
-      const int y = p / P, x = p % P;
-      const bool valid = y < D && x < D;
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * ACC);
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_tf32(128, NB);
+      const uint32_t idesc2 = make_idesc_tf32(128, NOUT);
+      int it = 0, j = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+        const int grp = item % groups_img;
+        const int ntile = min(G, tiles_img - grp * G);
+        const int buf = j & 1;
+        if (j >= 2) mbar_wait(&acc_empty[buf], ((j >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t dbase = tmem_base + (uint32_t)(buf * 256);
+        for (int cg = 0; cg < ngroups; ++cg, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem_raw + (size_t)s * stage_bytes);
+          const uint64_t ad = make_smem_desc(st, PH, 8);
+          const uint64_t ald = make_smem_desc(st + a_bytes, PH, 8);
+          const uint64_t bd = make_smem_desc(st + a_bytes * (SPLIT3 ? 2 : 1), NB, 8);
+          const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
+          const uint32_t al_lo32 = (uint32_t)ald, al_hi32 = (uint32_t)(ald >> 32);
+          const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
+          for (int t = 0; t < ntile; ++t) {
+            const uint32_t dcol = dbase + (uint32_t)(t * NB);
 #pragma unroll
-      for (int c0 = 0; c0 < NOUT; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + c0, v);
+            for (int tap = 0; tap < 25; ++tap) {
+              const uint32_t aoff = (uint32_t)(128 * t + (tap / 5) * P + (tap % 5));   // 16-byte units
+              const uint32_t boff = (uint32_t)(tap * 2 * NB);
+              mma_tf32(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
+              if (SPLIT3) mma_tf32(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
+            }
+          }
+          tc_commit(&empty_bar[s]);                      // smem stage free once these MMAs have read it
+        }
+        tc_commit(&acc_full[buf]);                       // accumulators of this item complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warp % 4 = TMEM lane quadrant, warp / 4 = tile parity) =====================
+    const int quad = warp & 3, half = warp >> 2;
+    int j = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+      const int n = item / groups_img, grp = item % groups_img;
+      const int ntile = min(G, tiles_img - grp * G);
+      const int q0 = grp * G * 128;
+      const int buf = j & 1;
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      for (int t = half; t < ntile; t += 2) {
+        const int p = q0 + 128 * t + quad * 32 + lane;
+        const int y = p / P, x = p % P;
+        const bool valid = y < D && x < D;
+        const size_t obase = (((size_t)n * out_planes + out_chunk0) * D + (valid ? y : 0)) * D + (valid ? x : 0);
+        const size_t plane = (size_t)D * D;
+        // prefetch the ELU' reference values of this pixel (independent loads, latency overlapped with the TMEM reads)
+        float4 ra[NOUT / 4];
+        if (epi == EPI_MUL_ELUGRAD) {
+#pragma unroll
+          for (int c4 = 0; c4 < NOUT / 4; ++c4)
+            ra[c4] = (valid && c4 < out_chunks) ? __ldg(&ref[obase + c4 * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + t * NB);
+        float v[NOUT];
+#pragma unroll
+        for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + c0, v + c0);
         if (SPLIT3) {
-          float u[16];
-          tmem_ld16(trow + NOUT + c0, u);
+          float u[NOUT];
+#pragma unroll
+          for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + NOUT + c0, u + c0);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += u[j];
+          for (int i = 0; i < NOUT; ++i) v[i] += u[i];
         } else {
           tmem_ld_wait();
         }
         if (valid) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const int c4 = c0 / 4 + j4;
+          for (int c4 = 0; c4 < NOUT / 4; ++c4) {
             if (c4 >= out_chunks) continue;
-            float4 r = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-            if (bias) {
-              const int cb = c4 * 4;
-              r.x += cb < cout_real ? bias[cb] : 0.f;
-              r.y += cb + 1 < cout_real ? bias[cb + 1] : 0.f;
-              r.z += cb + 2 < cout_real ? bias[cb + 2] : 0.f;
-              r.w += cb + 3 < cout_real ? bias[cb + 3] : 0.f;
-            }
-            const size_t o = (((size_t)n * out_planes + out_chunk0 + c4) * D + y) * D + x;
+            float4 r = make_float4(v[c4 * 4] + s_bias[c4 * 4], v[c4 * 4 + 1] + s_bias[c4 * 4 + 1],
+                                   v[c4 * 4 + 2] + s_bias[c4 * 4 + 2], v[c4 * 4 + 3] + s_bias[c4 * 4 + 3]);
             if (epi == EPI_ELU) {
               r.x = elu_f(r.x); r.y = elu_f(r.y); r.z = elu_f(r.z); r.w = elu_f(r.w);
             } else if (epi == EPI_MUL_ELUGRAD) {
-              float4 a = ref[o];
-              r.x *= elu_grad_from_out(a.x); r.y *= elu_grad_from_out(a.y);
-              r.z *= elu_grad_from_out(a.z); r.w *= elu_grad_from_out(a.w);
+              r.x *= elu_grad_from_out(ra[c4].x); r.y *= elu_grad_from_out(ra[c4].y);
+              r.z *= elu_grad_from_out(ra[c4].z); r.w *= elu_grad_from_out(ra[c4].w);
             }
-            out[o] = r;
+            out[obase + c4 * plane] = r;
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);                      // this thread is done reading the buffer
     }
-  } else if (lane == 0) {
-    // ===================== MMA issuer (one thread) =====================
-    const uint32_t idesc1 = make_idesc_tf32(128, NB);
-    const uint32_t idesc2 = make_idesc_tf32(128, NOUT);
-    for (int cg = 0; cg < ngroups; ++cg) {
-      const int s = cg % NSTAGE;
-      mbar_wait(&full_bar[s], (cg / NSTAGE) & 1);
-      tc_fence_after();
-      const uint32_t st = smem_u32(smem_raw + (size_t)s * stage_bytes);
-      const uint64_t ad = make_smem_desc(st, PH, 8);
-      const uint64_t ald = make_smem_desc(st + a_bytes, PH, 8);
-      const uint64_t bd = make_smem_desc(st + a_bytes * (SPLIT3 ? 2 : 1), NB, 8);
-      const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
-      const uint32_t al_lo32 = (uint32_t)ald, al_hi32 = (uint32_t)(ald >> 32);
-      const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
-      for (int t = 0; t < ntile; ++t) {
-        const uint32_t dcol = tmem_base + (uint32_t)(t * ACC);
-#pragma unroll
-        for (int tap = 0; tap < 25; ++tap) {
-          const uint32_t aoff = (uint32_t)(128 * t + (tap / 5) * P + (tap % 5));   // 16-byte units
-          const uint32_t boff = (uint32_t)(tap * 2 * NB);
-          mma_tf32(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
-          if (SPLIT3) mma_tf32(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
-        }
-      }
-      if (cg + 1 < ngroups) tc_commit(&empty_bar[s]);
-    }
-    tc_commit(&accum_bar);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
+
+int g_num_sms = 0;
 
 template <int NOUT, bool SPLIT3>
 int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* wt, const float* bias, int cout_real,
@@ -209,10 +238,17 @@ int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* w
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_tc_kernel<NOUT, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    OP3_CHECK(cudaGetDevice(&dev));
+    OP3_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   const int tiles_img = (D * P + 127) / 128;
   const int groups_img = (tiles_img + G - 1) / G;
-  conv5x5_tc_kernel<NOUT, SPLIT3><<<N * groups_img, TC_THREADS, smem, st>>>(in, D, G, wt, bias, cout_real, out, out_planes,
-                                                                          out_chunk0, out_chunks, epi, ref);
+  const int n_items = N * groups_img;
+  const int grid = n_items < g_num_sms ? n_items : g_num_sms;      // persistent: one CTA per SM
+  conv5x5_tc_kernel<NOUT, SPLIT3><<<grid, TC_THREADS, smem, st>>>(in, N, D, G, wt, bias, cout_real, out, out_planes,
+                                                                  out_chunk0, out_chunks, epi, ref);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
@@ -228,8 +264,8 @@ size_t conv5x5_tc_weight_floats(int cin_pad, int cout) {
 }
 
 // Weight slab layout consumed by the kernel (built by op3_prepare): [K group of 8 ci][tap 25][k-chunk 2][row NB][4 ci]
-// with NB = nout rows (1xTF32: raw fp32) or 2*nout rows (3xTF32: trunc_tf32(w) rows, then w - trunc rows).  cout = 64 in
-// 3xTF32 mode is stored and run as two independent halves of 32 output channels (TMEM / smem budget).
+// with NB = nout rows (1xTF32: rn_tf32(w)) or 2*nout rows (3xTF32: hi rows, then lo rows).  cout = 64 in 3xTF32 mode is
+// stored and run as two independent halves of 32 output channels (TMEM / smem budget).
 int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float* wt,
                        const float* bias, float4* out, int epi, const float4* elu_ref) {
   if (N <= 0) return OP3_OK;
@@ -249,7 +285,6 @@ int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvI
   if (nout == 32) return launch_tc<32, false>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
   return launch_tc<64, false>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
 }
-
 
 // fp32 CUDA-core kernel in exact mode, tcgen05 kernel otherwise
 int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
