@@ -299,6 +299,128 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int S, in
   else if (dbias) dbias[i - n_w] += s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad v2 (cout >= 32): a thread owns ALL 25 taps of one input channel x 4 output channels (100 accumulators) and
+// walks one tile row with a 5x5 sliding register window: per pixel 5 LDS.32 + 1 LDS.128 feed 100 FMAs, the window
+// loads are conflict-free (lanes = 4 consecutive channels x broadcast) -> FMA-pipe bound instead of smem bound.
+// ------------------------------------------------------------------------------------------------
+template <int COUT, int WR2>
+__global__ void __launch_bounds__(COUT * WR2)
+conv5x5_wgrad2_kernel(ConvInput in, int N, int D, const float4* __restrict__ dpre, float* __restrict__ partial) {
+  constexpr int NSUB = COUT / 4;            // float4 groups of output channels
+  constexpr int GT = 4 * NSUB;              // threads per pixel group (= COUT)
+  constexpr int NT = GT * WR2;              // one pixel group per tile row
+  constexpr int IN_F4 = (WR2 + 4) * HW;
+  constexpr int DP_F4 = NSUB * WR2 * TW;
+  extern __shared__ float4 smem[];
+  float4* s_in[2] = {smem, smem + IN_F4 + DP_F4};
+  float4* s_dp[2] = {smem + IN_F4, smem + 2 * IN_F4 + DP_F4};
+
+  const int tid = threadIdx.x;
+  const int pg = tid / GT, rem = tid % GT, sub = rem / 4, ci = rem % 4;
+  const int c = blockIdx.y;
+  const int tiles_x = (D + TW - 1) / TW, tiles_y = D / WR2;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const long long total_tiles = (long long)N * tiles_per_img;
+
+  float acc[25][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 25; ++t)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[t][o] = 0.f;
+
+  auto load_tile = [&](long long t, int stage) {
+    int n = (int)(t / tiles_per_img);
+    int ti = (int)(t % tiles_per_img);
+    int tx0 = (ti % tiles_x) * TW, ty0 = (ti / tiles_x) * WR2;
+    const float4* src = src_chunk_ptr(in, c, n, D);
+    for (int e = tid; e < IN_F4; e += NT) {
+      int yy = e / HW, xx = e % HW;
+      int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
+      bool ok = gy >= 0 && gy < D && gx >= 0 && gx < D;
+      cp_async16(&s_in[stage][e], ok ? src + (size_t)gy * D + gx : src, ok);
+    }
+    for (int e = tid; e < DP_F4; e += NT) {
+      int ch = e / (WR2 * TW), p = e % (WR2 * TW);
+      int gy = ty0 + p / TW, gx = tx0 + p % TW;
+      bool ok = gy < D && gx < D;
+      const float4* sp = dpre + (((size_t)n * NSUB + ch) * D + (ok ? gy : 0)) * D + (ok ? gx : 0);
+      cp_async16(&s_dp[stage][e], sp, ok);
+    }
+    cp_async_commit();
+  };
+
+  long long t = blockIdx.x;
+  int stage = 0;
+  if (t < total_tiles) load_tile(t, 0);
+  for (; t < total_tiles; t += gridDim.x, stage ^= 1) {
+    long long tn = t + gridDim.x;
+    if (tn < total_tiles) {
+      load_tile(tn, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* tin = reinterpret_cast<const float*>(s_in[stage]) + ci;
+    const float4* tdp = s_dp[stage] + (size_t)(sub * WR2 + pg) * TW;
+    float w[5][5];                           // w[ky][slot]: input window, slot (x + kx) % 5 holds column x + kx
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[ky][k] = tin[(size_t)((pg + ky) * HW + k) * 4];
+#pragma unroll 1
+    for (int x0 = 0; x0 < TW; x0 += 5) {
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int x = x0 + u;
+        if (x < TW) {
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) w[ky][(u + 4) % 5] = tin[(size_t)((pg + ky) * HW + x + 4) * 4];
+          const float4 d = tdp[x];
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+              const float a = w[ky][(u + kx) % 5];
+              acc[ky * 5 + kx][0] = fmaf(a, d.x, acc[ky * 5 + kx][0]);
+              acc[ky * 5 + kx][1] = fmaf(a, d.y, acc[ky * 5 + kx][1]);
+              acc[ky * 5 + kx][2] = fmaf(a, d.z, acc[ky * 5 + kx][2]);
+              acc[ky * 5 + kx][3] = fmaf(a, d.w, acc[ky * 5 + kx][3]);
+            }
+          if (c == 0 && ci == 0) { bsum[0] += d.x; bsum[1] += d.y; bsum[2] += d.z; bsum[3] += d.w; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // cross pixel-group reduction through smem (fixed order), one partial slab per CTA
+  float* red = reinterpret_cast<float*>(smem);  // [WR2][GT][104]
+  constexpr int PER_T = 104;
+#pragma unroll
+  for (int tp = 0; tp < 25; ++tp)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) red[(size_t)(pg * GT + rem) * PER_T + tp * 4 + o] = acc[tp][o];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) red[(size_t)(pg * GT + rem) * PER_T + 100 + o] = bsum[o];
+  __syncthreads();
+  const int cin_pad = in.total_chunks * 4;
+  float* slab = partial + (size_t)blockIdx.x * (25 * cin_pad * COUT + COUT);
+  for (int e = pg; e < PER_T; e += WR2) {      // the WR2 groups share the 104 outputs of each (ci, sub)
+    float sacc = 0.f;
+#pragma unroll
+    for (int p = 0; p < WR2; ++p) sacc += red[(size_t)(p * GT + rem) * PER_T + e];
+    if (e < 100) {
+      int tp = e / 4, o = e % 4;
+      slab[((size_t)tp * cin_pad + c * 4 + ci) * COUT + sub * 4 + o] = sacc;
+    } else if (c == 0 && ci == 0) {
+      slab[(size_t)25 * cin_pad * COUT + sub * 4 + (e - 100)] = sacc;
+    }
+  }
+}
+
 int wgrad_sets(int chunks) { int s = 296 / chunks; return s < 1 ? 1 : s; }
 
 template <int COUT, int COG, int PG>
@@ -321,6 +443,34 @@ int launch_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, const float
   if (S > total_tiles) S = (int)total_tiles;
   dim3 grid(S, chunks);
   conv5x5_wgrad_kernel<COUT, COG, PG><<<grid, NT, smem, st>>>(in, N, D, dpre, scratch);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  int n_w = 25 * chunks * 4 * COUT, n_b = COUT;
+  wgrad_reduce_kernel<<<ceil_div(n_w + n_b, 256), 256, 0, st>>>(scratch, S, n_w, n_b, dwt, dbias);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+template <int COUT, int WR2>
+int launch_wgrad2(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, float* scratch, float* dwt,
+                  float* dbias) {
+  constexpr int NT = COUT * WR2;
+  constexpr int IN_F4 = (WR2 + 4) * HW, DP_F4 = (COUT / 4) * WR2 * TW;
+  size_t smem = 2 * (size_t)(IN_F4 + DP_F4) * sizeof(float4);
+  size_t red = (size_t)NT * 104 * sizeof(float);
+  if (red > smem) smem = red;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad2_kernel<COUT, WR2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int chunks = in.total_chunks;
+  long long total_tiles = (long long)N * ceil_div(D, TW) * (D / WR2);
+  int S = wgrad_sets(chunks);
+  if (S > total_tiles) S = (int)total_tiles;
+  dim3 grid(S, chunks);
+  conv5x5_wgrad2_kernel<COUT, WR2><<<grid, NT, smem, st>>>(in, N, D, dpre, scratch);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   int n_w = 25 * chunks * 4 * COUT, n_b = COUT;
@@ -355,14 +505,14 @@ size_t conv5x5_wgrad_scratch_floats(int cin_pad, int cout) {
 
 int conv5x5_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
                   float* dwt, float* dbias) {
-  OP3_REQUIRE(D % WR == 0, "conv5x5_wgrad: D=%d must be a multiple of %d", D, WR);
+  OP3_REQUIRE(D % 8 == 0, "conv5x5_wgrad: D=%d must be a multiple of 8", D);
   if (N <= 0) return OP3_OK;
   const int cin_real = in.real_cin ? in.real_cin : in.total_chunks * 4;
   ProfScope prof(st, KID_CONV_WGRAD, 2.0 * 25 * cin_real * cout * (double)N * D * D);
   switch (cout) {
     case 4:  return launch_wgrad<4, 4, 4>(st, N, D, in, dpre, scratch, dwt, dbias);
-    case 32: return launch_wgrad<32, 8, 4>(st, N, D, in, dpre, scratch, dwt, dbias);
-    case 64: return launch_wgrad<64, 8, 2>(st, N, D, in, dpre, scratch, dwt, dbias);
+    case 32: return launch_wgrad2<32, 8>(st, N, D, in, dpre, scratch, dwt, dbias);
+    case 64: return launch_wgrad2<64, 4>(st, N, D, in, dpre, scratch, dwt, dbias);
     default: break;
   }
   set_error("conv5x5_wgrad: unsupported cout=%d", cout);
