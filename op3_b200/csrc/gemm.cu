@@ -7,14 +7,16 @@ namespace op3 {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 64, BN = 64, BK = 32;
 
+// 64x64x32 tiles, 4x4 micro-tiles; the next K-slab is fetched into registers while the current one is multiplied
+// (double-buffered smem, one barrier per slab) so the global-load latency of these small, latency-bound GEMMs overlaps.
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                    const float* __restrict__ B, int ldb, float* __restrict__ C,
                                                    int ldc, const float* __restrict__ bias, int act, int accumulate) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -23,42 +25,56 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float ra[8], rb[8];
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    // A tile: BM x BK
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       int e = tid + r * 256;
       int mm, kk;
       if (TA == 0) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
       int gm = m0 + mm, gk = k0 + kk;
-      float v = 0.f;
-      if (gm < M && gk < K) v = TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm];
-      As[kk][mm] = v;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int e = tid + r * 256;
-      int nn, kk;
+      ra[r] = (gm < M && gk < K) ? (TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm]) : 0.f;
+      int nn;
       if (TB == 0) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
-      int gn = n0 + nn, gk = k0 + kk;
-      float v = 0.f;
-      if (gn < N && gk < K) v = TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk];
-      Bs[kk][nn] = v;
+      int gn = n0 + nn;
+      gk = k0 + kk;
+      rb[r] = (gn < N && gk < K) ? (TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk]) : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int e = tid + r * 256;
+      int mm, kk;
+      if (TA == 0) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      As[buf][kk][mm] = ra[r];
+      int nn;
+      if (TB == 0) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
+      Bs[buf][kk][nn] = rb[r];
+    }
+  };
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BK, buf ^= 1) {
+    const bool more = k0 + BK < K;
+    if (more) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = As[buf][kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][kk][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    if (more) stash(buf ^ 1);
     __syncthreads();
   }
 #pragma unroll
