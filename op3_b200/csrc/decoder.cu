@@ -161,7 +161,7 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
   int gch = 1;  // chunks of g
   for (int i = 3; i >= 0; --i) {  // conv layer i+2, input a[i], output gradient g (dPre of that layer)
     const int cout = i == 3 ? 4 : 32;
-    if (pg) OP3_TRY(conv5x5_wgrad(st, N, D, single_src(A.a[i], 8), cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i]));
+    if (pg) OP3_TRY(conv5x5_wgrad_auto(st, N, D, single_src(A.a[i], 8), cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i]));
     float4* gn = gbuf[i & 1];
     // dgrad: conv over g with flipped/transposed weights, times ELU'(a[i]) -> dPre of the layer below
     OP3_TRY(conv5x5_auto(st, N, D, single_src(g, gch), 32, prep + L.dec_wd[i], prep + L.dec_td[i], nullptr, gn,

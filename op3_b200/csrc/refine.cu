@@ -391,11 +391,11 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   avgpool_bwd_kernel<<<dim3(ceil_div(Rs / 4 * DD, 256), N), 256, 0, st>>>(dpool, A.r3, Rs / 4, DD, g3);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
-  OP3_TRY(conv5x5_wgrad(st, N, D, one_src(A.r2, 8), Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2]));
+  OP3_TRY(conv5x5_wgrad_auto(st, N, D, one_src(A.r2, 8), Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2]));
   OP3_TRY(conv5x5_auto(st, N, D, one_src(g3, Rs / 4), 32, prep + L.ref_wd[2], prep + L.ref_td[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2));
-  OP3_TRY(conv5x5_wgrad(st, N, D, one_src(A.r1, 8), 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1]));
+  OP3_TRY(conv5x5_wgrad_auto(st, N, D, one_src(A.r1, 8), 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1]));
   OP3_TRY(conv5x5_auto(st, N, D, one_src(g2, 8), 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1));
-  OP3_TRY(conv5x5_wgrad(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0]));
+  OP3_TRY(conv5x5_wgrad_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0]));
   OP3_TRY(conv5x5_auto(st, N, D, one_src(g1, 8), REF_CIN_PAD, prep + L.ref_wd[0], prep + L.ref_td[0], nullptr,
                        reinterpret_cast<float4*>(d_in), EPI_NONE, nullptr));
   return OP3_OK;

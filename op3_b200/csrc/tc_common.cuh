@@ -110,6 +110,12 @@ size_t conv5x5_tc_weight_floats(int cin_pad, int cout);
 int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float* wt,
                        const float* bias, float4* out, int epi, const float4* elu_ref);
 
+// conv5x5_wgrad_tc.cu
+size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout);
+int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float4* dpre,
+                     float* scratch, float* dwt, float* dbias);
+int conv5x5_wgrad_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
+                       float* dwt, float* dbias);
 int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
                  const float* bias, float4* out, int epi, const float4* elu_ref);
 
