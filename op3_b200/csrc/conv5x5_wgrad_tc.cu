@@ -4,13 +4,17 @@
 // (tests/probes/probe_mnmajor.cu, probe_mn2.cu): kind::tf32 with MN-major (transposed) operands silently produces zeros
 // for every swizzle mode, so the loaders transpose 4 pixels x 4 channels blocks in registers into
 //     [pixel chunk of 4][channel row][4 pixels]            (16-byte rows, K-major, no swizzle).
-// A 16-byte K chunk holds 4 pixels, so a tap offset o = 4a + phi can only be applied in whole chunks; the residual
-// phase phi is absorbed by keeping FOUR copies of the G block, copy phi shifted by phi pixels.
-//   * One CTA owns one kernel ROW ky (5 taps): its X window needs no halo beyond 4 pixels and 5 accumulators
-//     (128 lanes x N columns each) fit TMEM.  grid = 5 x S persistent CTAs over (image, 64-pixel block) items.
-//   * 3xTF32: A rows = [X_hi (32); X_lo (32); ones], B rows = [G_hi; G_lo]: ONE MMA yields all hi/lo cross products,
-//     the quadrants are summed in the epilogue; the `ones` row gives the bias gradient for free.
-//   * warps 0-7 transpose/round/split operands into smem (2 stages), warp 8 issues the MMAs, warps 0-3 run the epilogue.
+// A 16-byte K chunk holds 4 pixels, so a tap offset can only be applied in whole chunks; the residual phase
+// (o mod 4 = kx mod 4, the pitch is a multiple of 4) is absorbed by shifted COPIES of the operands:
+//     X_sx[q] = X[q + sx], sx in {0,1}      G_sg[m] = G[m - sg], sg in {0,2}      =>  o = 4a + sg + sx covers every phase.
+// The two X copies are stacked along M, so ONE M=128 MMA  [X_0; X_1] x G_sg  accumulates TWO taps (kx = sg and sg+1):
+// a kernel row (5 taps) costs 3 MMAs per 8 pixels instead of 5, and all 128 accumulator lanes do useful work:
+//     lanes   0..31  X_0 hi (ci)    lanes 32..63  X_0 lo      -> tap kx = sg      (3xTF32: columns [G_hi | G_lo])
+//     lanes  64..95  X_1 hi         lanes 96..127 X_1 lo      -> tap kx = sg + 1
+//   * One CTA owns one kernel ROW ky: its X window needs no halo; grid = 5 x S persistent CTAs over (image, 64-pixel
+//     block) items; per-CTA partial slabs are reduced in a fixed order by a second kernel (deterministic).
+//   * warps 0-7 load (register double-buffered across items), transpose, round to tf32, split hi/lo; warp 8 issues the
+//     MMAs; warps 0-3 run the epilogue (quadrant sums).  The bias gradient is summed by the loaders of the ky = 0 CTAs.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -20,26 +24,25 @@ namespace {
 
 constexpr int WG_BP = 64;                    // pixels per block (8 K-steps of 8)
 constexpr int WG_CH = WG_BP / 4;             // 16 pixel chunks per block
-constexpr int WG_GCH = WG_CH + 1;            // G copies need one extra chunk (tap offsets a and a+1)
+constexpr int WG_GCH = WG_CH + 1;            // G copies need one extra chunk (tap kx = 4 uses chunk offset a + 1)
 constexpr int WG_LOADERS = 256;
 constexpr int WG_THREADS = 288;
-constexpr int WG_A_ROWS = 73;                // rows per A chunk (>= 65 used; == 1 mod 8 -> conflict-free 16-byte stores)
+constexpr int WG_A_ROWS = 129;               // 128 rows per A chunk, +1: chunk stride == 1 mod 8 rows -> conflict-free stores
 
 template <int NCO, bool SPLIT3>
 struct WgCfg {
-  static constexpr int NB = SPLIT3 ? 2 * NCO : NCO;          // B rows = accumulator columns per tap
+  static constexpr int NB = SPLIT3 ? 2 * NCO : NCO;          // B rows = accumulator columns per MMA
   static constexpr int B_ROWS = NB + 1;                      // == 1 mod 8
-  static constexpr int ONES_ROW = SPLIT3 ? 64 : 32;
-  static constexpr int A_BYTES = WG_CH * WG_A_ROWS * 16 + 2048;          // + slack: M=128 reads run past the last chunk
+  static constexpr int A_BYTES = WG_CH * WG_A_ROWS * 16;
   static constexpr int G_BYTES = WG_GCH * B_ROWS * 16;
-  static constexpr int STAGE_BYTES = A_BYTES + 4 * G_BYTES;
-  static constexpr int TMEM_COLS = 5 * NB <= 128 ? 128 : (5 * NB <= 256 ? 256 : 512);
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * G_BYTES;
+  static constexpr int TMEM_COLS = 3 * NB <= 64 ? 64 : (3 * NB <= 128 ? 128 : 256);
 };
 
 __device__ __forceinline__ void split_store(float4* hi_dst, float4* lo_dst, float a, float b, float c, float d, bool split) {
   float4 h = make_float4(tf32_rn(a), tf32_rn(b), tf32_rn(c), tf32_rn(d));
   *hi_dst = h;
-  if (split) *lo_dst = make_float4(tf32_rn(a - h.x), tf32_rn(b - h.y), tf32_rn(c - h.z), tf32_rn(d - h.w));
+  if (split) *lo_dst = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);   // exact; the tensor core truncates it (2^-22 rel.)
 }
 
 template <int NCO, bool SPLIT3>
@@ -48,7 +51,7 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
                         int g_chunks, int cout_total, int co0, float* __restrict__ partial) {
   using Cfg = WgCfg<NCO, SPLIT3>;
   constexpr int NB = Cfg::NB, B_ROWS = Cfg::B_ROWS;
-  const int P = D + 4;
+  const int P = D + 4;                                     // multiple of 4 (D is a multiple of 8)
   const int QN = (D + 4) * P;                              // padded-linear input pixels per image
   const int NBLK = (QN + WG_BP - 1) / WG_BP;
   const int ky = blockIdx.y;
@@ -56,9 +59,8 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
   const int cin_chunks = in.total_chunks;
   const int cin_pad = cin_chunks * 4;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  // tap offsets o_k = ky*P + kx = 4*a_k + phi_k
-  const int o0 = ky * P;
-  const int a_max = (o0 + 4) >> 2;
+  const int a0 = (ky * P) >> 2;                            // chunk offset of taps kx = 0..3; kx = 4 uses a0 + 1
+  const bool have = n_items > (int)blockIdx.x;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[2], empty_bar[2], acc_bar;
@@ -70,34 +72,22 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
-  // constant rows: the `ones` row of every A chunk (bias gradient), written once for both stages
-  for (int e = tid; e < 2 * WG_CH; e += WG_THREADS) {
-    int s = e / WG_CH, j = e % WG_CH;
-    float4* a = reinterpret_cast<float4*>(smem_raw + (size_t)s * Cfg::STAGE_BYTES) + (size_t)j * WG_A_ROWS + Cfg::ONES_ROW;
-    *a = make_float4(1.f, 1.f, 1.f, 1.f);
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);       // loaders of ky == 0: sum_p G[p][4*warp ..]
 
   if (warp < 8) {
-    // ===================== loaders: transpose 4 pixels x 4 channels, round to tf32, split hi/lo =====================
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int n = item / NBLK, blk = item % NBLK;
-      const int Q0 = blk * WG_BP;
-      const int s = it & 1;
-      if (it >= 2) mbar_wait(&empty_bar[s], ((it >> 1) - 1) & 1);
-      uint8_t* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
-      float4* A = reinterpret_cast<float4*>(st);
-      // Warp w owns channel chunk w of X (lanes 0..15 = pixel chunks) and of G (lanes 0..17 = raw aligned chunks
-      // rj = lane-1 in [-1,16]).  All global loads are issued first; the four phase copies of G are then assembled from
-      // the lane's own pixels and its left neighbour's (warp shuffles) instead of four separate loads.
-      float4 xv[4], gv[4];
-      const bool do_x = warp < cin_chunks && lane < WG_CH;
-      const bool do_g = warp < g_chunks && lane < WG_GCH + 1;
+    // ===================== loaders =====================
+    // Warp w owns channel chunk w of X and of G.  X: lane l holds raw aligned chunk l in [0,16].  G: lane l holds raw
+    // aligned chunk (l - 1) in [-1,16].  The shifted copies X_1 / G_2 take one pixel / two pixels from a neighbour lane.
+    const bool do_x = warp < cin_chunks && lane < WG_CH + 1;
+    const bool do_g = warp < g_chunks && lane < WG_GCH + 1;
+    auto load_item = [&](int item, float4* xv, float4* gv) {
+      const int n = item / NBLK, Q0 = (item % NBLK) * WG_BP;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { xv[e] = make_float4(0.f, 0.f, 0.f, 0.f); gv[e] = make_float4(0.f, 0.f, 0.f, 0.f); }
       if (do_x) {
         const float4* src = tc_src_chunk_ptr(in, warp, n, D);
         int q = Q0 + 4 * lane;
@@ -105,15 +95,13 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           bool ok = q + e < QN && iy >= 0 && iy < D && ix >= 0 && ix < D;
-          xv[e] = ok ? __ldg(src + (size_t)iy * D + ix) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) xv[e] = __ldg(src + (size_t)iy * D + ix);
           if (++ix >= P - 2) { ix -= P; ++iy; }
         }
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) gv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (do_g) {
         const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + warp) * D * D;
-        const int p = Q0 - 4 * a_max + 4 * (lane - 1);
+        const int p = Q0 - 4 * (a0 + 1) + 4 * (lane - 1);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int pe = p + e;
@@ -122,43 +110,68 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
           if (pe >= 0 && y < D && x < D) gv[e] = __ldg(src + (size_t)y * D + x);
         }
       }
-      if (do_x) {
-        float4* row = A + (size_t)lane * WG_A_ROWS + 4 * warp;
-        split_store(row + 0, row + 32 + 0, xv[0].x, xv[1].x, xv[2].x, xv[3].x, SPLIT3);
-        split_store(row + 1, row + 32 + 1, xv[0].y, xv[1].y, xv[2].y, xv[3].y, SPLIT3);
-        split_store(row + 2, row + 32 + 2, xv[0].z, xv[1].z, xv[2].z, xv[3].z, SPLIT3);
-        split_store(row + 3, row + 32 + 3, xv[0].w, xv[1].w, xv[2].w, xv[3].w, SPLIT3);
-      }
-      if (warp < g_chunks) {                      // whole warp: shuffles must be convergent
-        // left neighbour's pixels 1..3 (raw chunk rj-1), needed for phases 1..3
-        float4 lv[4];
-#pragma unroll
-        for (int e = 1; e < 4; ++e) {
-          lv[e].x = __shfl_up_sync(0xffffffffu, gv[e].x, 1); lv[e].y = __shfl_up_sync(0xffffffffu, gv[e].y, 1);
-          lv[e].z = __shfl_up_sync(0xffffffffu, gv[e].z, 1); lv[e].w = __shfl_up_sync(0xffffffffu, gv[e].w, 1);
+    };
+    float4 xv[4], gv[4], xn[4], gn[4];
+    int it = 0;
+    if (have) load_item(blockIdx.x, xv, gv);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int next = item + gridDim.x;
+      if (next < n_items) load_item(next, xn, gn);                 // in flight while this item is stored
+      if (it >= 2) mbar_wait(&empty_bar[s], ((it >> 1) - 1) & 1);
+      uint8_t* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
+      float4* A = reinterpret_cast<float4*>(st);
+      if (warp < cin_chunks) {                    // whole warp: shuffles must be convergent
+        // X_1 chunk j = pixels 4j+1 .. 4j+4 = own pixels 1..3 + right neighbour's pixel 0
+        float4 r0;
+        r0.x = __shfl_down_sync(0xffffffffu, xv[0].x, 1); r0.y = __shfl_down_sync(0xffffffffu, xv[0].y, 1);
+        r0.z = __shfl_down_sync(0xffffffffu, xv[0].z, 1); r0.w = __shfl_down_sync(0xffffffffu, xv[0].w, 1);
+        if (lane < WG_CH) {
+          float4* row = A + (size_t)lane * WG_A_ROWS + 4 * warp;
+          split_store(row + 0, row + 32 + 0, xv[0].x, xv[1].x, xv[2].x, xv[3].x, SPLIT3);
+          split_store(row + 1, row + 32 + 1, xv[0].y, xv[1].y, xv[2].y, xv[3].y, SPLIT3);
+          split_store(row + 2, row + 32 + 2, xv[0].z, xv[1].z, xv[2].z, xv[3].z, SPLIT3);
+          split_store(row + 3, row + 32 + 3, xv[0].w, xv[1].w, xv[2].w, xv[3].w, SPLIT3);
+          split_store(row + 64 + 0, row + 96 + 0, xv[1].x, xv[2].x, xv[3].x, r0.x, SPLIT3);
+          split_store(row + 64 + 1, row + 96 + 1, xv[1].y, xv[2].y, xv[3].y, r0.y, SPLIT3);
+          split_store(row + 64 + 2, row + 96 + 2, xv[1].z, xv[2].z, xv[3].z, r0.z, SPLIT3);
+          split_store(row + 64 + 3, row + 96 + 3, xv[1].w, xv[2].w, xv[3].w, r0.w, SPLIT3);
         }
+      }
+      if (warp < g_chunks) {
+        // G_2 local chunk lj = pixels 4lj-2 .. 4lj+1 = left neighbour's pixels 2,3 + own pixels 0,1
+        float4 l2, l3;
+        l2.x = __shfl_up_sync(0xffffffffu, gv[2].x, 1); l2.y = __shfl_up_sync(0xffffffffu, gv[2].y, 1);
+        l2.z = __shfl_up_sync(0xffffffffu, gv[2].z, 1); l2.w = __shfl_up_sync(0xffffffffu, gv[2].w, 1);
+        l3.x = __shfl_up_sync(0xffffffffu, gv[3].x, 1); l3.y = __shfl_up_sync(0xffffffffu, gv[3].y, 1);
+        l3.z = __shfl_up_sync(0xffffffffu, gv[3].z, 1); l3.w = __shfl_up_sync(0xffffffffu, gv[3].w, 1);
         if (lane >= 1 && lane < WG_GCH + 1) {     // local chunk lj = lane-1 in [0,17)
           const int lj = lane - 1;
+          float4* G0 = reinterpret_cast<float4*>(st + Cfg::A_BYTES) + (size_t)lj * B_ROWS + 4 * warp;
+          float4* G2 = reinterpret_cast<float4*>(st + Cfg::A_BYTES + Cfg::G_BYTES) + (size_t)lj * B_ROWS + 4 * warp;
+          split_store(G0 + 0, G0 + NCO + 0, gv[0].x, gv[1].x, gv[2].x, gv[3].x, SPLIT3);
+          split_store(G0 + 1, G0 + NCO + 1, gv[0].y, gv[1].y, gv[2].y, gv[3].y, SPLIT3);
+          split_store(G0 + 2, G0 + NCO + 2, gv[0].z, gv[1].z, gv[2].z, gv[3].z, SPLIT3);
+          split_store(G0 + 3, G0 + NCO + 3, gv[0].w, gv[1].w, gv[2].w, gv[3].w, SPLIT3);
+          split_store(G2 + 0, G2 + NCO + 0, l2.x, l3.x, gv[0].x, gv[1].x, SPLIT3);
+          split_store(G2 + 1, G2 + NCO + 1, l2.y, l3.y, gv[0].y, gv[1].y, SPLIT3);
+          split_store(G2 + 2, G2 + NCO + 2, l2.z, l3.z, gv[0].z, gv[1].z, SPLIT3);
+          split_store(G2 + 3, G2 + NCO + 3, l2.w, l3.w, gv[0].w, gv[1].w, SPLIT3);
+          if (ky == 0 && lane >= 2) {             // raw chunks 0..15 tile the pixel space exactly once over the blocks
 #pragma unroll
-          for (int phi = 0; phi < 4; ++phi) {
-            // copy phi, element e <- raw pixel (e - phi) of this chunk, or (e - phi + 4) of the left neighbour
-            float4 w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = e >= phi ? gv[e - phi] : lv[e - phi + 4];
-            float4* G = reinterpret_cast<float4*>(st + Cfg::A_BYTES + (size_t)phi * Cfg::G_BYTES);
-            float4* row = G + (size_t)lj * B_ROWS + 4 * warp;
-            split_store(row + 0, row + NCO + 0, w[0].x, w[1].x, w[2].x, w[3].x, SPLIT3);
-            split_store(row + 1, row + NCO + 1, w[0].y, w[1].y, w[2].y, w[3].y, SPLIT3);
-            split_store(row + 2, row + NCO + 2, w[0].z, w[1].z, w[2].z, w[3].z, SPLIT3);
-            split_store(row + 3, row + NCO + 3, w[0].w, w[1].w, w[2].w, w[3].w, SPLIT3);
+            for (int e = 0; e < 4; ++e) {
+              bias_acc.x += gv[e].x; bias_acc.y += gv[e].y; bias_acc.z += gv[e].z; bias_acc.w += gv[e].w;
+            }
           }
         }
       }
       fence_proxy_async();
       mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { xv[e] = xn[e]; gv[e] = gn[e]; }
     }
   } else if (lane == 0) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer: per 8 pixels, [X_0;X_1] x G_0(a0) | x G_2(a0) | x G_0(a0+1) =====================
     const uint32_t idesc = make_idesc_tf32(128, NB);
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -169,12 +182,12 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
       const uint64_t ad = make_smem_desc(st, WG_A_ROWS, 8);
       const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
 #pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        const int o = o0 + kx;
-        const int phi = o & 3, da = a_max - (o >> 2);          // local G chunk = X chunk + da
-        const uint64_t bd = make_smem_desc(st + Cfg::A_BYTES + phi * Cfg::G_BYTES + da * B_ROWS * 16, B_ROWS, 8);
+      for (int m = 0; m < 3; ++m) {
+        // local G chunk of X chunk jx is jx + (a0 + 1) - a:  taps kx = 0..3 -> +1, tap kx = 4 -> +0
+        const int copy = m == 1 ? 1 : 0, dj = m == 2 ? 0 : 1;
+        const uint64_t bd = make_smem_desc(st + Cfg::A_BYTES + copy * Cfg::G_BYTES + dj * B_ROWS * 16, B_ROWS, 8);
         const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
-        const uint32_t dcol = tmem_base + (uint32_t)(kx * NB);
+        const uint32_t dcol = tmem_base + (uint32_t)(m * NB);
 #pragma unroll
         for (int ks = 0; ks < WG_BP / 8; ++ks)
           mma_tf32(dcol, a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32, b_lo32 + (uint32_t)(2 * ks * B_ROWS), b_hi32, idesc,
@@ -186,35 +199,43 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
   }
   // ===================== epilogue: quadrant sums -> per-CTA partial slab =====================
   __syncthreads();                      // loaders are done with smem; reuse it as the combine buffer
-  float* red = reinterpret_cast<float*>(smem_raw);         // [5 taps][32 ci][NCO] contributions of the X_lo rows
+  float* red = reinterpret_cast<float*>(smem_raw);         // [3 MMAs][2 taps][32 ci][NCO]: sums of the X_lo rows
+  float* s_bias = red + 3 * 2 * 32 * NCO;                  // [8 warps][4]
   float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
-  if (warp < 4) {
-    if (n_items > (int)blockIdx.x) {
-      mbar_wait(&acc_bar, 0);
-      tc_fence_after();
-    }
-    const bool have = n_items > (int)blockIdx.x;
-    // pass 1: warp 1 (lanes 32..63 = X_lo rows) parks its quadrant sums in smem
-    if (SPLIT3 && warp == 1) {
-      for (int kx = 0; kx < 5; ++kx)
-#pragma unroll
-        for (int c0 = 0; c0 < NCO; c0 += 16) {
-          float v[16], u[16];
-          const uint32_t t = tmem_base + ((uint32_t)32 << 16) + (uint32_t)(kx * NB + c0);
-          if (have) { tmem_ld16(t, v); tmem_ld16(t + NCO, u); tmem_ld_wait(); }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) red[((size_t)kx * 32 + lane) * NCO + c0 + i] = have ? v[i] + u[i] : 0.f;
-        }
+  if (warp < 8 && have) {               // nobody may touch smem before the last MMAs have consumed their operands
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+  }
+  if (warp < 8) {                        // bias partial of this CTA (ky == 0 only; fixed shuffle tree)
+    bias_acc.x = warp_sum(bias_acc.x); bias_acc.y = warp_sum(bias_acc.y);
+    bias_acc.z = warp_sum(bias_acc.z); bias_acc.w = warp_sum(bias_acc.w);
+    if (lane == 0) {
+      s_bias[warp * 4 + 0] = bias_acc.x; s_bias[warp * 4 + 1] = bias_acc.y;
+      s_bias[warp * 4 + 2] = bias_acc.z; s_bias[warp * 4 + 3] = bias_acc.w;
     }
   }
-  __syncthreads();
-  if (warp == 0) {
-    const bool have = n_items > (int)blockIdx.x;
-    for (int kx = 0; kx < 5; ++kx)
+  // lanes 32..63 (warp 1) and 96..127 (warp 3) hold the X_lo rows: park their sums in smem
+  if (SPLIT3 && (warp == 1 || warp == 3)) {
+    for (int m = 0; m < 3; ++m)
 #pragma unroll
       for (int c0 = 0; c0 < NCO; c0 += 16) {
         float v[16], u[16];
-        const uint32_t t = tmem_base + (uint32_t)(kx * NB + c0);
+        const uint32_t t = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * NB + c0);
+        if (have) { tmem_ld16(t, v); tmem_ld16(t + NCO, u); tmem_ld_wait(); }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) red[((size_t)(m * 2 + (warp >> 1)) * 32 + lane) * NCO + c0 + i] = have ? v[i] + u[i] : 0.f;
+      }
+  }
+  __syncthreads();
+  if (warp == 0 || warp == 2) {          // lanes 0..31 / 64..95: X_hi rows of tap kx = 2m / 2m + 1
+    const int sub = warp >> 1;
+    for (int m = 0; m < 3; ++m) {
+      const int kx = 2 * m + sub;
+      if (kx > 4) continue;              // the upper half of the third MMA is a non-existent tap
+#pragma unroll
+      for (int c0 = 0; c0 < NCO; c0 += 16) {
+        float v[16], u[16];
+        const uint32_t t = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * NB + c0);
         if (have) {
           tmem_ld16(t, v);
           if (SPLIT3) tmem_ld16(t + NCO, u);
@@ -226,33 +247,16 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
             const int co = c0 + i;
             if (co < g_chunks * 4) {
               float r = have ? v[i] : 0.f;
-              if (SPLIT3) r += (have ? u[i] : 0.f) + red[((size_t)kx * 32 + lane) * NCO + co];
+              if (SPLIT3) r += (have ? u[i] : 0.f) + red[((size_t)(m * 2 + sub) * 32 + lane) * NCO + co];
               slab[((size_t)(ky * 5 + kx) * cin_pad + lane) * cout_total + co0 + co] = r;
             }
           }
         }
       }
-  }
-  // bias gradient: the `ones` row (TMEM lane ONES_ROW) of tap (ky = 0, kx = 0); other CTAs contribute zero
-  if (warp == Cfg::ONES_ROW / 32) {
-    const bool have = n_items > (int)blockIdx.x && ky == 0;
-#pragma unroll
-    for (int c0 = 0; c0 < NCO; c0 += 16) {
-      float v[16], u[16];
-      const uint32_t t = tmem_base + ((uint32_t)Cfg::ONES_ROW << 16) + (uint32_t)c0;
-      if (have) {
-        tmem_ld16(t, v);
-        if (SPLIT3) tmem_ld16(t + NCO, u);
-        tmem_ld_wait();
-      }
-      if (lane == 0 && ky == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < g_chunks * 4)
-            slab[(size_t)25 * cin_pad * cout_total + co0 + c0 + i] = have ? v[i] + (SPLIT3 ? u[i] : 0.f) : 0.f;
-      }
     }
   }
+  if (ky == 0 && tid < g_chunks * 4)
+    slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid];       // warp w summed channel chunk w
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -276,7 +280,7 @@ int launch_wgrad_tc(cudaStream_t st, int N, int D, const ConvInput& in, const fl
                     int g_chunks, int cout_total, int co0, float* scratch) {
   using Cfg = WgCfg<NCO, SPLIT3>;
   size_t smem = 2 * (size_t)Cfg::STAGE_BYTES;
-  size_t red = (size_t)5 * 32 * NCO * sizeof(float);
+  size_t red = (size_t)(3 * 2 * 32 * NCO + 64) * sizeof(float);
   if (red > smem) smem = red;
   OP3_REQUIRE(smem <= 226 * 1024, "conv5x5_wgrad_tc: %zu bytes of shared memory", smem);
   static bool attr_set = false;
@@ -302,17 +306,15 @@ size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout) {
 int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float4* dpre,
                      float* scratch, float* dwt, float* dbias) {
   if (N <= 0) return OP3_OK;
-  OP3_REQUIRE(cout % 4 == 0 && cout <= 64 && in.total_chunks <= 8, "conv5x5_wgrad_tc: unsupported cin chunks %d / cout %d",
-              in.total_chunks, cout);
+  OP3_REQUIRE(cout % 4 == 0 && cout <= 64 && in.total_chunks <= 8 && D % 4 == 0,
+              "conv5x5_wgrad_tc: unsupported cin chunks %d / cout %d / D %d", in.total_chunks, cout, D);
   const int cin_real = in.real_cin ? in.real_cin : in.total_chunks * 4;
   ProfScope prof(st, KID_CONV_WGRAD, 2.0 * 25 * cin_real * cout * (double)N * D * D);
   const bool s3 = precision == OP3_PREC_TF32X3;
   const int planes = cout / 4;
-  // every CTA writes its full region of its slab; slabs of different kernel rows are disjoint, so no zero fill is needed,
-  // but halves / rows that are never written must not leak old data: clear once.
   const int cin_pad = in.total_chunks * 4;
   const size_t slab = (size_t)25 * cin_pad * cout + cout;
-  OP3_CHECK(cudaMemsetAsync(scratch, 0, (size_t)wg_sets() * slab * sizeof(float), st));
+  OP3_CHECK(cudaMemsetAsync(scratch, 0, (size_t)wg_sets() * slab * sizeof(float), st));   // padding entries stay zero
   if (cout <= 16) {
     OP3_TRY((s3 ? launch_wgrad_tc<16, true>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)
                 : launch_wgrad_tc<16, false>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)));
@@ -329,7 +331,6 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
   OP3_LAUNCH_CHECK();
   return OP3_OK;
 }
-
 
 int conv5x5_wgrad_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
                        float* dwt, float* dbias) {
