@@ -195,6 +195,13 @@ typedef struct Op3RefineIO {
 size_t op3_refine_acts_floats(const Op3Dims* d);
 size_t op3_refine_scratch_floats(const Op3Dims* d);
 int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float* prepared, const Op3RefineIO* io, void* stream);
+/* Standalone RefinementNetwork.forward(input, hidden1, hidden2, extra_input) (refinement_network.py:189-219).
+ * in_chunks [N][5][D][D] float4: the 15 input channels + 2 coordinate planes packed in this library's chunk order
+ * (chunk 0: colors rgb, mask_logits; 1: mask, posterior_mask, LN(mask_grad), LN(leave_out); 2: LN(x_hat_grad) rgb, 0;
+ * 3: image rgb, LN(pixel ll); 4: x, y, 0, 0); extra [N][5*Rs]; h, c [N][128]. */
+int op3_refine_net_fwd(const Op3Dims* d, const Op3Params* p, const float* prepared, const float* in_chunks,
+                       const float* extra, const float* h, const float* c, float* acts, float* l1_out, float* l2_out,
+                       float* h_out, float* c_out, void* stream);
 /* upstream: d_l1_new, d_l2_new [N][Rs], d_h, d_c [N][128] (any may be NULL = zero).  Outputs: d_in [N][5][D][D] float4
  * (conv input chunk gradients), and ADDS the direct paths into dl1, dl2 [N][Rs], dz_samples (into dz_acc[:,Rd:],
  * row stride R), dh, dc [N][128].  Weight gradients are accumulated into grads / prep_grad. */

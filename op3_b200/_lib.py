@@ -82,6 +82,8 @@ SIGNATURES = {
     "op3_refine_acts_floats": (C.c_size_t, [_P(Op3Dims)]),
     "op3_refine_scratch_floats": (C.c_size_t, [_P(Op3Dims)]),
     "op3_refine_fwd": (C.c_int, [_P(Op3Dims), _P(Op3Params), c_fp, _P(Op3RefineIO), c_fp]),
+    "op3_refine_net_fwd": (C.c_int, [_P(Op3Dims), _P(Op3Params), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                     c_fp]),
     "op3_refine_bwd": (C.c_int, [_P(Op3Dims), _P(Op3Params), c_fp, _P(Op3RefineIO), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                  c_fp, c_fp, c_fp, c_fp, _P(Op3Params), c_fp, c_fp, c_fp]),
     "op3_dynamics_acts_floats": (C.c_size_t, [_P(Op3Dims)]),

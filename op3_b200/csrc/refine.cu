@@ -318,6 +318,40 @@ extern "C" int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float*
   return OP3_OK;
 }
 
+// Standalone RefinementNetwork.forward (refinement_network.py:189-219): the caller supplies the 17 conv input channels
+// already packed as 5 float4 chunks in this library's channel order (see ref_l1_channel) and the 5*Rs extra inputs.
+extern "C" int op3_refine_net_fwd(const Op3Dims* d, const Op3Params* p, const float* prep, const float* in_chunks,
+                                  const float* extra, const float* h, const float* c, float* acts, float* l1_out,
+                                  float* l2_out, float* h_out, float* c_out, void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(p && prep && in_chunks && extra && h && c && acts && l1_out && l2_out && h_out && c_out,
+              "op3_refine_net_fwd: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = d->B * d->K, D = d->D, DD = D * D, Rs = d->Rs;
+  const int XW = HID + 5 * Rs;
+  PrepLayout L = prep_layout(d);
+  RefActs A = ref_acts(d, acts);
+  ConvInput in = one_src(reinterpret_cast<const float4*>(in_chunks), 5);
+  in.real_cin = 17;
+  OP3_TRY(conv5x5_auto(st, N, D, in, 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr));
+  avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  OP3_TRY(gemm(st, N, HID, Rs, A.pooled, Rs, 0, p->ref_fc.w, Rs, 1, A.X, XW, p->ref_fc.b, ACT_ELU, 0));
+  OP3_CHECK(cudaMemcpy2DAsync(A.X + HID, (size_t)XW * sizeof(float), extra, (size_t)5 * Rs * sizeof(float),
+                              (size_t)5 * Rs * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
+  OP3_TRY(gemm(st, N, 4 * LSTM, XW, A.X, XW, 0, p->lstm_w_ih, XW, 1, A.gates, 4 * LSTM, p->lstm_b_ih, ACT_NONE, 0));
+  OP3_TRY(gemm(st, N, 4 * LSTM, LSTM, h, LSTM, 0, p->lstm_w_hh, LSTM, 1, A.gates, 4 * LSTM, p->lstm_b_hh, ACT_NONE, 1));
+  lstm_fwd_kernel<<<ceil_div(N * LSTM, 256), 256, 0, st>>>(N, A.gates, c, h_out, c_out);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  OP3_TRY(gemm(st, N, Rs, LSTM, h_out, LSTM, 0, p->ref_last_fc.w, LSTM, 1, l1_out, Rs, p->ref_last_fc.b, ACT_NONE, 0));
+  OP3_TRY(gemm(st, N, Rs, LSTM, h_out, LSTM, 0, p->ref_last_fc2.w, LSTM, 1, l2_out, Rs, p->ref_last_fc2.b, ACT_NONE, 0));
+  return OP3_OK;
+}
+
 extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float* prep, const Op3RefineIO* io,
                               const float* d_l1n, const float* d_l2n, const float* d_h, const float* d_c, float* d_in,
                               float* dl1, float* dl2,

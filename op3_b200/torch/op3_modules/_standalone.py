@@ -106,6 +106,53 @@ def physics_forward(net, sampled_state, actions, K=None, engine=None):
     return deter, l1, l2, act_att, pair_att, deltas
 
 
+# reference channel (op3_model.py:219-229 order + coords 15,16) stored at each of the 20 packed channels; -1 = zero
+_REF_CHANNEL = [3, 4, 5, 7, 6, 8, 9, 11, 12, 13, 14, -1, 0, 1, 2, 10, 15, 16, -1, -1]
+
+
 def refinement_forward(net, a, h, c, extra):
-    raise NotImplementedError("RefinementNetwork.forward has no standalone kernel entry yet: the refinement conv input is "
-                              "gathered from the mixture kernel's outputs inside OP3Model.run_schedule (op3_refine_fwd)")
+    """RefinementNetwork.forward (refinement_network.py:189-219): a (N,15,D,D), h/c (N,128) or (1,N,128), extra (N,5*Rs)
+    -> (lambdas1 (N,Rs), lambdas2 (N,Rs), h (1,N,128), c (1,N,128))."""
+    lib = _lib.load()
+    _require_cuda(a, "input")
+    dev = a.device
+    N, _, D, _ = a.shape
+    Rs = net.output_size
+    st = _stream(dev)
+    x = torch.cat([a.detach().float(), net.coords.to(dev).float().expand(N, 2, D, D)], 1)          # (N,17,D,D)
+    idx = torch.tensor([max(ch, 0) for ch in _REF_CHANNEL], device=dev)
+    keep = torch.tensor([1.0 if ch >= 0 else 0.0 for ch in _REF_CHANNEL], device=dev).view(1, 20, 1, 1)
+    packed = (x[:, idx] * keep).view(N, 5, 4, D, D).permute(0, 1, 3, 4, 2).contiguous()       # [N][5][D][D][4]
+    ps = Op3Params()
+    keepalive = []
+
+    def setp(field, lin):
+        w, b = lin.weight.detach().contiguous(), lin.bias.detach().contiguous()
+        _require_cuda(w, "refinement weights")
+        keepalive.extend([w, b])
+        field.w, field.b = w.data_ptr(), b.data_ptr()
+    for i, cv in enumerate(net.conv_layers):
+        w, b = cv.weight.detach().contiguous(), cv.bias.detach().contiguous()
+        _require_cuda(w, "refinement weights")
+        keepalive.extend([w, b])
+        ps.ref_conv_w[i], ps.ref_conv_b[i] = w.data_ptr(), b.data_ptr()
+    setp(ps.ref_fc, net.fc_layers[0])
+    setp(ps.ref_last_fc, net.last_fc)
+    setp(ps.ref_last_fc2, net.last_fc2)
+    for name, field in [("weight_ih_l0", "lstm_w_ih"), ("weight_hh_l0", "lstm_w_hh"), ("bias_ih_l0", "lstm_b_ih"),
+                        ("bias_hh_l0", "lstm_b_hh")]:
+        t = getattr(net.lstm, name).detach().contiguous()
+        keepalive.append(t)
+        setattr(ps, field, t.data_ptr())
+    d = Op3Dims(B=N, K=1, D=D, Rd=0, Rs=Rs, A=0, beta=0.0)
+    prep = torch.empty(lib.op3_prepared_floats(C.byref(d)), device=dev)
+    check(lib.op3_prepare(C.byref(d), C.byref(ps), ptr(prep), st), "op3_prepare")
+    acts = torch.empty(lib.op3_refine_acts_floats(C.byref(d)), device=dev)
+    hh = h.detach().reshape(N, -1).contiguous().float()
+    cc = c.detach().reshape(N, -1).contiguous().float()
+    ex = extra.detach().contiguous().float()
+    l1, l2 = torch.empty(N, Rs, device=dev), torch.empty(N, Rs, device=dev)
+    h2, c2 = torch.empty(N, hh.shape[1], device=dev), torch.empty(N, hh.shape[1], device=dev)
+    check(lib.op3_refine_net_fwd(C.byref(d), C.byref(ps), ptr(prep), ptr(packed), ptr(ex), ptr(hh), ptr(cc), ptr(acts),
+                                 ptr(l1), ptr(l2), ptr(h2), ptr(c2), st), "op3_refine_net_fwd")
+    return l1, l2, h2.unsqueeze(0), c2.unsqueeze(0)

@@ -34,6 +34,27 @@ def test_decoder_forward_matches_oracle_and_golden():
     assert torch.equal(l2, logits) and torch.equal(c2, colors)
 
 
+def test_refinement_network_forward_matches_golden_and_oracle():
+    """RefinementNetwork.forward as a standalone module (refinement_network.py:189-219) against the reference fixture."""
+    g = load_golden("modules")
+    m, p = build_model(4, 3, seed=3)
+    gen = torch.Generator().manual_seed(int(g["ref/seed"]))
+    torch.randn(6, 128, generator=gen)                      # the decoder case's draw precedes these in make_golden.py
+    a = torch.randn(6, 15, 64, 64, generator=gen)
+    h = torch.randn(6, 128, generator=gen) * 0.3
+    c = torch.randn(6, 128, generator=gen) * 0.3
+    extra = torch.randn(6, 320, generator=gen)
+    l1, l2, h2, c2 = m.refinement_net(a.cuda(), h.cuda(), c.cuda(), extra.cuda())
+    assert h2.shape == (1, 6, 128) and c2.shape == (1, 6, 128)
+    ref = orc.refinement_net(p, a, h, c, extra)
+    for name, ours, want in [("l1", l1, ref[0]), ("l2", l2, ref[1]), ("h2", h2[0], ref[2]), ("c2", c2[0], ref[3])]:
+        gold = torch.from_numpy(g["ref/" + name])
+        assert max_abs(want, gold) <= 1e-5, name
+        assert max_abs(ours, gold) <= 2e-5 * max(1.0, gold.abs().max().item()), (name, max_abs(ours, gold))
+    with pytest.raises(RuntimeError):
+        m.refinement_net(a, h.cuda(), c.cuda(), extra.cuda())
+
+
 def test_decoder_backward_matches_autograd():
     lib_mod = _lib()
     lib = lib_mod.load()

@@ -1,0 +1,72 @@
+"""GPU: MPC rollout at BASELINE.json's full size (4096 candidate action sequences, pickplace K=4) through
+size-independent properties: run-to-run bit reproducibility of costs and ranking, independence of a candidate's cost
+from the batch it is evaluated in (chunking / sharding invariance, which is what makes multi-GPU candidate sharding
+exact), permutation equivariance of the ranking, and agreement of a small subset with the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import op3_oracle as orc
+from gpu_util import build_model, NoiseInjector
+from op3_b200.mpc import Cost
+from op3_b200.parallel import shard_range
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(K=4):
+    m, p = build_model(4, K, seed=7)
+    m.eval_mode = True
+    frames = orc.synth_frames(1, 2, seed=31).cuda()
+    acts = orc.synth_actions(1, 2, seed=32)[:, :, [0, 1, 3, 4]].cuda()
+    with NoiseInjector(orc.make_noise(1, K, 64, 5, seed=40)):
+        info = m.batch_internal_inference(frames, acts, None, np.array([0., 0., 1., 0.]))
+    return m, p, info
+
+
+def _costs(m, info, cand, noise, goal_image, chunk=None):
+    if chunk is not None:
+        m.inference_chunk = chunk
+    with NoiseInjector([noise[i:i + m.inference_chunk] for i in range(0, cand.shape[0], m.inference_chunk)]):
+        pred = m.batch_internal_inference(None, cand, info["state"], np.array([1.]))
+    cost = Cost(None, core_type="final_recon", aggregate="sum")
+    c, _ = cost.pair_costs(goal_image, pred["final_recon"].unsqueeze(1))
+    return c[0]
+
+
+def test_mpc_4096_candidates_properties():
+    K, Na = 4, 4096
+    m, p, info = _setup(K)
+    cand = orc.synth_actions(Na, 1, seed=33)[:, :, [0, 1, 3, 4]].cuda()
+    noise = orc.make_noise(Na, K, 64, 1, seed=50)[0]
+    goal_image = orc.synth_frames(1, 1, seed=34)[:, 0].cuda()
+    c1 = _costs(m, info, cand, noise, goal_image, chunk=512)
+    c2 = _costs(m, info, cand, noise, goal_image, chunk=512)
+    assert torch.equal(c1, c2), "costs are not bit-reproducible run to run"
+    order = torch.argsort(c1, stable=True)
+    # chunking / sharding invariance: any shard evaluated on its own gives bit-identical costs
+    for rank, world in [(0, 8), (5, 8), (3, 4)]:
+        s, e = shard_range(Na, rank, world)
+        cs = _costs(m, info, cand[s:e], noise[s:e], goal_image, chunk=256)
+        assert torch.equal(cs, c1[s:e]), "candidate costs depend on the batch they are evaluated in"
+    # permutation equivariance of the selected action
+    perm = torch.randperm(Na, generator=torch.Generator().manual_seed(1))
+    cp = _costs(m, info, cand[perm.cuda()], noise[perm], goal_image, chunk=512)
+    assert torch.equal(cp, c1[perm.cuda()])
+    assert perm[torch.argmin(cp).item()].item() == order[0].item()
+    gap = (c1[order[1]] - c1[order[0]]).item() / c1[order[0]].item()
+    print("4096 candidates: best %d cost %.6e, relative gap to second %.3e" % (order[0].item(), c1[order[0]].item(), gap))
+    # a small subset against the CPU oracle (same weights, state and noise)
+    sub = 16
+    st = info["state"]
+    rep = lambda t: t.detach().cpu().repeat(sub, 1, 1)
+    state = {"prior": {"lambdas1": rep(st["prior"]["lambdas1"]), "lambdas2": rep(st["prior"]["lambdas1"])},
+             "post": {"deter_state": rep(st["post"]["deter_state"]), "lambdas1": rep(st["post"]["lambdas1"]),
+                      "lambdas2": rep(st["post"]["lambdas2"]), "samples": rep(st["post"]["samples"]),
+                      "extra_info": [st["post"]["extra_info"][0].cpu().repeat(sub, 1, 1).reshape(sub * K, -1),
+                                     st["post"]["extra_info"][1].cpu().repeat(sub, 1, 1).reshape(sub * K, -1)]}}
+    with torch.no_grad():
+        o = orc.run_schedule(p, None, cand[:sub].cpu(), [1], [0], [noise[:sub]], K, init_state=state)
+    oc = ((goal_image.cpu().view(1, 3, 64, 64) - o["final_recon"]) ** 2).mean((1, 2, 3))
+    assert torch.allclose(c1[:sub].cpu(), oc, rtol=2e-5, atol=1e-8)
+    assert torch.equal(torch.argsort(c1[:sub].cpu()), torch.argsort(oc))
