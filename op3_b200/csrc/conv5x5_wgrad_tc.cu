@@ -13,8 +13,9 @@
 //     lanes  64..95  X_1 hi         lanes 96..127 X_1 lo      -> tap kx = sg + 1
 //   * One CTA owns one kernel ROW ky: its X window needs no halo; grid = 5 x S persistent CTAs over (image, 64-pixel
 //     block) items; per-CTA partial slabs are reduced in a fixed order by a second kernel (deterministic).
-//   * warps 0-7 load (register double-buffered across items), transpose, round to tf32, split hi/lo; warp 8 issues the
-//     MMAs; warps 0-3 run the epilogue (quadrant sums).  The bias gradient is summed by the loaders of the ky = 0 CTAs.
+//   * warps 0-15 load (two groups, one per smem stage; register double-buffered across items), transpose, round to
+//     tf32, split hi/lo; warp 16 issues the MMAs; warps 0-3 run the epilogue (quadrant sums).  The bias gradient is
+//     summed by the G loaders of the ky = 0 CTAs.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -25,8 +26,8 @@ namespace {
 constexpr int WG_BP = 64;                    // pixels per block (8 K-steps of 8)
 constexpr int WG_CH = WG_BP / 4;             // 16 pixel chunks per block
 constexpr int WG_GCH = WG_CH + 1;            // G copies need one extra chunk (tap kx = 4 uses chunk offset a + 1)
-constexpr int WG_LOADERS = 256;
-constexpr int WG_THREADS = 288;
+constexpr int WG_LOADERS = 512;             // two groups of 8 loader warps, one per smem stage
+constexpr int WG_THREADS = WG_LOADERS + 32;  // + the MMA issuer warp
 constexpr int WG_A_ROWS = 129;               // 128 rows per A chunk, +1: chunk stride == 1 mod 8 rows -> conflict-free stores
 
 template <int NCO, bool SPLIT3>
@@ -67,108 +68,145 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
   __shared__ uint32_t tmem_base_s;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], WG_LOADERS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], WG_LOADERS / 2); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
+  if (warp == WG_LOADERS / 32) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);       // loaders of ky == 0: sum_p G[p][4*warp ..]
 
-  if (warp < 8) {
+  if (warp < WG_LOADERS / 32) {
     // ===================== loaders =====================
-    // Warp w owns channel chunk w of X and of G.  X: lane l holds raw aligned chunk l in [0,16].  G: lane l holds raw
-    // aligned chunk (l - 1) in [-1,16].  The shifted copies X_1 / G_2 take one pixel / two pixels from a neighbour lane.
-    const bool do_x = warp < cin_chunks && lane < WG_CH + 1;
-    const bool do_g = warp < g_chunks && lane < WG_GCH + 1;
-    auto load_item = [&](int item, float4* xv, float4* gv) {
-      const int n = item / NBLK, Q0 = (item % NBLK) * WG_BP;
+    // Two groups of 8 warps; group g fills stage g with every second item of this CTA.  Inside a group warps 0-3 build
+    // the X operand and warps 4-7 the G operand; a warp covers TWO channel chunks (half-warps) x 16 pixel chunks, so all
+    // 32 lanes work.  Every lane reads its own shifted pixels from global memory (L1 hits), there are no shuffles.
+    const int grp = warp >> 3, wl = warp & 7;
+    const int half = lane >> 4, j = lane & 15;
+    const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)P - 1) / (uint32_t)P);      // exact n / P for n < 2^24
+    uint8_t* st = smem_raw + (size_t)grp * Cfg::STAGE_BYTES;
+    const int first = blockIdx.x + grp * gridDim.x, stride = 2 * gridDim.x;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wl < 4) {
+      const int cc = 2 * wl + half;                        // X channel chunk of this half-warp
+      const bool act = cc < cin_chunks;
+      float4* row = reinterpret_cast<float4*>(st) + (size_t)j * WG_A_ROWS + 4 * cc;
+      auto load_x = [&](int item, float4* xv) {            // pixels q .. q+4 of the padded-linear input space
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { xv[e] = make_float4(0.f, 0.f, 0.f, 0.f); gv[e] = make_float4(0.f, 0.f, 0.f, 0.f); }
-      if (do_x) {
-        const float4* src = tc_src_chunk_ptr(in, warp, n, D);
-        int q = Q0 + 4 * lane;
-        int iy = q / P - 2, ix = q - (iy + 2) * P - 2;
+        for (int e = 0; e < 5; ++e) xv[e] = zero4;
+        if (!act) return;
+        const int n = item / NBLK, q = (item - n * NBLK) * WG_BP + 4 * j;
+        const float4* src = tc_src_chunk_ptr(in, cc, n, D);
+        const int r = (int)__umulhi((uint32_t)q, magic);
+        const int iy = r - 2, ix = q - r * P - 2;          // q..q+3 share a row (q and P are multiples of 4)
+        if (q < QN && (unsigned)iy < (unsigned)D) {
+          const float4* rp = src + (size_t)iy * D + ix;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          bool ok = q + e < QN && iy >= 0 && iy < D && ix >= 0 && ix < D;
-          if (ok) xv[e] = __ldg(src + (size_t)iy * D + ix);
-          if (++ix >= P - 2) { ix -= P; ++iy; }
+          for (int e = 0; e < 4; ++e)
+            if ((unsigned)(ix + e) < (unsigned)D) xv[e] = __ldg(rp + e);
         }
-      }
-      if (do_g) {
-        const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + warp) * D * D;
-        const int p = Q0 - 4 * (a0 + 1) + 4 * (lane - 1);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int pe = p + e;
-          const int y = pe >= 0 ? pe / P : 0;
-          const int x = pe - y * P;
-          if (pe >= 0 && y < D && x < D) gv[e] = __ldg(src + (size_t)y * D + x);
-        }
-      }
-    };
-    float4 xv[4], gv[4], xn[4], gn[4];
-    int it = 0;
-    if (have) load_item(blockIdx.x, xv, gv);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      const int next = item + gridDim.x;
-      if (next < n_items) load_item(next, xn, gn);                 // in flight while this item is stored
-      if (it >= 2) mbar_wait(&empty_bar[s], ((it >> 1) - 1) & 1);
-      uint8_t* st = smem_raw + (size_t)s * Cfg::STAGE_BYTES;
-      float4* A = reinterpret_cast<float4*>(st);
-      if (warp < cin_chunks) {                    // whole warp: shuffles must be convergent
-        // X_1 chunk j = pixels 4j+1 .. 4j+4 = own pixels 1..3 + right neighbour's pixel 0
-        float4 r0;
-        r0.x = __shfl_down_sync(0xffffffffu, xv[0].x, 1); r0.y = __shfl_down_sync(0xffffffffu, xv[0].y, 1);
-        r0.z = __shfl_down_sync(0xffffffffu, xv[0].z, 1); r0.w = __shfl_down_sync(0xffffffffu, xv[0].w, 1);
-        if (lane < WG_CH) {
-          float4* row = A + (size_t)lane * WG_A_ROWS + 4 * warp;
+        int ix4 = ix + 4, iy4 = iy;
+        if (ix4 >= P - 2) { ix4 -= P; ++iy4; }
+        if (q + 4 < QN && (unsigned)iy4 < (unsigned)D && (unsigned)ix4 < (unsigned)D) xv[4] = __ldg(src + (size_t)iy4 * D + ix4);
+      };
+      float4 xv[5], xn[5];
+      if (first < n_items) load_x(first, xv);
+      int k = 0;
+      for (int item = first; item < n_items; item += stride, ++k) {
+        if (item + stride < n_items) load_x(item + stride, xn);      // in flight while this item is stored
+        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (act) {
+          // X_0 chunk j = pixels 4j .. 4j+3, X_1 chunk j = pixels 4j+1 .. 4j+4 (transposed: one 16-byte row per channel)
           split_store(row + 0, row + 32 + 0, xv[0].x, xv[1].x, xv[2].x, xv[3].x, SPLIT3);
           split_store(row + 1, row + 32 + 1, xv[0].y, xv[1].y, xv[2].y, xv[3].y, SPLIT3);
           split_store(row + 2, row + 32 + 2, xv[0].z, xv[1].z, xv[2].z, xv[3].z, SPLIT3);
           split_store(row + 3, row + 32 + 3, xv[0].w, xv[1].w, xv[2].w, xv[3].w, SPLIT3);
-          split_store(row + 64 + 0, row + 96 + 0, xv[1].x, xv[2].x, xv[3].x, r0.x, SPLIT3);
-          split_store(row + 64 + 1, row + 96 + 1, xv[1].y, xv[2].y, xv[3].y, r0.y, SPLIT3);
-          split_store(row + 64 + 2, row + 96 + 2, xv[1].z, xv[2].z, xv[3].z, r0.z, SPLIT3);
-          split_store(row + 64 + 3, row + 96 + 3, xv[1].w, xv[2].w, xv[3].w, r0.w, SPLIT3);
+          split_store(row + 64 + 0, row + 96 + 0, xv[1].x, xv[2].x, xv[3].x, xv[4].x, SPLIT3);
+          split_store(row + 64 + 1, row + 96 + 1, xv[1].y, xv[2].y, xv[3].y, xv[4].y, SPLIT3);
+          split_store(row + 64 + 2, row + 96 + 2, xv[1].z, xv[2].z, xv[3].z, xv[4].z, SPLIT3);
+          split_store(row + 64 + 3, row + 96 + 3, xv[1].w, xv[2].w, xv[3].w, xv[4].w, SPLIT3);
         }
-      }
-      if (warp < g_chunks) {
-        // G_2 local chunk lj = pixels 4lj-2 .. 4lj+1 = left neighbour's pixels 2,3 + own pixels 0,1
-        float4 l2, l3;
-        l2.x = __shfl_up_sync(0xffffffffu, gv[2].x, 1); l2.y = __shfl_up_sync(0xffffffffu, gv[2].y, 1);
-        l2.z = __shfl_up_sync(0xffffffffu, gv[2].z, 1); l2.w = __shfl_up_sync(0xffffffffu, gv[2].w, 1);
-        l3.x = __shfl_up_sync(0xffffffffu, gv[3].x, 1); l3.y = __shfl_up_sync(0xffffffffu, gv[3].y, 1);
-        l3.z = __shfl_up_sync(0xffffffffu, gv[3].z, 1); l3.w = __shfl_up_sync(0xffffffffu, gv[3].w, 1);
-        if (lane >= 1 && lane < WG_GCH + 1) {     // local chunk lj = lane-1 in [0,17)
-          const int lj = lane - 1;
-          float4* G0 = reinterpret_cast<float4*>(st + Cfg::A_BYTES) + (size_t)lj * B_ROWS + 4 * warp;
-          float4* G2 = reinterpret_cast<float4*>(st + Cfg::A_BYTES + Cfg::G_BYTES) + (size_t)lj * B_ROWS + 4 * warp;
-          split_store(G0 + 0, G0 + NCO + 0, gv[0].x, gv[1].x, gv[2].x, gv[3].x, SPLIT3);
-          split_store(G0 + 1, G0 + NCO + 1, gv[0].y, gv[1].y, gv[2].y, gv[3].y, SPLIT3);
-          split_store(G0 + 2, G0 + NCO + 2, gv[0].z, gv[1].z, gv[2].z, gv[3].z, SPLIT3);
-          split_store(G0 + 3, G0 + NCO + 3, gv[0].w, gv[1].w, gv[2].w, gv[3].w, SPLIT3);
-          split_store(G2 + 0, G2 + NCO + 0, l2.x, l3.x, gv[0].x, gv[1].x, SPLIT3);
-          split_store(G2 + 1, G2 + NCO + 1, l2.y, l3.y, gv[0].y, gv[1].y, SPLIT3);
-          split_store(G2 + 2, G2 + NCO + 2, l2.z, l3.z, gv[0].z, gv[1].z, SPLIT3);
-          split_store(G2 + 3, G2 + NCO + 3, l2.w, l3.w, gv[0].w, gv[1].w, SPLIT3);
-          if (ky == 0 && lane >= 2) {             // raw chunks 0..15 tile the pixel space exactly once over the blocks
+        fence_proxy_async();
+        mbar_arrive(&full_bar[grp]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 5; ++e) xv[e] = xn[e];
+      }
+    } else {
+      const int cc = 2 * (wl - 4) + half;                  // G channel chunk of this half-warp
+      const bool act = cc < g_chunks;
+      const int lj = j + 1;                                // local chunks 1..16; lane j == 0 also stores chunk 0 of G_0
+      float4* G0 = reinterpret_cast<float4*>(st + Cfg::A_BYTES) + (size_t)lj * B_ROWS + 4 * cc;
+      float4* G2 = reinterpret_cast<float4*>(st + Cfg::A_BYTES + Cfg::G_BYTES) + (size_t)lj * B_ROWS + 4 * cc;
+      auto load_g = [&](int item, float4* gv, float4* gm) {  // gv: pixels p-2 .. p+3, gm: pixels p-4, p-3 (lane j == 0)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) gv[e] = zero4;
+        gm[0] = zero4; gm[1] = zero4;
+        if (!act) return;
+        const int n = item / NBLK, Q0 = (item - n * NBLK) * WG_BP;
+        const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + cc) * D * D;
+        const int p = Q0 - 4 * (a0 + 1) + 4 * lj;
+        if (p >= 0) {
+          const int y = (int)__umulhi((uint32_t)p, magic), x = p - y * P;
+          if (y < D) {
+            const float4* rp = src + (size_t)y * D + x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (x + e < D) gv[2 + e] = __ldg(rp + e);
+          }
+        }
+        const int pm = p - 4;
+        if (pm >= 0) {
+          const int y = (int)__umulhi((uint32_t)pm, magic), x = pm - y * P;
+          if (y < D) {
+            const float4* rp = src + (size_t)y * D + x;
+            if (x + 2 < D) gv[0] = __ldg(rp + 2);
+            if (x + 3 < D) gv[1] = __ldg(rp + 3);
+            if (j == 0) {
+              if (x < D) gm[0] = __ldg(rp);
+              if (x + 1 < D) gm[1] = __ldg(rp + 1);
+            }
+          }
+        }
+      };
+      float4 gv[6], gm[2], gn[6], gmn[2];
+      if (first < n_items) load_g(first, gv, gm);
+      int k = 0;
+      for (int item = first; item < n_items; item += stride, ++k) {
+        if (item + stride < n_items) load_g(item + stride, gn, gmn);
+        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (act) {
+          // G_0 chunk lj = pixels p .. p+3, G_2 chunk lj = pixels p-2 .. p+1
+          split_store(G0 + 0, G0 + NCO + 0, gv[2].x, gv[3].x, gv[4].x, gv[5].x, SPLIT3);
+          split_store(G0 + 1, G0 + NCO + 1, gv[2].y, gv[3].y, gv[4].y, gv[5].y, SPLIT3);
+          split_store(G0 + 2, G0 + NCO + 2, gv[2].z, gv[3].z, gv[4].z, gv[5].z, SPLIT3);
+          split_store(G0 + 3, G0 + NCO + 3, gv[2].w, gv[3].w, gv[4].w, gv[5].w, SPLIT3);
+          split_store(G2 + 0, G2 + NCO + 0, gv[0].x, gv[1].x, gv[2].x, gv[3].x, SPLIT3);
+          split_store(G2 + 1, G2 + NCO + 1, gv[0].y, gv[1].y, gv[2].y, gv[3].y, SPLIT3);
+          split_store(G2 + 2, G2 + NCO + 2, gv[0].z, gv[1].z, gv[2].z, gv[3].z, SPLIT3);
+          split_store(G2 + 3, G2 + NCO + 3, gv[0].w, gv[1].w, gv[2].w, gv[3].w, SPLIT3);
+          if (j == 0) {                                    // chunk 0 of G_0 (tap kx = 4 reads G_0 one chunk lower)
+            float4* Gz = G0 - B_ROWS;
+            split_store(Gz + 0, Gz + NCO + 0, gm[0].x, gm[1].x, gv[0].x, gv[1].x, SPLIT3);
+            split_store(Gz + 1, Gz + NCO + 1, gm[0].y, gm[1].y, gv[0].y, gv[1].y, SPLIT3);
+            split_store(Gz + 2, Gz + NCO + 2, gm[0].z, gm[1].z, gv[0].z, gv[1].z, SPLIT3);
+            split_store(Gz + 3, Gz + NCO + 3, gm[0].w, gm[1].w, gv[0].w, gv[1].w, SPLIT3);
+          }
+          if (ky == 0) {                                   // chunks 1..16 tile the pixel space exactly once over the blocks
+#pragma unroll
+            for (int e = 2; e < 6; ++e) {
               bias_acc.x += gv[e].x; bias_acc.y += gv[e].y; bias_acc.z += gv[e].z; bias_acc.w += gv[e].w;
             }
           }
         }
-      }
-      fence_proxy_async();
-      mbar_arrive(&full_bar[s]);
+        fence_proxy_async();
+        mbar_arrive(&full_bar[grp]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { xv[e] = xn[e]; gv[e] = gn[e]; }
+        for (int e = 0; e < 6; ++e) gv[e] = gn[e];
+        gm[0] = gmn[0]; gm[1] = gmn[1];
+      }
     }
   } else if (lane == 0) {
     // ===================== MMA issuer: per 8 pixels, [X_0;X_1] x G_0(a0) | x G_2(a0) | x G_0(a0+1) =====================
@@ -200,18 +238,21 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
   // ===================== epilogue: quadrant sums -> per-CTA partial slab =====================
   __syncthreads();                      // loaders are done with smem; reuse it as the combine buffer
   float* red = reinterpret_cast<float*>(smem_raw);         // [3 MMAs][2 taps][32 ci][NCO]: sums of the X_lo rows
-  float* s_bias = red + 3 * 2 * 32 * NCO;                  // [8 warps][4]
+  float* s_bias = red + 3 * 2 * 32 * NCO;                  // [2 groups][8 chunks][4]
   float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
-  if (warp < 8 && have) {               // nobody may touch smem before the last MMAs have consumed their operands
+  if (warp < WG_LOADERS / 32 && have) {  // nobody may touch smem before the last MMAs have consumed their operands
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
   }
-  if (warp < 8) {                        // bias partial of this CTA (ky == 0 only; fixed shuffle tree)
-    bias_acc.x = warp_sum(bias_acc.x); bias_acc.y = warp_sum(bias_acc.y);
-    bias_acc.z = warp_sum(bias_acc.z); bias_acc.w = warp_sum(bias_acc.w);
-    if (lane == 0) {
-      s_bias[warp * 4 + 0] = bias_acc.x; s_bias[warp * 4 + 1] = bias_acc.y;
-      s_bias[warp * 4 + 2] = bias_acc.z; s_bias[warp * 4 + 3] = bias_acc.w;
+  if (warp < WG_LOADERS / 32 && (warp & 7) >= 4) {   // bias partial of this CTA (ky == 0 only; fixed shuffle tree per half-warp)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      bias_acc.x += __shfl_xor_sync(0xffffffffu, bias_acc.x, o); bias_acc.y += __shfl_xor_sync(0xffffffffu, bias_acc.y, o);
+      bias_acc.z += __shfl_xor_sync(0xffffffffu, bias_acc.z, o); bias_acc.w += __shfl_xor_sync(0xffffffffu, bias_acc.w, o);
+    }
+    if ((lane & 15) == 0) {
+      float* dst = s_bias + ((warp >> 3) * 8 + 2 * ((warp & 7) - 4) + (lane >> 4)) * 4;
+      dst[0] = bias_acc.x; dst[1] = bias_acc.y; dst[2] = bias_acc.z; dst[3] = bias_acc.w;
     }
   }
   // lanes 32..63 (warp 1) and 96..127 (warp 3) hold the X_lo rows: park their sums in smem
@@ -256,10 +297,10 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
     }
   }
   if (ky == 0 && tid < g_chunks * 4)
-    slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid];       // warp w summed channel chunk w
+    slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid] + s_bias[32 + tid];   // the two loader groups
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == WG_LOADERS / 32) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int S, int n_w, int n_b, float* __restrict__ dwt,
