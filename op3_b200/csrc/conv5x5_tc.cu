@@ -286,11 +286,13 @@ int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvI
   return launch_tc<64, false>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
 }
 
-// fp32 CUDA-core kernel in exact mode, tcgen05 kernel otherwise
+// fp32 CUDA-core kernel in exact mode, tcgen05 kernel otherwise.  The 4-channel output layer of the decoder stays on the
+// CUDA cores in every mode: an MMA costs the same shared-memory operand traffic for N = 8 as for N = 64, so the tensor
+// kernel needs 0.38 ms where the FFMA kernel needs 0.21 ms (profiles/r01_launches_*.txt).
 int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
                  const float* bias, float4* out, int epi, const float4* elu_ref) {
   const int prec = op3_get_precision();
-  if (prec == OP3_PREC_FP32) return conv5x5_forward(st, N, D, in, cout, wt_ffma, bias, out, epi, elu_ref);
+  if (prec == OP3_PREC_FP32 || cout == 4) return conv5x5_forward(st, N, D, in, cout, wt_ffma, bias, out, epi, elu_ref);
   return conv5x5_tc_forward(st, prec, N, D, in, cout, wt_tc, bias, out, epi, elu_ref);
 }
 

@@ -7,8 +7,8 @@
 // A 16-byte K chunk holds 4 pixels, so a tap offset can only be applied in whole chunks; the residual phase
 // (o mod 4 = kx mod 4, the pitch is a multiple of 4) is absorbed by shifted COPIES of the operands:
 //     X_sx[q] = X[q + sx], sx in {0,1}      G_sg[m] = G[m - sg], sg in {0,2}      =>  o = 4a + sg + sx covers every phase.
-// The two X copies are stacked along M, so ONE M=128 MMA  [X_0; X_1] x G_sg  accumulates TWO taps (kx = sg and sg+1):
-// a kernel row (5 taps) costs 3 MMAs per 8 pixels instead of 5, and all 128 accumulator lanes do useful work:
+// The two X copies are stacked along M and the two G copies along N, so ONE M=128 MMA  [X_0; X_1] x [G_0 | G_2]
+// accumulates FOUR taps (kx = 0..3) and a second one ([X_0; X_1] x G_0 one chunk lower) the fifth:
 //     lanes   0..31  X_0 hi (ci)    lanes 32..63  X_0 lo      -> tap kx = sg      (3xTF32: columns [G_hi | G_lo])
 //     lanes  64..95  X_1 hi         lanes 96..127 X_1 lo      -> tap kx = sg + 1
 //   * One CTA owns one kernel ROW ky: its X window needs no halo; grid = 5 x S persistent CTAs over (image, 64-pixel
@@ -32,11 +32,11 @@ constexpr int WG_A_ROWS = 129;               // 128 rows per A chunk, +1: chunk 
 
 template <int NCO, bool SPLIT3>
 struct WgCfg {
-  static constexpr int NB = SPLIT3 ? 2 * NCO : NCO;          // B rows = accumulator columns per MMA
-  static constexpr int B_ROWS = NB + 1;                      // == 1 mod 8
+  static constexpr int NB = SPLIT3 ? 2 * NCO : NCO;          // rows of one G copy = accumulator columns per tap pair
+  static constexpr int B_ROWS = 2 * NB + 1;                  // [G_0 rows | G_2 rows] per chunk; == 1 mod 8
   static constexpr int A_BYTES = WG_CH * WG_A_ROWS * 16;
   static constexpr int G_BYTES = WG_GCH * B_ROWS * 16;
-  static constexpr int STAGE_BYTES = A_BYTES + 2 * G_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + G_BYTES;
   static constexpr int TMEM_COLS = 3 * NB <= 64 ? 64 : (3 * NB <= 128 ? 128 : 256);
 };
 
@@ -139,7 +139,7 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
       const bool act = cc < g_chunks;
       const int lj = j + 1;                                // local chunks 1..16; lane j == 0 also stores chunk 0 of G_0
       float4* G0 = reinterpret_cast<float4*>(st + Cfg::A_BYTES) + (size_t)lj * B_ROWS + 4 * cc;
-      float4* G2 = reinterpret_cast<float4*>(st + Cfg::A_BYTES + Cfg::G_BYTES) + (size_t)lj * B_ROWS + 4 * cc;
+      float4* G2 = G0 + NB;
       auto load_g = [&](int item, float4* gv, float4* gm) {  // gv: pixels p-2 .. p+3, gm: pixels p-4, p-3 (lane j == 0)
 #pragma unroll
         for (int e = 0; e < 6; ++e) gv[e] = zero4;
@@ -209,8 +209,10 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
       }
     }
   } else if (lane == 0) {
-    // ===================== MMA issuer: per 8 pixels, [X_0;X_1] x G_0(a0) | x G_2(a0) | x G_0(a0+1) =====================
-    const uint32_t idesc = make_idesc_tf32(128, NB);
+    // ===================== MMA issuer: per 8 pixels, [X_0;X_1] x [G_0|G_2](a0) (N = 2 NB) and [X_0;X_1] x G_0(a0+1) ==========
+    // An MMA's cost is its shared-memory operand traffic ((4 KB of A + 32 B x N of B) / 128 B per clock for N <= 128), so
+    // the two G copies share one read of A.
+    const uint32_t idesc2 = make_idesc_tf32(128, 2 * NB), idesc1 = make_idesc_tf32(128, NB);
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int s = it & 1;
@@ -219,17 +221,18 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
       const uint32_t st = smem_u32(smem_raw + (size_t)s * Cfg::STAGE_BYTES);
       const uint64_t ad = make_smem_desc(st, WG_A_ROWS, 8);
       const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
+      // local G chunk of X chunk jx is jx + (a0 + 1) - a:  taps kx = 0..3 -> +1, tap kx = 4 -> +0
+      const uint64_t bd2 = make_smem_desc(st + Cfg::A_BYTES + B_ROWS * 16, B_ROWS, 8);
+      const uint64_t bd1 = make_smem_desc(st + Cfg::A_BYTES, B_ROWS, 8);
+      const uint32_t b2_lo32 = (uint32_t)bd2, b2_hi32 = (uint32_t)(bd2 >> 32);
+      const uint32_t b1_lo32 = (uint32_t)bd1, b1_hi32 = (uint32_t)(bd1 >> 32);
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        // local G chunk of X chunk jx is jx + (a0 + 1) - a:  taps kx = 0..3 -> +1, tap kx = 4 -> +0
-        const int copy = m == 1 ? 1 : 0, dj = m == 2 ? 0 : 1;
-        const uint64_t bd = make_smem_desc(st + Cfg::A_BYTES + copy * Cfg::G_BYTES + dj * B_ROWS * 16, B_ROWS, 8);
-        const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
-        const uint32_t dcol = tmem_base + (uint32_t)(m * NB);
-#pragma unroll
-        for (int ks = 0; ks < WG_BP / 8; ++ks)
-          mma_tf32(dcol, a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32, b_lo32 + (uint32_t)(2 * ks * B_ROWS), b_hi32, idesc,
-                   (it > 0 || ks > 0) ? 1u : 0u);
+      for (int ks = 0; ks < WG_BP / 8; ++ks) {
+        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+        mma_tf32(tmem_base, a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32, b2_lo32 + (uint32_t)(2 * ks * B_ROWS), b2_hi32,
+                 idesc2, acc);
+        mma_tf32(tmem_base + (uint32_t)(2 * NB), a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32,
+                 b1_lo32 + (uint32_t)(2 * ks * B_ROWS), b1_hi32, idesc1, acc);
       }
       tc_commit(&empty_bar[s]);
     }
@@ -376,7 +379,7 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
 int conv5x5_wgrad_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
                        float* dwt, float* dbias) {
   const int prec = op3_get_precision();
-  if (prec == OP3_PREC_FP32) return conv5x5_wgrad(st, N, D, in, cout, dpre, scratch, dwt, dbias);
+  if (prec == OP3_PREC_FP32 || cout == 4) return conv5x5_wgrad(st, N, D, in, cout, dpre, scratch, dwt, dbias);   // see conv5x5_auto
   return conv5x5_wgrad_tc(st, prec, N, D, in, cout, dpre, scratch, dwt, dbias);
 }
 
