@@ -237,6 +237,14 @@ int op3_adam_clip(long long n, float* params, const float* grads, float* exp_avg
  * argk [G][Na] (int).  Fixed reduction order: results are bit-reproducible run to run. */
 int op3_mpc_cost(int Na, int Kp, int G, int D, const float* pred, const float* goal, float* cost, int* argk,
                  void* stream);
+/* Standalone OP3Model.get_loss (op3_model.py:313-327): colors [B][K][3][D][D], mask [B][K][1][D][D] (post-softmax),
+ * image [B][3][D][D], lambdas [B*K][Rs] -> color_probs [B][K][D][D], pixel_ll [B][D][D] (pixel_complete_log_likelihood),
+ * losses[3] = (kle_loss, complete_log_likelihood, total_loss).  scratch: op3_get_loss_scratch_floats, 8-byte aligned. */
+size_t op3_get_loss_scratch_floats(const Op3Dims* d);
+int op3_get_loss(const Op3Dims* d, const float* colors, const float* mask, const float* image, const float* post_l1,
+                 const float* post_l2, const float* prior_l1, const float* prior_l2, float* color_probs, float* pixel_ll,
+                 float* losses, float* scratch, void* stream);
+
 /* sub_images[a][k][c] = colors*mask (op3_model.py:612) from planar colours / masks */
 int op3_sub_images(long long n_slots, int D, const float* colors, const float* mask, float* out, void* stream);
 

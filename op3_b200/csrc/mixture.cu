@@ -416,6 +416,100 @@ extern "C" size_t op3_mixture_stats_floats(const Op3Dims* d) {
   return stats_layout(d->B, d->K, d->D).total;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Standalone OP3Model.get_loss (op3_model.py:313-327) on caller-provided NCHW colours and post-softmax masks.
+// ---------------------------------------------------------------------------------------------------------
+namespace op3 {
+namespace {
+
+__global__ void __launch_bounds__(MIX_THREADS) get_loss_pixels_kernel(int K, int DD, const float* __restrict__ colors,
+                                                                      const float* __restrict__ mask,
+                                                                      const float* __restrict__ image,
+                                                                      float* __restrict__ color_probs,
+                                                                      float* __restrict__ pixel_ll, double* __restrict__ partial) {
+  const int b = blockIdx.y, pix = blockIdx.x * MIX_THREADS + threadIdx.x;
+  __shared__ double s_red[MIX_THREADS];
+  double nl = 0.0;
+  if (pix < DD) {
+    const float* img = image + (size_t)b * 3 * DD;
+    const float x0 = __ldg(img + pix), x1 = __ldg(img + DD + pix), x2 = __ldg(img + 2 * DD + pix);
+    float P = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float* c = colors + (size_t)(b * K + k) * 3 * DD;
+      const float d0 = __ldg(c + pix) - x0, d1 = __ldg(c + DD + pix) - x1, d2 = __ldg(c + 2 * DD + pix) - x2;
+      const float p = expf(-(d0 * d0 + d1 * d1 + d2 * d2) / 0.06f) / 0.24805f;
+      color_probs[(size_t)(b * K + k) * DD + pix] = p;
+      P += __ldg(mask + (size_t)(b * K + k) * DD + pix) * p;
+    }
+    pixel_ll[(size_t)b * DD + pix] = P;
+    nl = -(double)logf(P + 1e-12f);
+  }
+  s_red[threadIdx.x] = nl;
+  __syncthreads();
+  for (int o = MIX_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)b * gridDim.x + blockIdx.x] = s_red[0];
+}
+
+__global__ void __launch_bounds__(256) get_loss_final_kernel(int B, int n_kl, int n_part, const double* __restrict__ partial,
+                                                             const float* __restrict__ post_l1, const float* __restrict__ post_l2,
+                                                             const float* __restrict__ prior_l1,
+                                                             const float* __restrict__ prior_l2, float beta,
+                                                             float* __restrict__ losses) {
+  __shared__ double s_kl[256], s_cl[256];
+  const int tid = threadIdx.x;
+  double kl = 0.0, cl = 0.0;
+  for (int i = tid; i < n_kl; i += 256) {
+    const float sq_ = softplus_std(post_l2[i]), spv = softplus_std(prior_l2[i]);
+    const float dm = post_l1[i] - prior_l1[i];
+    kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
+  }
+  for (int i = tid; i < n_part; i += 256) cl += partial[i];
+  s_kl[tid] = kl; s_cl[tid] = cl;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { s_kl[tid] += s_kl[tid + o]; s_cl[tid] += s_cl[tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float klf = (float)(s_kl[0] / B), clog = (float)(s_cl[0] / B);
+    losses[0] = klf;
+    losses[1] = clog;
+    losses[2] = clog + beta * klf;
+  }
+}
+
+}  // namespace
+}  // namespace op3
+
+extern "C" size_t op3_get_loss_scratch_floats(const Op3Dims* d) {
+  if (validate_dims(d) != OP3_OK) return 0;
+  return 2 * (size_t)d->B * ((d->D * d->D + MIX_THREADS - 1) / MIX_THREADS);
+}
+
+extern "C" int op3_get_loss(const Op3Dims* d, const float* colors, const float* mask, const float* image,
+                            const float* post_l1, const float* post_l2, const float* prior_l1, const float* prior_l2,
+                            float* color_probs, float* pixel_ll, float* losses, float* scratch, void* stream) {
+  OP3_TRY(validate_dims(d));
+  OP3_REQUIRE(colors && mask && image && post_l1 && post_l2 && prior_l1 && prior_l2 && color_probs && pixel_ll && losses && scratch,
+              "op3_get_loss: NULL argument");
+  OP3_REQUIRE(((uintptr_t)scratch & 7) == 0, "op3_get_loss: scratch must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int DD = d->D * d->D, tiles = (DD + MIX_THREADS - 1) / MIX_THREADS;
+  ProfScope prof(st, KID_MIXTURE, (double)d->B * DD * (6.0 * d->K + 4.0) * 4.0);
+  double* partial = reinterpret_cast<double*>(scratch);
+  get_loss_pixels_kernel<<<dim3(tiles, d->B), MIX_THREADS, 0, st>>>(d->K, DD, colors, mask, image, color_probs, pixel_ll, partial);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  get_loss_final_kernel<<<1, 256, 0, st>>>(d->B, d->B * d->K * d->Rs, d->B * tiles, partial, post_l1, post_l2, prior_l1, prior_l2,
+                                           d->beta, losses);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
 extern "C" size_t op3_mixture_bwd_scratch_floats(const Op3Dims* d) { (void)d; return 0; }
 
 // `want_loss`: bit 0 = compute LN statistics + losses (needed for loss and/or refine inputs); bit 1 = losses[3] is the

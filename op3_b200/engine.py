@@ -223,9 +223,7 @@ class Engine:
         lw = [float(w) for w in loss_schedule]
         T1 = len(schedule)
         for s in schedule:
-            if s not in (0, 1):
-                if s == 2:
-                    raise NotImplementedError("schedule code 2 (next-step refinement, 'sequence_iodine') is not built")
+            if s not in (0, 1, 2):
                 raise ValueError("Invalid schedule entry: {}".format(s))
         st = torch.cuda.current_stream(dev).cuda_stream
         d = self.dims(B)
@@ -270,7 +268,7 @@ class Engine:
             post, prior = init_state["post"], init_state["prior"]
             if post["samples"].shape[0] != B:
                 raise ValueError("initial_hidden_state batch %d != input batch %d" % (post["samples"].shape[0], B))
-            if schedule and schedule[0] == 0 and not post["lambdas1"].requires_grad:
+            if schedule and schedule[0] in (0, 2) and not post["lambdas1"].requires_grad:
                 # contract of the reference (trap T9): autograd.grad in refine() needs lambdas that require grad
                 raise RuntimeError("One of the differentiated Tensors does not require grad")
             s0.l1 = post["lambdas1"].detach().reshape(N, Rs).contiguous().float()
@@ -388,7 +386,7 @@ class Engine:
         steps, decodes = [], []
         cur, state = 0, s0
         cached = None
-        if T1 and schedule[0] == 0:
+        if T1 and schedule[0] in (0, 2):
             if images is None:
                 raise ValueError("refinement steps need images")
             cached = decode(s0, None, images[:, 0], 0.0, True, False)
@@ -398,6 +396,12 @@ class Engine:
             eps_new = noise_fn(B, K, Rs, dev).reshape(N, Rs).contiguous()
             if code == 0:
                 step = refine(state, cached, eps_new)
+            elif code == 2:
+                # next-step refinement (op3_model.py:368-376): refine on the current frame, then advance the frame index.
+                # The action goes to the refinement net as add_fc_input, which the built 'size_dependent_conv'
+                # architecture (added_fc_input_size=0) ignores (refinement_network.py:201-202).
+                step = refine(state, cached, eps_new)
+                cur += 1
             else:
                 act = None
                 if m.action_dim > 0:
@@ -407,7 +411,7 @@ class Engine:
                 step = dynamics(state, act, eps_new)
                 cur += 1
             state = step.dst
-            refine_after = i + 1 < T1 and schedule[i + 1] == 0
+            refine_after = i + 1 < T1 and schedule[i + 1] in (0, 2)
             need_img = lw[i] != 0.0 or refine_after or (i == T1 - 1 and images is not None)
             img = images[:, cur] if (need_img and images is not None) else None
             if (lw[i] != 0.0 or refine_after) and img is None:

@@ -184,8 +184,8 @@ class OP3Model(nn.Module):
     def refine(self, hidden_states, images, action=None, previous_decode_loss_info=None):
         """op3_model.py:195-264 (inference form): one refinement step on `images` (B,3,D,D).  Like the reference it
         needs posterior lambdas that require grad (a detached state must pass through a dynamics step first)."""
-        if action is not None:
-            raise NotImplementedError("next-step refinement with actions ('sequence_iodine') is not built")
+        # `action` is only forwarded to the refinement net as add_fc_input (op3_model.py:233-244); the built
+        # 'size_dependent_conv' architecture has added_fc_input_size=0 and ignores it (refinement_network.py:201-202)
         return self._step_from(hidden_states, images, None, 0)
 
     def dynamics(self, hidden_states, actions):
@@ -203,9 +203,35 @@ class OP3Model(nn.Module):
         return colors.view(B, K, 3, D, D), torch.softmax(logits, dim=1), logits
 
     def get_loss(self, hidden_states, colors, mask, target_imgs):
-        """op3_model.py:313-327 is fused into op3_mixture_fwd (softmax + likelihood + KL in one pass over the decode);
-        it has no standalone entry point here.  Use run_schedule with a non-zero loss_schedule entry."""
-        raise NotImplementedError("get_loss is fused into run_schedule (op3_mixture_fwd)")
+        """op3_model.py:313-327 as a standalone (inference-form, detached) call: colors (B,K,3,D,D), mask (B,K,1,D,D),
+        target_imgs (B,3,D,D) -> (color_probs (B,K,D,D), pixel_complete_log_likelihood (B,D,D), kle_loss,
+        complete_log_likelihood, total_loss).  Training uses the fused form inside run_schedule (op3_mixture_fwd)."""
+        import ctypes as C
+        from op3_b200 import _lib
+        from op3_b200._lib import check, ptr
+        lib = _lib.load()
+        for name, t in [("colors", colors), ("mask", mask), ("target_imgs", target_imgs)]:
+            if not t.is_cuda:
+                raise RuntimeError("op3_b200: %s is on %s; the OP3 kernels are CUDA-only (no CPU fallback)" % (name, t.device))
+        B, K, _, D, _ = colors.shape
+        dev = colors.device
+        d = self.engine.dims(B)
+        if K != d.K or D != d.D:
+            raise ValueError("colors must be (B,%d,3,%d,%d), got %s" % (d.K, d.D, d.D, tuple(colors.shape)))
+        f = lambda t, shape: t.detach().reshape(shape).contiguous().float()
+        post, prior = hidden_states["post"], hidden_states["prior"]
+        Rs = self.sto_size
+        tens = [f(colors, (B, K, 3, D, D)), f(mask, (B, K, 1, D, D)), f(target_imgs, (B, 3, D, D)),
+                f(post["lambdas1"], (B * K, Rs)), f(post["lambdas2"], (B * K, Rs)),
+                f(prior["lambdas1"].to(dev).expand(B, K, Rs), (B * K, Rs)), f(prior["lambdas2"].to(dev).expand(B, K, Rs), (B * K, Rs))]
+        color_probs = torch.empty(B, K, D, D, device=dev)
+        pixel_ll = torch.empty(B, D, D, device=dev)
+        losses = torch.empty(3, device=dev)
+        scratch = torch.empty(lib.op3_get_loss_scratch_floats(C.byref(d)) // 2 + 1, device=dev, dtype=torch.float64)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.op3_get_loss(C.byref(d), *[ptr(t) for t in tens], ptr(color_probs), ptr(pixel_ll), ptr(losses),
+                               scratch.data_ptr(), st), "op3_get_loss")
+        return color_probs, pixel_ll, losses[0], losses[1], losses[2]
 
     # ------------------------------------------------------------------ state utilities (op3_model.py:446-558)
     def get_rprp_schedule(self, seed_steps, num_images, num_refine_per_physics):

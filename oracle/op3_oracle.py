@@ -385,7 +385,7 @@ def dynamics(p, state, actions, eps, det=64):
 
 def run_schedule(p, images, actions, schedule, loss_schedule, noise, K, beta=1e-2, det=64, sto=64,
                  init_state=None, D=64):
-    """op3_model.py:333-434 (schedule codes 0 refine / 1 dynamics).  ``noise`` is consumed front to back:
+    """op3_model.py:333-434 (schedule codes 0 refine / 1 dynamics / 2 next-step refine).  ``noise`` is consumed front to back:
     one draw for the initial state (if not passed in), one per step.  Returns a dict."""
     noise = list(noise)
     B = images.shape[0] if images is not None else actions.shape[0]
@@ -397,6 +397,11 @@ def run_schedule(p, images, actions, schedule, loss_schedule, noise, K, beta=1e-
             state = refine(p, state, images[:, cur], cached, noise.pop(0), beta, D)
         elif code == 1:
             state = dynamics(p, state, None if actions is None else actions[:, cur], noise.pop(0), det)
+            cur += 1
+        elif code == 2:
+            # op3_model.py:368-376 next-step refinement: the action is handed to the refinement net as add_fc_input,
+            # which 'size_dependent_conv' (added_fc_input_size=0) ignores (refinement_network.py:201-202)
+            state = refine(p, state, images[:, cur], cached, noise.pop(0), beta, D)
             cur += 1
         else:
             raise ValueError("Invalid schedule entry: {}".format(code))

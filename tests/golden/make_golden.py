@@ -202,5 +202,7 @@ if __name__ == "__main__":
     train_case("pickplace_small", pickplace_variant, K=3, action_dim=4, B=2, T=3, schedule=[0, 0, 1, 1, 0],
                full_masks=False)
     train_case("stack_c1", stack_variant, K=7, action_dim=0, B=8, T=2, schedule=[0, 0, 0, 0, 1], full_masks=False)
+    train_case("pickplace_nextstep", pickplace_variant, K=3, action_dim=4, B=2, T=4, schedule=[0, 2, 2, 1, 0],
+               full_masks=False)
     module_case()
     mpc_case()

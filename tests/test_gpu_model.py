@@ -17,6 +17,7 @@ CASES = {
     "stack_small": dict(action_dim=0, K=3, B=2, T=2, schedule=[0, 0, 1]),
     "pickplace_small": dict(action_dim=4, K=3, B=2, T=3, schedule=[0, 0, 1, 1, 0]),
     "stack_c1": dict(action_dim=0, K=7, B=8, T=2, schedule=[0, 0, 0, 0, 1]),
+    "pickplace_nextstep": dict(action_dim=4, K=3, B=2, T=4, schedule=[0, 2, 2, 1, 0]),     # code 2: op3_model.py:368-376
 }
 
 
@@ -58,7 +59,7 @@ def test_train_step_matches_golden_and_oracle(name):
         check_summary(g, "grad/" + k, v, 2e-4, 2e-6 * gn, what=name)
 
 
-@pytest.mark.parametrize("name", ["stack_small", "pickplace_small"])
+@pytest.mark.parametrize("name", ["stack_small", "pickplace_small", "pickplace_nextstep"])
 def test_full_gradients_match_oracle(name):
     cfg = CASES[name]
     m, p, out, grads = run_ours(name, cfg)
@@ -138,3 +139,26 @@ def test_mpc_rollout_and_ranking_match_golden():
         assert np.abs(np.asarray(sc) - g[key + "sorted"]).max() <= 2e-6
         if agg == "min":
             assert np.array_equal(np.asarray(gidx), g[key + "gidx"])
+
+
+def test_get_loss_standalone_matches_oracle():
+    """OP3Model.get_loss (op3_model.py:313-327) as a public method on caller-provided colours / masks."""
+    m, p = build_model(4, 3, seed=0)
+    B, K, D = 3, 3, 64
+    g = torch.Generator().manual_seed(11)
+    colors = torch.rand(B, K, 3, D, D, generator=g)
+    mask = torch.softmax(torch.randn(B, K, 1, D, D, generator=g), 1)
+    img = (colors[:, 0] + 0.05 * torch.randn(B, 3, D, D, generator=g)).clamp(0, 1)
+    state = {"post": {"lambdas1": torch.randn(B, K, 64, generator=g), "lambdas2": torch.randn(B, K, 64, generator=g)},
+             "prior": {"lambdas1": 0.3 * torch.randn(B, K, 64, generator=g), "lambdas2": torch.randn(B, K, 64, generator=g)}}
+    want = orc.get_loss(state, colors, mask, img, 1e-2)
+    cu = lambda t: t.cuda()
+    state_cu = {a: {k: cu(v) for k, v in b.items()} for a, b in state.items()}
+    got = m.get_loss(state_cu, cu(colors), cu(mask), cu(img))
+    assert got[0].shape == (B, K, D, D) and got[1].shape == (B, D, D)
+    assert max_abs(got[0], want[0]) <= 1e-5 * want[0].abs().max().item()
+    assert max_abs(got[1], want[1]) <= 1e-5 * want[1].abs().max().item()
+    for i in (2, 3, 4):
+        assert abs(got[i].item() - want[i].item()) <= 2e-6 * abs(want[i].item()), (i, got[i].item(), want[i].item())
+    with pytest.raises(RuntimeError):
+        m.get_loss(state_cu, colors, cu(mask), cu(img))

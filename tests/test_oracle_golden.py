@@ -8,7 +8,7 @@ import torch
 from oracle import op3_oracle as orc
 from helpers import load_golden, check_summary
 
-CASES = [("stack_small", 0), ("pickplace_small", 4), ("stack_c1", 0)]
+CASES = [("stack_small", 0), ("pickplace_small", 4), ("stack_c1", 0), ("pickplace_nextstep", 4)]
 
 
 @pytest.mark.parametrize("name,action_dim", CASES)
