@@ -125,6 +125,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel, precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the family's main kernel, from the committed
+    `ncu --set full` capture (profiles/r01_ncu_traffic.json); None when that kernel/mode was not captured."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")) as f:
+            return json.load(f).get("%s/%s" % (kernel, precision), {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def mixture_roofline(model, dev, hbm_peak, which):
     """Achieved HBM GB/s of the fused mixture forward (stats + finalize + emit) on the workload's shapes, timed alone
     with CUDA events; an L2-sized buffer is overwritten between iterations."""
@@ -162,7 +172,7 @@ def mixture_roofline(model, dev, hbm_peak, which):
     alg_bytes = (11 * K + 4) * 4.0 * B * D * D
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "mixture forward (mix_stats + mix_finalize + mix_emit)", "achieved": achieved,
-            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "ms_per_call": ms,
+            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic("mixture_fwd", "any"), "ms_per_call": ms,
             "algorithmic_bytes_per_call": alg_bytes, "peak_source": which}
 
 
@@ -173,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "fp32"), choices=["fp32", "tf32x3", "tf32"],
+    ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the 5x5 convolutions (see op3_set_precision)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -299,11 +309,14 @@ def main():
         "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(B_PER_GPU * T * 3 * D * D + B_PER_GPU * T * 4 * 4), "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": fam[dom] + (" (fp32 CUDA cores)" if (args.precision == "fp32" or dom == 1) else " (tcgen05 kind::tf32, %s)" % args.precision),
+        "roofline": {"bound": "tensor", "kernel": fam[dom] + (" (fp32 CUDA cores)" if args.precision == "fp32" else " (tcgen05 kind::tf32, %s)" % args.precision),
                      "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                     "traffic": None, "avg_launch_ms": pms[dom] / max(pn[dom], 1),
+                     "traffic": ncu_traffic(("conv_fwd", "conv_wgrad")[dom], args.precision),
+                     "avg_launch_ms": pms[dom] / max(pn[dom], 1),
                      "share_of_step": pms[dom] / ms_total,
-                     "peak_source": "%s bf16_tflops_sustained / 2 (dense TF32)" % which},
+                     "peak_source": "%s bf16_tflops_sustained / 2 (dense TF32)" % which,
+                     # 3xTF32 issues three tensor-core products per algorithmic FLOP: its own ceiling is peak / 3
+                     "frac_of_mode_ceiling": achieved / (tf32_peak / (3.0 if args.precision == "tf32x3" else 1.0))},
         "roofline_mixture": mixture_roofline(model, dev, hbm, which),
         "kernel_families": fams,
     }

@@ -70,7 +70,7 @@ struct StatsLayout {
   size_t ln;        // [B][K][3][2] + [B][2] floats: (mean, 1/(std+eps)) per LayerNorm2D group
   size_t partial;   // [B][tiles][nq] doubles: raw sum / sum of squares per group, -log P sum, squared recon error
   size_t sample;    // [B][3] doubles: per-sample clog, kl, squared error (+ 2 floats of counter at the end)
-  size_t counter;   // 1 unsigned (last-block-done reduction of the loss scalars)
+  size_t counter;   // [B + 1] unsigned: tiles done per sample, samples done (last-block-done reduction of the loss scalars)
   size_t gpart;     // [B*blocks][12] doubles (LN2D parameter-gradient partials of the backward pass)
   size_t total;
 };
@@ -82,11 +82,13 @@ __host__ __device__ inline StatsLayout stats_layout(int B, int K, int D) {
   L.ln = o; o += (size_t)B * K * 6 + (size_t)B * 2; o = (o + 1) & ~(size_t)1;
   L.partial = o; o += 2 * (size_t)B * L.tiles * L.nq;
   L.sample = o; o += 2 * (size_t)B * 3;
-  L.counter = o; o += 2;
+  L.counter = o; o += (size_t)(B + 2) & ~(size_t)1;
   L.gpart = o; o += 2 * (size_t)B * ((D * D + MIX_THREADS - 1) / MIX_THREADS) * 12;
   L.total = o;
   return L;
 }
+
+__device__ __forceinline__ float softplus_std(float x) { return sqrtf(logf(1.f + expf(fminf(x, 80.f))) + 1e-5f); }
 
 // ---------------------------------------------------------------------------------------------------------
 // pass A: masks / colours / final_recon outputs + LN statistics + loss partials.
@@ -96,7 +98,7 @@ __host__ __device__ inline StatsLayout stats_layout(int B, int K, int D) {
 template <int KMAX>
 __global__ void __launch_bounds__(MIX_THREADS)
 mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long mse_bstride, int B, int K, int D,
-                 int want_stats) {
+                 int want_stats, int Rs, float beta) {
   const int DD = D * D;
   const int b = blockIdx.y, tile = blockIdx.x;
   const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
@@ -104,7 +106,7 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
   const float* img = io.image ? io.image + (size_t)b * io.image_bstride : nullptr;
   StatsLayout L = stats_layout(B, K, D);
   __shared__ double s_red[MIX_THREADS / 32][6 * 16 + 4];
-  if (want_stats && tile == 0 && b == 0 && tid == 0) *reinterpret_cast<unsigned*>(io.stats + L.counter) = 0u;
+  __shared__ bool s_last;
 
   Pixel<KMAX> px;
   float acc[6 * KMAX], shift[3 * KMAX];
@@ -187,9 +189,52 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
     for (int w = 0; w < MIX_THREADS / 32; ++w) s += s_red[w][tid];
     reinterpret_cast<double*>(io.stats + L.partial)[((size_t)b * L.tiles + tile) * L.nq + tid] = s;
   }
-}
 
-__device__ __forceinline__ float softplus_std(float x) { return sqrtf(logf(1.f + expf(fminf(x, 80.f))) + 1e-5f); }
+  // ---- loss scalars (get_loss, op3_model.py:313-327): the LAST tile of a sample sums that sample's partials (fixed
+  // order) and its KL; the last sample to finish sums the per-sample values (fixed order).  Counters are zeroed by
+  // the host (memset node) before the launch.
+  unsigned* counters = reinterpret_cast<unsigned*>(io.stats + L.counter);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&counters[b], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* part = reinterpret_cast<const double*>(io.stats + L.partial);
+  double* samp = reinterpret_cast<double*>(io.stats + L.sample);
+  double kl = 0.0;
+  for (int i = tid; i < K * Rs; i += MIX_THREADS) {
+    size_t o = (size_t)b * K * Rs + i;
+    float sq_ = softplus_std(io.post_l2[o]), spv = softplus_std(io.prior_l2[o]);
+    float dm = io.post_l1[o] - io.prior_l1[o];
+    kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
+  }
+  kl = warp_sum_d(kl);
+  __syncthreads();                       // s_red is reused
+  if (lane == 0) s_red[warp][0] = kl;
+  __syncthreads();
+  if (tid == 0) {
+    double klv = 0.0, cl = 0.0, sq = 0.0;
+#pragma unroll
+    for (int w = 0; w < MIX_THREADS / 32; ++w) klv += s_red[w][0];
+    for (int t = 0; t < L.tiles; ++t) {
+      cl += __ldcg(part + ((size_t)b * L.tiles + t) * L.nq + 6 * K + 2);
+      sq += __ldcg(part + ((size_t)b * L.tiles + t) * L.nq + 6 * K + 3);
+    }
+    samp[b * 3] = cl; samp[b * 3 + 1] = klv; samp[b * 3 + 2] = sq;
+    __threadfence();
+    if (atomicAdd(&counters[B], 1u) == (unsigned)B - 1) {
+      __threadfence();
+      cl = 0.0; klv = 0.0; sq = 0.0;
+      for (int i = 0; i < B; ++i) { cl += __ldcg(samp + i * 3); klv += __ldcg(samp + i * 3 + 1); sq += __ldcg(samp + i * 3 + 2); }
+      float clog = (float)(cl / B), klf = (float)(klv / B);
+      io.losses[0] = clog;
+      io.losses[1] = klf;
+      io.losses[2] = clog + beta * klf;
+      io.losses[3] = mse_image ? (float)(sq / ((double)B * 3.0 * D * D)) : 0.f;
+    }
+  }
+}
 
 // LN statistics of sample b, group q in [0, 3K] (q = 3K: the pixel-likelihood group): (mean, 1/(std + 1e-5)), unbiased std
 __device__ __forceinline__ float2 ln_stat_from_partials(const double* part, const StatsLayout& L, int b, int K, int q, int DD) {
@@ -205,54 +250,6 @@ __device__ __forceinline__ float2 ln_stat_from_partials(const double* part, cons
   double var = (s2 - s * s / n) / (n - 1.0);
   if (var < 0.0) var = 0.0;
   return make_float2((float)mean, 1.f / ((float)sqrt(var) + 1e-5f));
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// loss scalars: one CTA per sample (clog, squared recon error from the partials; KL over K*Rs elements), the last CTA
-// to finish sums the per-sample values in a fixed order.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) mix_loss_kernel(Op3MixtureIO io, int B, int K, int D, int Rs, float beta, int want_mse) {
-  StatsLayout L = stats_layout(B, K, D);
-  const double* part = reinterpret_cast<const double*>(io.stats + L.partial);
-  double* samp = reinterpret_cast<double*>(io.stats + L.sample);
-  const int b = blockIdx.x, tid = threadIdx.x;
-  __shared__ double s_red[128];
-  __shared__ bool s_last;
-  double kl = 0.0;
-  for (int i = tid; i < K * Rs; i += 128) {
-    size_t o = (size_t)b * K * Rs + i;
-    float sq_ = softplus_std(io.post_l2[o]), spv = softplus_std(io.prior_l2[o]);
-    float dm = io.post_l1[o] - io.prior_l1[o];
-    kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
-  }
-  s_red[tid] = kl;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (tid < o) s_red[tid] += s_red[tid + o];
-    __syncthreads();
-  }
-  if (tid == 0) {
-    double cl = 0.0, sq = 0.0;
-    for (int t = 0; t < L.tiles; ++t) {
-      cl += part[((size_t)b * L.tiles + t) * L.nq + 6 * K + 2];
-      sq += part[((size_t)b * L.tiles + t) * L.nq + 6 * K + 3];
-    }
-    samp[b * 3] = cl; samp[b * 3 + 1] = s_red[0]; samp[b * 3 + 2] = sq;
-    __threadfence();
-    unsigned done = atomicAdd(reinterpret_cast<unsigned*>(io.stats + L.counter), 1u);
-    s_last = done == (unsigned)B - 1;
-  }
-  __syncthreads();
-  if (s_last && tid == 0) {
-    __threadfence();
-    double cl = 0.0, klv = 0.0, sq = 0.0;
-    for (int i = 0; i < B; ++i) { cl += samp[i * 3]; klv += samp[i * 3 + 1]; sq += samp[i * 3 + 2]; }
-    float clog = (float)(cl / B), klf = (float)(klv / B);
-    io.losses[0] = clog;
-    io.losses[1] = klf;
-    io.losses[2] = clog + beta * klf;
-    io.losses[3] = want_mse ? (float)(sq / ((double)B * 3.0 * D * D)) : 0.f;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -529,7 +526,9 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
   // algorithmic bytes: full forward (11K+4)*4 per pixel-sample, outputs-only (8K+3... see DESIGN.md)
   ProfScope prof(st, KID_MIXTURE, (emit ? (11.0 * K + 4) : (8.0 * K + 6)) * 4.0 * B * D * D);
   dim3 gs(L.tiles, B);
-#define OP3_MIX_STATS(KM) mix_stats_kernel<KM><<<gs, MIX_THREADS, 0, st>>>(*io, io->mse_image, io->mse_image_bstride, B, K, D, want_stats)
+  if (want_stats) OP3_CHECK(cudaMemsetAsync(io->stats + L.counter, 0, (size_t)(B + 1) * sizeof(unsigned), st));
+#define OP3_MIX_STATS(KM) \
+  mix_stats_kernel<KM><<<gs, MIX_THREADS, 0, st>>>(*io, io->mse_image, io->mse_image_bstride, B, K, D, want_stats, d->Rs, d->beta)
   if (K <= 4) OP3_MIX_STATS(4); else if (K <= 8) OP3_MIX_STATS(8); else OP3_MIX_STATS(16);
 #undef OP3_MIX_STATS
   OP3_COUNT_LAUNCH();
@@ -546,9 +545,6 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
     OP3_COUNT_LAUNCH();
     OP3_LAUNCH_CHECK();
   }
-  mix_loss_kernel<<<B, 128, 0, st>>>(*io, B, K, D, d->Rs, d->beta, io->mse_image != nullptr);
-  OP3_COUNT_LAUNCH();
-  OP3_LAUNCH_CHECK();
   return OP3_OK;
 }
 

@@ -177,6 +177,31 @@ def mpc_case():
     print("mpc ok", res["cost/final_recon_sum/order"][:5])
 
 
+def mpc_large_case(Na=4096):
+    """BASELINE.json's MPC size: the reference itself (chunks of 10, op3_model.py:569-642) rolls 4096 candidate actions
+    out of the B=1 state of mpc_case and ranks them with Cost(final_recon, mse, sum) (mpc_pickplace.py:50-236)."""
+    K = 4
+    m, p = build_reference(pickplace_variant, K, 4, seed=7)
+    m.eval_mode = True
+    frames = synth_frames(1, 2, seed=31)
+    acts = synth_actions(1, 2, seed=32)[:, :, [0, 1, 3, 4]]
+    sched = np.array([0, 0, 1, 0], dtype=np.float64)
+    NOISE.load(orc.make_noise(1, K, 64, len(sched) + 1, seed=40))
+    info = m.batch_internal_inference(frames, acts, None, sched)
+    cand = synth_actions(Na, 1, seed=33)[:, :, [0, 1, 3, 4]]
+    full_noise = orc.make_noise(Na, K, 64, 1, seed=50)[0]
+    NOISE.load([full_noise[i:i + 10] for i in range(0, Na, 10)])
+    pred = m.batch_internal_inference(None, cand, info["state"], np.array([1.0]))
+    goal_image = synth_frames(1, 1, seed=34)[:, 0]
+    cost = ref_mpc.Cost(None, core_type="final_recon", compare_func="mse", post_process="raw", aggregate="sum")
+    sc, order, gidx = cost.get_action_rankings(info["state"]["post"]["samples"][0], info["sub_images"][0], goal_image,
+                                               pred["state"]["post"]["samples"], pred["sub_images"], pred["final_recon"],
+                                               plot_actions=0)
+    np.savez_compressed(os.path.join(HERE, "mpc_4096.npz"), Na=Na, K=K, sorted=np.asarray(sc, dtype=np.float32),
+                        order=np.asarray(order, dtype=np.int32))
+    print("mpc_4096 ok", np.asarray(order)[:5], np.asarray(sc)[:3])
+
+
 def schedule_case():
     """TrainingScheduler outputs (op3_trainer.py:36-111) for every schedule type under a fixed numpy seed."""
     from op3.torch.op3_modules.op3_trainer import TrainingScheduler as Ref
@@ -206,3 +231,4 @@ if __name__ == "__main__":
                full_masks=False)
     module_case()
     mpc_case()
+    mpc_large_case()

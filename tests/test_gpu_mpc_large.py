@@ -8,6 +8,7 @@ import torch
 
 from oracle import op3_oracle as orc
 from gpu_util import build_model, NoiseInjector
+from helpers import load_golden
 from op3_b200.mpc import Cost
 from op3_b200.parallel import shard_range
 
@@ -56,6 +57,21 @@ def test_mpc_4096_candidates_properties():
     assert perm[torch.argmin(cp).item()].item() == order[0].item()
     gap = (c1[order[1]] - c1[order[0]]).item() / c1[order[0]].item()
     print("4096 candidates: best %d cost %.6e, relative gap to second %.3e" % (order[0].item(), c1[order[0]].item(), gap))
+    # the reference itself on the same 4096 candidates (tests/golden/make_golden.py: mpc_large_case): selected action
+    # index-exact, sorted costs within fp32 noise, full ranking identical except between near-tied neighbours
+    g = load_golden("mpc_4096")
+    ref_order, ref_sorted = g["order"].astype(np.int64), g["sorted"]
+    ours_sorted, ours_order = c1.cpu().numpy()[order.cpu().numpy()], order.cpu().numpy()
+    assert ours_order[0] == ref_order[0], "argmin differs from the reference: %d vs %d" % (ours_order[0], ref_order[0])
+    assert np.allclose(ours_sorted, ref_sorted, rtol=2e-5, atol=0)
+    elites = Na // 10                                            # CEM keeps the top 10 % (mpc_pickplace.py:376-410)
+    assert set(ours_order[:elites].tolist()) == set(ref_order[:elites].tolist())
+    diff = np.nonzero(ours_order != ref_order)[0]
+    ours_cost = c1.cpu().numpy()
+    for i in diff:
+        a, b = ours_cost[ours_order[i]], ours_cost[ref_order[i]]
+        assert abs(a - b) <= 2e-5 * abs(a), "rank %d: candidates %d / %d are not a near tie" % (i, ours_order[i], ref_order[i])
+    print("vs reference: %d of %d ranks differ (all near ties <= 2e-5 rel)" % (len(diff), Na))
     # a small subset against the CPU oracle (same weights, state and noise)
     sub = 16
     st = info["state"]
