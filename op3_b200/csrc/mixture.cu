@@ -92,8 +92,8 @@ __device__ __forceinline__ float softplus_std(float x) { return sqrtf(logf(1.f +
 
 // ---------------------------------------------------------------------------------------------------------
 // pass A: masks / colours / final_recon outputs + LN statistics + loss partials.
-// Every thread centres its sums on the values of ITS first pixel (fp32, no cancellation), converts them to raw fp64
-// sums (sum x = S1 + n s, sum x^2 = S2 + 2 s S1 + n s^2) and the block reduces those in a fixed order.
+// Every warp centres its sums on the values of its FIRST pixel (fp32, no cancellation), reduces them with shuffles,
+// converts them to raw fp64 sums (sum x = S1 + n s, sum x^2 = S2 + 2 s S1 + n s^2) and the block adds those in a fixed order.
 // ---------------------------------------------------------------------------------------------------------
 template <int KMAX>
 __global__ void __launch_bounds__(MIX_THREADS)
@@ -134,7 +134,11 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
         if (want_stats) {
           float mg = px.mask_grad(k), lo = px.leave_out(k), cf = px.xh_coef(k);
           float x0 = cf * (px.v[k].x - px.x0), x1 = cf * (px.v[k].y - px.x1), x2 = cf * (px.v[k].z - px.x2);
-          if (npix == 0) { shift[3 * k] = mg; shift[3 * k + 1] = lo; shift[3 * k + 2] = x0; }
+          if (npix == 0) {             // warp-uniform branch: DD % 32 == 0, a warp's 32 pixels are all valid or all not
+            shift[3 * k] = __shfl_sync(0xffffffffu, mg, 0);
+            shift[3 * k + 1] = __shfl_sync(0xffffffffu, lo, 0);
+            shift[3 * k + 2] = __shfl_sync(0xffffffffu, x0, 0);
+          }
           float d = mg - shift[3 * k];
           acc[6 * k] += d; acc[6 * k + 1] += d * d;
           d = lo - shift[3 * k + 1];
@@ -149,7 +153,7 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
       fr[0] = r0; fr[DD] = r1; fr[2 * DD] = r2;
     }
     if (want_stats) {
-      if (npix == 0) shiftP = px.P;
+      if (npix == 0) shiftP = __shfl_sync(0xffffffffu, px.P, 0);
       float d = px.P - shiftP;
       accP += d; accP2 += d * d;
       accLog += -logf(px.P + 1e-12f);
@@ -163,24 +167,31 @@ mix_stats_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
   }
   if (!want_stats) return;
 
-  // raw fp64 sums -> warp shuffle -> smem -> per-(sample, tile) partial
-  const double n1 = (double)npix, n3 = 3.0 * npix;
+  // centred fp32 sums -> warp shuffle (fp32: 64 centred values) -> lane 0 converts to RAW fp64 sums -> smem -> per-(sample,
+  // tile) partial.  All lanes of a warp share lane 0's shift, so the centred sums add directly.
+  const double n1 = 32.0 * npix, n3 = 96.0 * npix;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k)
     if (k < K) {
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
-        double sft = npix ? (double)shift[3 * k + g] : 0.0, nn = g == 2 ? n3 : n1;
-        double S1 = acc[6 * k + 2 * g], S2 = acc[6 * k + 2 * g + 1];
-        double sx = warp_sum_d(S1 + nn * sft), sxx = warp_sum_d(S2 + 2.0 * sft * S1 + nn * sft * sft);
-        if (lane == 0) { s_red[warp][6 * k + 2 * g] = sx; s_red[warp][6 * k + 2 * g + 1] = sxx; }
+        float S1 = warp_sum(acc[6 * k + 2 * g]), S2 = warp_sum(acc[6 * k + 2 * g + 1]);
+        if (lane == 0) {
+          double sft = npix ? (double)shift[3 * k + g] : 0.0, nn = g == 2 ? n3 : n1;
+          s_red[warp][6 * k + 2 * g] = (double)S1 + nn * sft;
+          s_red[warp][6 * k + 2 * g + 1] = (double)S2 + 2.0 * sft * (double)S1 + nn * sft * sft;
+        }
       }
     }
   {
-    double sft = npix ? (double)shiftP : 0.0;
-    double s0 = warp_sum_d((double)accP + n1 * sft), s1 = warp_sum_d((double)accP2 + 2.0 * sft * accP + n1 * sft * sft);
-    double s2 = warp_sum_d((double)accLog), s3 = warp_sum_d((double)accSq);
-    if (lane == 0) { s_red[warp][6 * K] = s0; s_red[warp][6 * K + 1] = s1; s_red[warp][6 * K + 2] = s2; s_red[warp][6 * K + 3] = s3; }
+    float S1 = warp_sum(accP), S2 = warp_sum(accP2), S3 = warp_sum(accLog), S4 = warp_sum(accSq);
+    if (lane == 0) {
+      double sft = npix ? (double)shiftP : 0.0;
+      s_red[warp][6 * K] = (double)S1 + n1 * sft;
+      s_red[warp][6 * K + 1] = (double)S2 + 2.0 * sft * (double)S1 + n1 * sft * sft;
+      s_red[warp][6 * K + 2] = (double)S3;
+      s_red[warp][6 * K + 3] = (double)S4;
+    }
   }
   __syncthreads();
   if (tid < L.nq) {
