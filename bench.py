@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32"],
+    ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32", "f16x3"],
                     help="arithmetic of the 5x5 convolutions (see op3_set_precision)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -304,7 +304,8 @@ def main():
     line = {
         "metric": "train_sequences_per_sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split on tcgen05)", "tf32": "tf32"}[args.precision],
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split on tcgen05)", "tf32": "tf32",
+                                       "f16x3": "f32 (fp16 hi/lo split fwd/dgrad + 3xTF32 wgrad on tcgen05)"}[args.precision],
         "data": "synthetic", "config": dict(CONFIG, precision=args.precision),
         "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(B_PER_GPU * T * 3 * D * D + B_PER_GPU * T * 4 * 4), "d2h_bytes_per_step": 16},
@@ -316,7 +317,7 @@ def main():
                      "share_of_step": pms[dom] / ms_total,
                      "peak_source": "%s bf16_tflops_sustained / 2 (dense TF32)" % which,
                      # 3xTF32 issues three tensor-core products per algorithmic FLOP: its own ceiling is peak / 3
-                     "frac_of_mode_ceiling": achieved / (tf32_peak / (3.0 if args.precision == "tf32x3" else 1.0))},
+                     "frac_of_mode_ceiling": achieved / (tf32_peak / (3.0 if args.precision == "tf32x3" else (1.5 if args.precision == "f16x3" and dom == 0 else (3.0 if args.precision == "f16x3" else 1.0))))},
         "roofline_mixture": mixture_roofline(model, dev, hbm, which),
         "kernel_families": fams,
     }

@@ -90,7 +90,9 @@ unsigned long long op3_launch_count(void);
 /* Arithmetic of the 5x5 convolutions (decoder layers 2-5, refinement conv stack, forward and dgrad):
  *   0 = fp32 CUDA-core kernels (exact mode, bit-faithful fp32 products),
  *   1 = tcgen05 3xTF32 operand splitting (fp32-grade; parity mode),
- *   2 = tcgen05 1xTF32 (speed mode; operands truncated to 19 bits).
+ *   2 = tcgen05 1xTF32 (speed mode; operands rounded to 11-bit significands),
+ *   3 = tcgen05 fp16 hi/lo operand split with per-image power-of-two scaling for forward/dgrad (fp32-grade like mode 1
+ *       at half the operand bytes per FLOP); weight gradients use mode 1.
  * Process-wide; call op3_prepare again after changing it (the derived weights depend on the mode). */
 int op3_set_precision(int mode);
 int op3_get_precision(void);

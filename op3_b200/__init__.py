@@ -22,12 +22,13 @@ _ALIASES = {
 }
 
 
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "f16x3": 3}
 
 
 def set_precision(name):
     """Arithmetic of the 5x5 convolutions: 'fp32' (CUDA cores, exact), 'tf32x3' (tcgen05, fp32-grade operand
-    splitting) or 'tf32' (tcgen05, 1xTF32 speed mode).  Process-wide; derived weights are rebuilt on the next call."""
+    splitting), 'tf32' (tcgen05, 1xTF32 speed mode) or 'f16x3' (tcgen05, fp16 hi/lo split with per-image operand
+    scaling for forward/dgrad: fp32-grade like tf32x3 at half the operand bytes; weight gradients stay 3xTF32).  Process-wide; derived weights are rebuilt on the next call."""
     from . import _lib
     _lib.check(_lib.load().op3_set_precision(PRECISIONS[name]), "op3_set_precision")
 

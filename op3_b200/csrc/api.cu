@@ -55,7 +55,7 @@ extern "C" int op3_profile_collect(double* ms, double* work, long long* launches
 
 static int g_precision = OP3_PREC_FP32;
 extern "C" int op3_set_precision(int mode) {
-  if (mode < 0 || mode > 2) { op3::set_error("op3_set_precision: mode %d not in {0 fp32, 1 tf32x3, 2 tf32}", mode); return OP3_ERR_ARG; }
+  if (mode < 0 || mode > 3) { op3::set_error("op3_set_precision: mode %d not in {0 fp32, 1 tf32x3, 2 tf32, 3 f16x3}", mode); return OP3_ERR_ARG; }
   g_precision = mode;
   return OP3_OK;
 }

@@ -30,27 +30,31 @@ namespace {
 constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_THREADS = 128;
 constexpr int TC_THREADS = (LOAD_WARP0 + 4) * 32;
 
-template <int NOUT, bool SPLIT3>
+// MODE: 0 = 1xTF32, 1 = 3xTF32 (hi/lo split), 2 = fp16 hi/lo split (K = 16 per MMA, per-image operand scaling)
+template <int NOUT, int MODE>
 struct TcCfg {
+  static constexpr bool SPLIT3 = MODE != 0;
+  static constexpr bool F16 = MODE == 2;
   static constexpr int NB = SPLIT3 ? 2 * NOUT : NOUT;            // B rows per tap slab = TMEM columns per tile
   static constexpr int GMAX = 256 / NB;                          // tiles per item: two accumulator buffers in 512 columns
   static constexpr int NSTAGE = SPLIT3 ? 2 : (NOUT == 64 ? 2 : 3);
   static_assert(GMAX >= 1 && 2 * GMAX * NB <= 512, "accumulators exceed TMEM");
 };
 
-template <int NOUT, bool SPLIT3>
+template <int NOUT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ wt, const float* __restrict__ bias,
                   int cout_real, float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
-                  const float4* __restrict__ ref) {
-  using Cfg = TcCfg<NOUT, SPLIT3>;
+                  const float4* __restrict__ ref, const uint32_t* __restrict__ maxbits, const float* __restrict__ wscale) {
+  using Cfg = TcCfg<NOUT, MODE>;
   constexpr int NB = Cfg::NB, NSTAGE = Cfg::NSTAGE;
+  constexpr bool SPLIT3 = Cfg::SPLIT3, F16 = Cfg::F16;
   const int P = D + 4;                                   // padded row pitch
   const int PH = 128 * G + 4 * P + 4;                    // halo pixels of one group
   const int tiles_img = (D * P + 127) / 128;
   const int groups_img = (tiles_img + G - 1) / G;
   const int n_items = N * groups_img;
-  const int ngroups = (in.total_chunks + 1) / 2;         // K groups of 8 channels
+  const int ngroups = F16 ? (in.total_chunks + 3) / 4 : (in.total_chunks + 1) / 2;   // K groups of 16 / 8 channels
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -89,29 +93,70 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
         float4* w_s = reinterpret_cast<float4*>(st + a_bytes * (SPLIT3 ? 2 : 1));
         const float4* wsrc = reinterpret_cast<const float4*>(wt) + (size_t)cg * (25 * 2 * NB);
         for (int e = lt; e < 25 * 2 * NB; e += LOAD_THREADS) cp_async16(&w_s[e], &wsrc[e], true);
-        for (int kc = 0; kc < 2; ++kc) {
-          const int c = cg * 2 + kc;
-          const float4* src = c < in.total_chunks ? tc_src_chunk_ptr(in, c, n, D) : nullptr;
-          int q = q0 + lt;
-          int iy = q / P - 2, ix = q % P - 2;
-          for (int h = lt; h < PH; h += LOAD_THREADS) {
-            bool ok = src != nullptr && iy >= 0 && iy < D && ix >= 0 && ix < D;
-            cp_async16(&a_raw[kc * PH + h], ok ? src + (size_t)iy * D + ix : reinterpret_cast<const float4*>(wt), ok);
-            ix += LOAD_THREADS;                          // advance LOAD_THREADS pixels in padded-linear space
-            while (ix >= P - 2) { ix -= P; ++iy; }
+        if (F16) {
+          // fp32 planes -> registers -> scaled fp16 hi / lo, 8 channels (two float4 chunks) per 16-byte row
+          const float sc = __uint_as_float(f16_scale_bits(maxbits[n]));
+          uint4* a_hi16 = reinterpret_cast<uint4*>(st);
+          uint4* a_lo16 = reinterpret_cast<uint4*>(st + a_bytes);
+          for (int kc = 0; kc < 2; ++kc) {
+            const int c = cg * 4 + 2 * kc;
+            const float4* src0 = c < in.total_chunks ? tc_src_chunk_ptr(in, c, n, D) : nullptr;
+            const float4* src1 = c + 1 < in.total_chunks ? tc_src_chunk_ptr(in, c + 1, n, D) : nullptr;
+            int q = q0 + lt;
+            int iy = q / P - 2, ix = q % P - 2;
+            for (int h0 = lt; h0 < PH; h0 += 4 * LOAD_THREADS) {
+              float4 v0[4], v1[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const bool ok = h0 + u * LOAD_THREADS < PH && iy >= 0 && iy < D && ix >= 0 && ix < D;
+                const size_t off = (size_t)iy * D + ix;
+                v0[u] = (ok && src0) ? __ldg(src0 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v1[u] = (ok && src1) ? __ldg(src1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ix += LOAD_THREADS;
+                while (ix >= P - 2) { ix -= P; ++iy; }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int h = h0 + u * LOAD_THREADS;
+                if (h < PH) {
+                  uint4 hi, lo;
+                  f16_split2(v0[u].x * sc, v0[u].y * sc, hi.x, lo.x);
+                  f16_split2(v0[u].z * sc, v0[u].w * sc, hi.y, lo.y);
+                  f16_split2(v1[u].x * sc, v1[u].y * sc, hi.z, lo.z);
+                  f16_split2(v1[u].z * sc, v1[u].w * sc, hi.w, lo.w);
+                  a_hi16[kc * PH + h] = hi;
+                  a_lo16[kc * PH + h] = lo;
+                }
+              }
+            }
           }
+          cp_async_commit();
+          cp_async_wait<0>();
+        } else {
+          for (int kc = 0; kc < 2; ++kc) {
+            const int c = cg * 2 + kc;
+            const float4* src = c < in.total_chunks ? tc_src_chunk_ptr(in, c, n, D) : nullptr;
+            int q = q0 + lt;
+            int iy = q / P - 2, ix = q % P - 2;
+            for (int h = lt; h < PH; h += LOAD_THREADS) {
+              bool ok = src != nullptr && iy >= 0 && iy < D && ix >= 0 && ix < D;
+              cp_async16(&a_raw[kc * PH + h], ok ? src + (size_t)iy * D + ix : reinterpret_cast<const float4*>(wt), ok);
+              ix += LOAD_THREADS;                          // advance LOAD_THREADS pixels in padded-linear space
+              while (ix >= P - 2) { ix -= P; ++iy; }
+            }
+          }
+          cp_async_commit();
+          cp_async_wait<0>();
+          // round the granules this thread loaded itself to tf32 (and split off a_lo in 3xTF32 mode)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int h = lt; h < PH; h += LOAD_THREADS) {
+              float4 v = a_raw[kc * PH + h];
+              float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+              a_raw[kc * PH + h] = hi;
+              if (SPLIT3)
+                a_lo[kc * PH + h] = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+            }
         }
-        cp_async_commit();
-        cp_async_wait<0>();
-        // round the granules this thread loaded itself to tf32 (and split off a_lo in 3xTF32 mode)
-        for (int kc = 0; kc < 2; ++kc)
-          for (int h = lt; h < PH; h += LOAD_THREADS) {
-            float4 v = a_raw[kc * PH + h];
-            float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-            a_raw[kc * PH + h] = hi;
-            if (SPLIT3)
-              a_lo[kc * PH + h] = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
-          }
         fence_proxy_async();
         mbar_arrive(&full_bar[s]);
       }
@@ -119,8 +164,8 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc1 = make_idesc_tf32(128, NB);
-      const uint32_t idesc2 = make_idesc_tf32(128, NOUT);
+      const uint32_t idesc1 = F16 ? make_idesc_f16(128, NB) : make_idesc_tf32(128, NB);
+      const uint32_t idesc2 = F16 ? make_idesc_f16(128, NOUT) : make_idesc_tf32(128, NOUT);
       int it = 0, j = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
         const int grp = item % groups_img;
@@ -146,8 +191,13 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
             for (int tap = 0; tap < 25; ++tap) {
               const uint32_t aoff = (uint32_t)(128 * t + (tap / 5) * P + (tap % 5));   // 16-byte units
               const uint32_t boff = (uint32_t)(tap * 2 * NB);
-              mma_tf32(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
-              if (SPLIT3) mma_tf32(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
+              if (F16) {
+                mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
+                mma_f16(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
+              } else {
+                mma_tf32(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
+                if (SPLIT3) mma_tf32(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
+              }
             }
           }
           tc_commit(&empty_bar[s]);                      // smem stage free once these MMAs have read it
@@ -164,6 +214,8 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
       const int ntile = min(G, tiles_img - grp * G);
       const int q0 = grp * G * 128;
       const int buf = j & 1;
+      float inv_scale = 1.f;
+      if (F16) inv_scale = 1.f / (__uint_as_float(f16_scale_bits(maxbits[n])) * __ldg(wscale));   // powers of two: exact
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       for (int t = half; t < ntile; t += 2) {
@@ -189,7 +241,7 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
           for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + NOUT + c0, u + c0);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < NOUT; ++i) v[i] += u[i];
+          for (int i = 0; i < NOUT; ++i) v[i] = F16 ? (v[i] + u[i]) * inv_scale : v[i] + u[i];
         } else {
           tmem_ld_wait();
         }
@@ -220,22 +272,38 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
 
 int g_num_sms = 0;
 
-template <int NOUT, bool SPLIT3>
+// per-image largest magnitude of a conv input (fp32 bit pattern; non-negative floats order like unsigned ints)
+__global__ void __launch_bounds__(256) tc_absmax_kernel(ConvInput in, int D, uint32_t* __restrict__ maxbits) {
+  const int n = blockIdx.x, c = blockIdx.y;
+  const float4* src = tc_src_chunk_ptr(in, c, n, D);
+  float m = 0.f;
+  if (src)
+    for (int i = threadIdx.x; i < D * D; i += 256) {
+      const float4 v = __ldg(src + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&maxbits[n], __float_as_uint(m));
+}
+
+template <int NOUT, int MODE>
 int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* wt, const float* bias, int cout_real,
-              float4* out, int out_planes, int out_chunk0, int out_chunks, int epi, const float4* ref) {
-  using Cfg = TcCfg<NOUT, SPLIT3>;
+              float4* out, int out_planes, int out_chunk0, int out_chunks, int epi, const float4* ref,
+              const uint32_t* maxbits, const float* wscale) {
+  using Cfg = TcCfg<NOUT, MODE>;
   const int P = D + 4;
   int G = Cfg::GMAX;
   size_t smem = 0;
   for (; G >= 1; --G) {
     const int PH = 128 * G + 4 * P + 4;
-    smem = (size_t)Cfg::NSTAGE * ((size_t)2 * PH * 16 * (SPLIT3 ? 2 : 1) + 25 * 2 * Cfg::NB * 16);
+    smem = (size_t)Cfg::NSTAGE * ((size_t)2 * PH * 16 * (Cfg::SPLIT3 ? 2 : 1) + 25 * 2 * Cfg::NB * 16);
     if (smem <= 226 * 1024) break;
   }
   OP3_REQUIRE(G >= 1, "conv5x5_tc: D=%d does not fit in shared memory", D);
   static bool attr_set = false;
   if (!attr_set) {
-    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tc_kernel<NOUT, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tc_kernel<NOUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   if (g_num_sms == 0) {
@@ -247,8 +315,8 @@ int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* w
   const int groups_img = (tiles_img + G - 1) / G;
   const int n_items = N * groups_img;
   const int grid = n_items < g_num_sms ? n_items : g_num_sms;      // persistent: one CTA per SM
-  conv5x5_tc_kernel<NOUT, SPLIT3><<<grid, TC_THREADS, smem, st>>>(in, N, D, G, wt, bias, cout_real, out, out_planes,
-                                                                  out_chunk0, out_chunks, epi, ref);
+  conv5x5_tc_kernel<NOUT, MODE><<<grid, TC_THREADS, smem, st>>>(in, N, D, G, wt, bias, cout_real, out, out_planes,
+                                                                out_chunk0, out_chunks, epi, ref, maxbits, wscale);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
@@ -260,40 +328,64 @@ int tc_nout(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 
 size_t conv5x5_tc_weight_floats(int cin_pad, int cout) {
   const int groups = (cin_pad / 4 + 1) / 2;
-  return (size_t)groups * 25 * 2 * (2 * tc_nout(cout)) * 4;       // sized for the 3x layout (hi and lo rows)
+  return (size_t)groups * 25 * 2 * (2 * tc_nout(cout)) * 4 + 8;   // sized for the 3x layout (hi and lo rows) / 2 fp16 slabs + scales
 }
 
+// one fp16 slab: [K group of 16 ci][tap 25][k-chunk 2][row 2*nout][8 halves], then 4 floats whose first is the weight scale
+size_t conv5x5_tc_f16_slab_floats(int cin_pad, int nout) {
+  const int groups16 = (cin_pad / 4 + 3) / 4;
+  return (size_t)groups16 * 25 * 2 * (2 * nout) * 4 + 4;
+}
+
+size_t tc_scratch_floats(int N) { return ((size_t)N + 3) & ~(size_t)3; }
+
 // Weight slab layout consumed by the kernel (built by op3_prepare): [K group of 8 ci][tap 25][k-chunk 2][row NB][4 ci]
-// with NB = nout rows (1xTF32: rn_tf32(w)) or 2*nout rows (3xTF32: hi rows, then lo rows).  cout = 64 in 3xTF32 mode is
+// with NB = nout rows (1xTF32: rn_tf32(w)) or 2*nout rows (3xTF32: hi rows, then lo rows).  cout = 64 in the split modes is
 // stored and run as two independent halves of 32 output channels (TMEM / smem budget).
 int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float* wt,
-                       const float* bias, float4* out, int epi, const float4* elu_ref) {
+                       const float* bias, float4* out, int epi, const float4* elu_ref, float* tc_scratch) {
   if (N <= 0) return OP3_OK;
   OP3_REQUIRE(cout % 4 == 0 && cout <= 64, "conv5x5_tc: unsupported cout=%d", cout);
   const int cin_real = in.real_cin ? in.real_cin : in.total_chunks * 4;
   ProfScope prof(st, KID_CONV_FWD, 2.0 * 25 * cin_real * (cout == 20 ? 17 : cout) * (double)N * D * D);
   const int nout = tc_nout(cout);
   const int planes = cout / 4;
-  if (precision == OP3_PREC_TF32X3) {
-    if (nout == 16) return launch_tc<16, true>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
-    if (nout == 32) return launch_tc<32, true>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
-    const size_t half = (size_t)((in.total_chunks + 1) / 2) * 25 * 2 * 64 * 4;
-    OP3_TRY((launch_tc<32, true>(st, N, D, in, wt, bias, 32, out, planes, 0, 8, epi, elu_ref)));
-    return launch_tc<32, true>(st, N, D, in, wt + half, bias ? bias + 32 : nullptr, cout - 32, out, planes, 8, planes - 8, epi, elu_ref);
+  if (precision == OP3_PREC_F16X3) {
+    OP3_REQUIRE(tc_scratch != nullptr, "conv5x5_tc: the fp16 mode needs tc_scratch");
+    uint32_t* maxbits = reinterpret_cast<uint32_t*>(tc_scratch);
+    OP3_CHECK(cudaMemsetAsync(maxbits, 0, (size_t)N * sizeof(uint32_t), st));
+    tc_absmax_kernel<<<dim3(N, in.total_chunks), 256, 0, st>>>(in, D, maxbits);
+    OP3_COUNT_LAUNCH();
+    OP3_LAUNCH_CHECK();
+    const int h_nout = nout == 64 ? 32 : nout;
+    const size_t slab = conv5x5_tc_f16_slab_floats(in.total_chunks * 4, h_nout);
+    if (nout == 16) return launch_tc<16, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
+    if (nout == 32) return launch_tc<32, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
+    OP3_TRY((launch_tc<32, 2>(st, N, D, in, wt, bias, 32, out, planes, 0, 8, epi, elu_ref, maxbits, wt + slab - 4)));
+    return launch_tc<32, 2>(st, N, D, in, wt + slab, bias ? bias + 32 : nullptr, cout - 32, out, planes, 8, planes - 8, epi, elu_ref,
+                            maxbits, wt + 2 * slab - 4);
   }
-  if (nout == 16) return launch_tc<16, false>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
-  if (nout == 32) return launch_tc<32, false>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
-  return launch_tc<64, false>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref);
+  if (precision == OP3_PREC_TF32X3) {
+    if (nout == 16) return launch_tc<16, 1>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, nullptr, nullptr);
+    if (nout == 32) return launch_tc<32, 1>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, nullptr, nullptr);
+    const size_t half = (size_t)((in.total_chunks + 1) / 2) * 25 * 2 * 64 * 4;
+    OP3_TRY((launch_tc<32, 1>(st, N, D, in, wt, bias, 32, out, planes, 0, 8, epi, elu_ref, nullptr, nullptr)));
+    return launch_tc<32, 1>(st, N, D, in, wt + half, bias ? bias + 32 : nullptr, cout - 32, out, planes, 8, planes - 8, epi, elu_ref,
+                            nullptr, nullptr);
+  }
+  if (nout == 16) return launch_tc<16, 0>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, nullptr, nullptr);
+  if (nout == 32) return launch_tc<32, 0>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, nullptr, nullptr);
+  return launch_tc<64, 0>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, nullptr, nullptr);
 }
 
 // fp32 CUDA-core kernel in exact mode, tcgen05 kernel otherwise.  The 4-channel output layer of the decoder stays on the
 // CUDA cores in every mode: an MMA costs the same shared-memory operand traffic for N = 8 as for N = 64, so the tensor
 // kernel needs 0.38 ms where the FFMA kernel needs 0.21 ms (profiles/r01_launches_*.txt).
 int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
-                 const float* bias, float4* out, int epi, const float4* elu_ref) {
+                 const float* bias, float4* out, int epi, const float4* elu_ref, float* tc_scratch) {
   const int prec = op3_get_precision();
   if (prec == OP3_PREC_FP32 || cout == 4) return conv5x5_forward(st, N, D, in, cout, wt_ffma, bias, out, epi, elu_ref);
-  return conv5x5_tc_forward(st, prec, N, D, in, cout, wt_tc, bias, out, epi, elu_ref);
+  return conv5x5_tc_forward(st, prec, N, D, in, cout, wt_tc, bias, out, epi, elu_ref, tc_scratch);
 }
 
 }  // namespace op3

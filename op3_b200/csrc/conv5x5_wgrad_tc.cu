@@ -354,7 +354,7 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
               "conv5x5_wgrad_tc: unsupported cin chunks %d / cout %d / D %d", in.total_chunks, cout, D);
   const int cin_real = in.real_cin ? in.real_cin : in.total_chunks * 4;
   ProfScope prof(st, KID_CONV_WGRAD, 2.0 * 25 * cin_real * cout * (double)N * D * D);
-  const bool s3 = precision == OP3_PREC_TF32X3;
+  const bool s3 = precision != OP3_PREC_TF32;       // the fp16 forward mode keeps 3xTF32 weight gradients
   const int planes = cout / 4;
   const int cin_pad = in.total_chunks * 4;
   const size_t slab = (size_t)25 * cin_pad * cout + cout;

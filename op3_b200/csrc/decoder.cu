@@ -110,13 +110,13 @@ using namespace op3;
 
 extern "C" size_t op3_decoder_acts_floats(const Op3Dims* d, int N) {
   if (validate_dims(d) != OP3_OK) return 0;
-  return (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) + 4 * (size_t)N * 32 * d->D * d->D;
+  return (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) + 4 * (size_t)N * 32 * d->D * d->D + tc_scratch_floats(N);
 }
 
 extern "C" size_t op3_decoder_scratch_floats(const Op3Dims* d, int N) {
   if (validate_dims(d) != OP3_OK) return 0;
   return 2 * (size_t)N * 32 * d->D * d->D + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) +
-         conv5x5_wgrad_scratch_floats(32, 32);
+         conv5x5_wgrad_scratch_floats(32, 32) + tc_scratch_floats(N);
 }
 
 extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const float* z, float* acts, float* out,
@@ -127,6 +127,7 @@ extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const
   PrepLayout L = prep_layout(d);
   const int R = d->Rd + d->Rs, D = d->D;
   DecActs A = dec_acts(d, N, acts);
+  float* tcs = acts + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) + 4 * (size_t)N * 32 * D * D;   // fp16-mode operand maxima
   // T[n][cls*32+co] = b[co] + sum_c z[n][c] * Wsum[cls*32+co][c]
   OP3_TRY(gemm(st, N, NCLS * 32, R, z, R, 0, prep + L.wsum, R, 1, A.T, NCLS * 32, prep + L.biasT, ACT_NONE, 0));
   dim3 grid(ceil_div(8 * D * D, 256), N);
@@ -136,9 +137,9 @@ extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const
   // layers 2-4 are the implicit-GEMM hot spot (M = N*D*D pixels, N = 32, K = 800); layer 5 has 4 outputs
   for (int i = 0; i < 3; ++i)
     OP3_TRY(conv5x5_auto(st, N, D, single_src(A.a[i], 8), 32, prep + L.dec_wf[i], prep + L.dec_tf[i], prep + L.dec_bf[i],
-                         A.a[i + 1], EPI_ELU, nullptr));
+                         A.a[i + 1], EPI_ELU, nullptr, tcs));
   OP3_TRY(conv5x5_auto(st, N, D, single_src(A.a[3], 8), 4, prep + L.dec_wf[3], prep + L.dec_tf[3], prep + L.dec_bf[3],
-                       reinterpret_cast<float4*>(out), EPI_NONE, nullptr));
+                       reinterpret_cast<float4*>(out), EPI_NONE, nullptr, tcs));
   return OP3_OK;
 }
 
@@ -155,6 +156,7 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
   float4* gbuf[2] = {reinterpret_cast<float4*>(scratch), reinterpret_cast<float4*>(scratch + plane)};
   float* dT = scratch + 2 * plane;
   float* wscr = dT + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3);
+  float* tcs = wscr + conv5x5_wgrad_scratch_floats(32, 32);
 
   // layer 5 (32 -> 4, no activation): g5 = d_out
   const float4* g = reinterpret_cast<const float4*>(d_out);
@@ -165,7 +167,7 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
     float4* gn = gbuf[i & 1];
     // dgrad: conv over g with flipped/transposed weights, times ELU'(a[i]) -> dPre of the layer below
     OP3_TRY(conv5x5_auto(st, N, D, single_src(g, gch), 32, prep + L.dec_wd[i], prep + L.dec_td[i], nullptr, gn,
-                         EPI_MUL_ELUGRAD, A.a[i]));
+                         EPI_MUL_ELUGRAD, A.a[i], tcs));
     g = gn;
     gch = 8;
   }

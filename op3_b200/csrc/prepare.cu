@@ -107,6 +107,47 @@ __global__ void prep_tc_kernel(const float* __restrict__ W, int cout_src, int ci
   slab[i] = w;
 }
 
+// fp16 mode: scale[0] = power of two that brings max|W| into [2^13, 2^14) (see f16_scale_bits); one block
+__global__ void __launch_bounds__(1024) prep_wscale_kernel(const float* __restrict__ W, int n, float* __restrict__ scale) {
+  __shared__ float s_m[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(W[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 32; ++i) m = fmaxf(m, s_m[i]);
+    scale[0] = __uint_as_float(f16_scale_bits(__float_as_uint(m)));
+    scale[1] = scale[2] = scale[3] = 0.f;
+  }
+}
+
+// fp16 slab: [K group of 16 ci][tap 25][k-chunk 2][row 2*nout][8 halves]; rows [0,nout) = rn_f16(s w), rows [nout,2nout) =
+// rn_f16(s w - hi); same channel mapping as prep_tc_kernel.
+__global__ void prep_tc_f16_kernel(const float* __restrict__ W, int cout_src, int cin_src, int mode, int transposed,
+                                   int groups16, int nout, int co_base, const float* __restrict__ scale,
+                                   __half* __restrict__ slab) {
+  const int NB = 2 * nout;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int tot = groups16 * 25 * 2 * NB * 8;
+  if (i >= tot) return;
+  int e = i % 8, row = (i / 8) % NB, kc = (i / (8 * NB)) % 2, tap = (i / (16 * NB)) % 25, g = i / (400 * NB);
+  int k_in = g * 16 + kc * 8 + e;                // GEMM K channel
+  int n_out = (row % nout) + co_base;            // GEMM N channel
+  float w = 0.f;
+  if (!transposed) {
+    int ci = mode == 1 ? ref_l1_channel(k_in) : k_in;
+    if (ci >= 0 && ci < cin_src && n_out < cout_src) w = W[((size_t)n_out * cin_src + ci) * 25 + tap];
+  } else {
+    int ci = mode == 1 ? ref_l1_channel(n_out) : n_out;   // layer input channel = GEMM output
+    if (ci >= 0 && ci < cin_src && k_in < cout_src) w = W[((size_t)k_in * cin_src + ci) * 25 + (24 - tap)];
+  }
+  const float ws = w * scale[0];
+  const __half hi = __float2half_rn(ws);
+  slab[i] = row < nout ? hi : __float2half_rn(ws - __half2float(hi));
+}
+
 // ---- gradient folding ------------------------------------------------------------------------------------
 __global__ void fin_conv_kernel(const float* __restrict__ dwf, const float* __restrict__ dbf, int cout, int cin,
                                 int cin_pad, int mode, float* __restrict__ dW, float* __restrict__ db) {
@@ -209,6 +250,22 @@ extern "C" int op3_prepare(const Op3Dims* d, const Op3Params* p, float* prep, vo
     const int s3 = prec == OP3_PREC_TF32X3;
     auto build = [&](const float* W, int cout_src, int cin_src, int mode, int transposed, int gemm_cin_pad, int gemm_cout,
                      float* slab) {
+      if (prec == OP3_PREC_F16X3) {
+        const int nout_full = tc_nout(gemm_cout);
+        const int halves = nout_full == 64 ? 2 : 1, nout = halves == 2 ? 32 : nout_full;
+        const int groups16 = (gemm_cin_pad / 4 + 3) / 4;
+        const size_t per = conv5x5_tc_f16_slab_floats(gemm_cin_pad, nout);
+        const int tot = groups16 * 25 * 2 * (2 * nout) * 8;
+        for (int h = 0; h < halves; ++h) {
+          float* base = slab + (size_t)h * per;
+          prep_wscale_kernel<<<1, 1024, 0, st>>>(W, cout_src * cin_src * 25, base + per - 4);
+          OP3_COUNT_LAUNCH();
+          prep_tc_f16_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(W, cout_src, cin_src, mode, transposed, groups16, nout, 32 * h,
+                                                                base + per - 4, reinterpret_cast<__half*>(base));
+          OP3_COUNT_LAUNCH();
+        }
+        return;
+      }
       const int groups = (gemm_cin_pad / 4 + 1) / 2;
       const int nout_full = tc_nout(gemm_cout);
       const int halves = (s3 && nout_full == 64) ? 2 : 1;          // see conv5x5_tc_forward

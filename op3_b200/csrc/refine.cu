@@ -220,6 +220,8 @@ inline size_t ref_acts_floats(const Op3Dims* d) {
   const size_t N = (size_t)d->B * d->K, DD = (size_t)d->D * d->D;
   return N * (64 + d->Rs) * DD + N * (d->Rs + HID + 5 * d->Rs + 4 * LSTM + 2 * d->Rs);
 }
+inline size_t ref_acts_total(const Op3Dims* d) { return ((ref_acts_floats(d) + 3) & ~(size_t)3) + tc_scratch_floats(d->B * d->K); }
+inline float* ref_acts_tcs(const Op3Dims* d, float* base) { return base + ((ref_acts_floats(d) + 3) & ~(size_t)3); }
 
 inline ConvInput refine_l1_input(const Op3Dims* d, const Op3RefineIO* io, const float* prep, const PrepLayout& L) {
   ConvInput in{};
@@ -271,7 +273,7 @@ extern "C" int op3_state_bwd(const Op3Dims* d, int N, const float* l1, const flo
 
 extern "C" size_t op3_refine_acts_floats(const Op3Dims* d) {
   if (validate_dims(d) != OP3_OK) return 0;
-  return ref_acts_floats(d);
+  return ref_acts_total(d);
 }
 
 extern "C" size_t op3_refine_scratch_floats(const Op3Dims* d) {
@@ -280,7 +282,8 @@ extern "C" size_t op3_refine_scratch_floats(const Op3Dims* d) {
   size_t w = conv5x5_wgrad_scratch_floats(32, d->Rs);
   size_t w2 = conv5x5_wgrad_scratch_floats(32, 32);
   if (w2 > w) w = w2;
-  return N * (d->Rs + 64) * DD + N * (4 * LSTM + HID + 5 * d->Rs + LSTM + HID + d->Rs) + w;
+  return N * (d->Rs + 64) * DD + N * (4 * LSTM + HID + 5 * d->Rs + LSTM + HID + d->Rs) + ((w + 3) & ~(size_t)3) +
+         tc_scratch_floats((int)N);
 }
 
 extern "C" int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float* prep, const Op3RefineIO* io,
@@ -294,10 +297,11 @@ extern "C" int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float*
   const int XW = HID + 5 * Rs;
   PrepLayout L = prep_layout(d);
   RefActs A = ref_acts(d, io->acts);
+  float* tcs = ref_acts_tcs(d, io->acts);
   // conv stack 17(20) -> 32 -> 32 -> Rs, ELU each (refinement_network.py:195)
-  OP3_TRY(conv5x5_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr, tcs));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr, tcs));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr, tcs));
   avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
@@ -331,11 +335,12 @@ extern "C" int op3_refine_net_fwd(const Op3Dims* d, const Op3Params* p, const fl
   const int XW = HID + 5 * Rs;
   PrepLayout L = prep_layout(d);
   RefActs A = ref_acts(d, acts);
+  float* tcs = ref_acts_tcs(d, acts);
   ConvInput in = one_src(reinterpret_cast<const float4*>(in_chunks), 5);
   in.real_cin = 17;
-  OP3_TRY(conv5x5_auto(st, N, D, in, 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr));
+  OP3_TRY(conv5x5_auto(st, N, D, in, 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr, tcs));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr, tcs));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr, tcs));
   avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
@@ -377,6 +382,11 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   float* dfc = scratch + o; o += (size_t)N * HID;   // (unused separately: dX[:, :HID] is used in place)
   float* dpool = scratch + o; o += (size_t)N * Rs;
   float* wscr = scratch + o;
+  {
+    size_t w = conv5x5_wgrad_scratch_floats(32, Rs), w2 = conv5x5_wgrad_scratch_floats(32, 32);
+    o += ((w > w2 ? w : w2) + 3) & ~(size_t)3;
+  }
+  float* tcs = scratch + o;               // fp16-mode operand maxima
   (void)dfc;
 
   // heads: lam = h2 W^T + b
@@ -426,11 +436,11 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   OP3_TRY(conv5x5_wgrad_auto(st, N, D, one_src(A.r2, 8), Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2]));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(g3, Rs / 4), 32, prep + L.ref_wd[2], prep + L.ref_td[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(g3, Rs / 4), 32, prep + L.ref_wd[2], prep + L.ref_td[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2, tcs));
   OP3_TRY(conv5x5_wgrad_auto(st, N, D, one_src(A.r1, 8), 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1]));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(g2, 8), 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1));
+  OP3_TRY(conv5x5_auto(st, N, D, one_src(g2, 8), 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1, tcs));
   OP3_TRY(conv5x5_wgrad_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0]));
   OP3_TRY(conv5x5_auto(st, N, D, one_src(g1, 8), REF_CIN_PAD, prep + L.ref_wd[0], prep + L.ref_td[0], nullptr,
-                       reinterpret_cast<float4*>(d_in), EPI_NONE, nullptr));
+                       reinterpret_cast<float4*>(d_in), EPI_NONE, nullptr, tcs));
   return OP3_OK;
 }

@@ -4,6 +4,7 @@
 //  * kind::tf32 TRUNCATES fp32 operands to 19 bits;
 //  * a single thread can issue one M=128 x K=8 MMA every ~48 cycles for N <= 64 (operand-fetch floor), N/4 beyond.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace op3 {
@@ -11,6 +12,8 @@ namespace op3 {
 #define OP3_PREC_FP32 0      /* CUDA-core fp32 kernels (exact mode)          */
 #define OP3_PREC_TF32X3 1    /* tcgen05 3xTF32 split (fp32-grade, parity)    */
 #define OP3_PREC_TF32 2      /* tcgen05 1xTF32 (speed mode)                  */
+#define OP3_PREC_F16X3 3     /* tcgen05 fp16 hi/lo split with per-image power-of-two operand scaling: the same 11-bit
+                                significands as 3xTF32 at half the operand bytes (forward/dgrad; wgrad stays 3xTF32) */
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -38,6 +41,36 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t alo, uint32_t
       "setp.ne.b32 p, %6, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n"
       :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f16: A/B fp16 (format 0), D fp32, K = 16 per MMA (two 16-byte K-chunks of 8 halves, LBO apart)
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Power-of-two scale that brings a tensor whose largest magnitude has the fp32 bit pattern `maxbits` into [2^13, 2^14)
+// (fp16 overflows at 2^16; products are accumulated in fp32).  Zero / denormal maxima get scale 1.
+__host__ __device__ __forceinline__ uint32_t f16_scale_bits(uint32_t maxbits) {
+  const uint32_t e = (maxbits >> 23) & 0xFFu;
+  if (e == 0u) return 0x3F800000u;
+  uint32_t se = 267u - e;                       // 127 + 13 - (e - 127)
+  if (se > 254u) se = 254u;
+  if (se < 1u) se = 1u;
+  return se << 23;
+}
+// (a, b) -> packed fp16 pairs hi = rn(a), lo = rn(a - hi): a_hi + a_lo carries 22 significand bits (exact residual)
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -107,8 +140,10 @@ __device__ __forceinline__ const float4* tc_src_chunk_ptr(const ConvInput& in, i
 // conv5x5_tc.cu
 int tc_nout(int cout);
 size_t conv5x5_tc_weight_floats(int cin_pad, int cout);
+size_t conv5x5_tc_f16_slab_floats(int cin_pad, int nout);   // one fp16 slab (+ its scale word), in floats
+size_t tc_scratch_floats(int N);                             // per-image operand maxima of the fp16 mode
 int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float* wt,
-                       const float* bias, float4* out, int epi, const float4* elu_ref);
+                       const float* bias, float4* out, int epi, const float4* elu_ref, float* tc_scratch);
 
 // conv5x5_wgrad_tc.cu
 size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout);
@@ -116,7 +151,8 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
                      float* scratch, float* dwt, float* dbias);
 int conv5x5_wgrad_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
                        float* dwt, float* dbias);
+// tc_scratch: tc_scratch_floats(N) floats of caller scratch (only touched in the fp16 mode)
 int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
-                 const float* bias, float4* out, int epi, const float4* elu_ref);
+                 const float* bias, float4* out, int epi, const float4* elu_ref, float* tc_scratch);
 
 }  // namespace op3

@@ -1,2 +1,10 @@
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv5x5_wgrad_tc_kernel|mix_bwd_kernel|conv5x5_wgrad_kernel" -s 4 -c 8 -o gpurun_out/prof_r01_bwd -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu6.log 2>&1; echo "ncu rc=$?"
-ls -la gpurun_out
+timeout 900 python -m pytest tests/test_gpu_precision.py -x -q -m gpu -s -k "f16x3" > gpurun_out/t_f16.log 2>&1; echo "pytest rc=$?"
+grep -E "rel|passed|failed|Error|error" gpurun_out/t_f16.log | head -40
+timeout 300 python bench.py --steps 3 --warmup 3 --precision f16x3 --no-cpu-baseline > gpurun_out/b_f16.json 2> gpurun_out/b_f16.err; echo "bench rc=$?"
+tail -3 gpurun_out/b_f16.err
+python - <<'PY'
+import json
+for f in ['gpurun_out/b_f16.json']:
+    j=json.loads(open(f).read().strip().splitlines()[-1])
+    print(j['config']['precision'], j['value'], j['ms_per_step'], {k:round(v['ms_per_step'],2) for k,v in j['kernel_families'].items()})
+PY
