@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32", "f16x3"],
+    ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "f16x3"), choices=["fp32", "tf32x3", "tf32", "f16x3"],
                     help="arithmetic of the 5x5 convolutions (see op3_set_precision)")
     args = ap.parse_args()
     if args.impl == "reference":
