@@ -317,6 +317,292 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int S,
   else if (dbias) dbias[i - n_w] += s;
 }
 
+
+// =====================================================================================================================
+// fp16 hi/lo-split variant (precision mode f16x3).  Same contraction, K = 16 pixels per MMA: a 16-byte K chunk holds 8
+// pixels, the row pitch is P = D + 8 (a multiple of 8) so a tap offset o = ky*P + kx = 8a + kx never carries into the
+// chunk index, and the phases kx = sx + sg are covered by X shifts sx in {0,1} (stacked along M) and G shifts sg in
+// {0,2,4} (stacked along N; even shifts keep half2 pixel pairs aligned): ONE M=128 x N=192 MMA per 16 pixels accumulates
+// all five taps of the kernel row (the sixth combination and the lo x lo quadrant are discarded).  Operands are scaled
+// by per-tensor powers of two (the sum runs over all images, so one scale per tensor) and split into fp16 hi + lo.
+//     lanes   0..31  X_0 hi    32..63  X_0 lo    64..95  X_1 hi    96..127 X_1 lo
+//     columns 64*c + [0,32) G_{2c} hi,  64*c + [32,64) G_{2c} lo,   c = 0,1,2
+// =====================================================================================================================
+constexpr int HG_BP = 128;                   // pixels per block (8 K-steps of 16)
+constexpr int HG_CH = HG_BP / 8;             // 16 pixel chunks of 8
+constexpr int HG_A_ROWS = 129;               // 128 + 1 (== 1 mod 8)
+constexpr int HG_B_ROWS = 193;               // 3 copies x (32 hi + 32 lo) + 1 (== 1 mod 8)
+constexpr int HG_A_BYTES = HG_CH * HG_A_ROWS * 16;
+constexpr int HG_B_BYTES = HG_CH * HG_B_ROWS * 16;
+constexpr int HG_STAGE_BYTES = HG_A_BYTES + HG_B_BYTES;
+
+// per-tensor largest magnitude (fp32 bit pattern) of a chunked activation tensor
+__global__ void __launch_bounds__(256) wg_absmax_kernel(ConvInput in, int D, uint32_t* __restrict__ out) {
+  const int n = blockIdx.x, c = blockIdx.y;
+  const float4* src = tc_src_chunk_ptr(in, c, n, D);
+  float m = 0.f;
+  if (src)
+    for (int i = threadIdx.x; i < D * D; i += 256) {
+      const float4 v = __ldg(src + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// two scaled floats -> packed fp16 pair hi and the pair lo = rn(value - hi)
+__device__ __forceinline__ void hg_pair(float a, float b, float sc, uint32_t& hi, uint32_t& lo) { f16_split2(a * sc, b * sc, hi, lo); }
+// (a.hi16, b.lo16): the pixel pair shifted by one pixel
+__device__ __forceinline__ uint32_t hg_shift1(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5432); }
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ dpre, int g_planes, int g_chunk0, int g_chunks,
+                         int cout_total, int co0, const uint32_t* __restrict__ xmax, const uint32_t* __restrict__ gmax,
+                         float* __restrict__ partial) {
+  constexpr int NCO = 32;
+  const int P = D + 8;                                     // multiple of 8
+  const int QN = (D + 4) * P;                              // padded-linear input pixels per image
+  const int NBLK = (QN + HG_BP - 1) / HG_BP;
+  const int ky = blockIdx.y;
+  const int n_items = N * NBLK;
+  const int cin_chunks = in.total_chunks;
+  const int cin_pad = cin_chunks * 4;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int a0 = (ky * P) >> 3;                            // chunk offset of this kernel row
+  const bool have = n_items > (int)blockIdx.x;
+  const float sx_scale = __uint_as_float(f16_scale_bits(__ldg(xmax)));
+  const float sg_scale = __uint_as_float(f16_scale_bits(__ldg(gmax)));
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[2], empty_bar[2], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], WG_LOADERS / 2); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == WG_LOADERS / 32) tmem_alloc<256>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if (warp < WG_LOADERS / 32) {
+    // ===================== loaders: group g fills stage g with every second item =====================
+    const int grp = warp >> 3, wl = warp & 7;
+    const int half = lane >> 4, j = lane & 15;
+    const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)P - 1) / (uint32_t)P);
+    uint8_t* st = smem_raw + (size_t)grp * HG_STAGE_BYTES;
+    const int first = blockIdx.x + grp * gridDim.x, stride = 2 * gridDim.x;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wl < 4) {
+      const int cc = 2 * wl + half;                        // X channel chunk of this half-warp
+      const bool act = cc < cin_chunks;
+      uint4* row = reinterpret_cast<uint4*>(st) + (size_t)j * HG_A_ROWS + 4 * cc;
+      auto load_x = [&](int item, float4* xv) {            // pixels q .. q+8 of the padded-linear input space
+#pragma unroll
+        for (int e = 0; e < 9; ++e) xv[e] = zero4;
+        if (!act) return;
+        const int n = item / NBLK, q = (item - n * NBLK) * HG_BP + 8 * j;
+        const float4* src = tc_src_chunk_ptr(in, cc, n, D);
+        const int r = (int)__umulhi((uint32_t)q, magic);
+        const int iy = r - 2, ix = q - r * P - 2;          // q..q+7 share a row (q and P are multiples of 8)
+        if (q < QN && (unsigned)iy < (unsigned)D) {
+          const float4* rp = src + (size_t)iy * D + ix;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if ((unsigned)(ix + e) < (unsigned)D) xv[e] = __ldg(rp + e);
+        }
+        int ix8 = ix + 8, iy8 = iy;
+        if (ix8 >= P - 2) { ix8 -= P; ++iy8; }
+        if (q + 8 < QN && (unsigned)iy8 < (unsigned)D && (unsigned)ix8 < (unsigned)D) xv[8] = __ldg(src + (size_t)iy8 * D + ix8);
+      };
+      float4 xv[9], xn[9];
+      if (first < n_items) load_x(first, xv);
+      int k = 0;
+      for (int item = first; item < n_items; item += stride, ++k) {
+        if (item + stride < n_items) load_x(item + stride, xn);
+        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (act) {
+#define OP3_HG_X_CHANNEL(C, R)                                                                                   \
+          {                                                                                                      \
+            uint32_t h01, l01, h23, l23, h45, l45, h67, l67, h8, l8;                                             \
+            hg_pair(xv[0].C, xv[1].C, sx_scale, h01, l01);                                                       \
+            hg_pair(xv[2].C, xv[3].C, sx_scale, h23, l23);                                                       \
+            hg_pair(xv[4].C, xv[5].C, sx_scale, h45, l45);                                                       \
+            hg_pair(xv[6].C, xv[7].C, sx_scale, h67, l67);                                                       \
+            hg_pair(xv[8].C, 0.f, sx_scale, h8, l8);                                                             \
+            row[R] = make_uint4(h01, h23, h45, h67);                                                             \
+            row[32 + R] = make_uint4(l01, l23, l45, l67);                                                        \
+            row[64 + R] = make_uint4(hg_shift1(h01, h23), hg_shift1(h23, h45), hg_shift1(h45, h67), hg_shift1(h67, h8)); \
+            row[96 + R] = make_uint4(hg_shift1(l01, l23), hg_shift1(l23, l45), hg_shift1(l45, l67), hg_shift1(l67, l8)); \
+          }
+          OP3_HG_X_CHANNEL(x, 0)
+          OP3_HG_X_CHANNEL(y, 1)
+          OP3_HG_X_CHANNEL(z, 2)
+          OP3_HG_X_CHANNEL(w, 3)
+#undef OP3_HG_X_CHANNEL
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[grp]);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) xv[e] = xn[e];
+      }
+    } else {
+      const int cc = 2 * (wl - 4) + half;                  // G channel chunk of this half-warp
+      const bool act = cc < g_chunks;
+      uint4* row = reinterpret_cast<uint4*>(st + HG_A_BYTES) + (size_t)j * HG_B_ROWS + 4 * cc;
+      int k = 0;
+      for (int item = first; item < n_items; item += stride, ++k) {
+        // pixels p0-4 .. p0+7 of the output-gradient space (chunk j - a0 of this block, plus the 4 pixels before it)
+        float4 gv[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) gv[e] = zero4;
+        if (act) {
+          const int n = item / NBLK, Q0 = (item - n * NBLK) * HG_BP;
+          const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + cc) * D * D;
+          const int p0 = Q0 + 8 * (j - a0);
+          if (p0 >= 0) {
+            const int y = (int)__umulhi((uint32_t)p0, magic), x = p0 - y * P;
+            if (y < D) {
+              const float4* rp = src + (size_t)y * D + x;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (x + e < D) gv[4 + e] = __ldg(rp + e);
+            }
+          }
+          const int pm = p0 - 8;                           // the chunk before: only its last 4 pixels are needed
+          if (pm >= 0) {
+            const int y = (int)__umulhi((uint32_t)pm, magic), x = pm - y * P;
+            if (y < D) {
+              const float4* rp = src + (size_t)y * D + x;
+#pragma unroll
+              for (int e = 4; e < 8; ++e)
+                if (x + e < D) gv[e - 4] = __ldg(rp + e);
+            }
+          }
+        }
+        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (act) {
+#define OP3_HG_G_CHANNEL(C, R)                                                                                   \
+          {                                                                                                      \
+            uint32_t hm2, lm2, hm1, lm1, h0, l0, h1, l1, h2, l2, h3, l3;                                         \
+            hg_pair(gv[0].C, gv[1].C, sg_scale, hm2, lm2);                                                       \
+            hg_pair(gv[2].C, gv[3].C, sg_scale, hm1, lm1);                                                       \
+            hg_pair(gv[4].C, gv[5].C, sg_scale, h0, l0);                                                         \
+            hg_pair(gv[6].C, gv[7].C, sg_scale, h1, l1);                                                         \
+            hg_pair(gv[8].C, gv[9].C, sg_scale, h2, l2);                                                         \
+            hg_pair(gv[10].C, gv[11].C, sg_scale, h3, l3);                                                       \
+            row[R] = make_uint4(h0, h1, h2, h3);              /* G_0: pixels p0 .. p0+7     */                    \
+            row[32 + R] = make_uint4(l0, l1, l2, l3);                                                            \
+            row[64 + R] = make_uint4(hm1, h0, h1, h2);        /* G_2: pixels p0-2 .. p0+5   */                    \
+            row[96 + R] = make_uint4(lm1, l0, l1, l2);                                                           \
+            row[128 + R] = make_uint4(hm2, hm1, h0, h1);      /* G_4: pixels p0-4 .. p0+3   */                    \
+            row[160 + R] = make_uint4(lm2, lm1, l0, l1);                                                         \
+          }
+          OP3_HG_G_CHANNEL(x, 0)
+          OP3_HG_G_CHANNEL(y, 1)
+          OP3_HG_G_CHANNEL(z, 2)
+          OP3_HG_G_CHANNEL(w, 3)
+#undef OP3_HG_G_CHANNEL
+          if (ky == 0) {                                   // a0 = 0: the chunks tile the pixel space exactly once
+#pragma unroll
+            for (int e = 4; e < 12; ++e) {
+              bias_acc.x += gv[e].x; bias_acc.y += gv[e].y; bias_acc.z += gv[e].z; bias_acc.w += gv[e].w;
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[grp]);
+      }
+    }
+  } else if (lane == 0) {
+    // ===================== MMA issuer: [X_0; X_1] x [G_0 | G_2 | G_4], K = 16 pixels =====================
+    const uint32_t idesc = make_idesc_f16(128, 192);
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      mbar_wait(&full_bar[s], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem_raw + (size_t)s * HG_STAGE_BYTES);
+      const uint64_t ad = make_smem_desc(st, HG_A_ROWS, 8);
+      const uint64_t bd = make_smem_desc(st + HG_A_BYTES, HG_B_ROWS, 8);
+      const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
+      const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
+#pragma unroll
+      for (int ks = 0; ks < HG_CH / 2; ++ks)
+        mma_f16(tmem_base, a_lo32 + (uint32_t)(2 * ks * HG_A_ROWS), a_hi32, b_lo32 + (uint32_t)(2 * ks * HG_B_ROWS), b_hi32, idesc,
+                (it > 0 || ks > 0) ? 1u : 0u);
+      tc_commit(&empty_bar[s]);
+    }
+    tc_commit(&acc_bar);
+  }
+  // ===================== epilogue =====================
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem_raw);         // [3 copies][2 shifts][32 ci][NCO]: the X_lo x G_hi sums
+  float* s_bias = red + 3 * 2 * 32 * NCO;                  // [2 groups][8 chunks][4]
+  float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
+  const float inv = 1.f / (sx_scale * sg_scale);           // powers of two: exact
+  if (warp < WG_LOADERS / 32 && have) {
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+  }
+  if (warp < WG_LOADERS / 32 && (warp & 7) >= 4) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      bias_acc.x += __shfl_xor_sync(0xffffffffu, bias_acc.x, o); bias_acc.y += __shfl_xor_sync(0xffffffffu, bias_acc.y, o);
+      bias_acc.z += __shfl_xor_sync(0xffffffffu, bias_acc.z, o); bias_acc.w += __shfl_xor_sync(0xffffffffu, bias_acc.w, o);
+    }
+    if ((lane & 15) == 0) {
+      float* dst = s_bias + ((warp >> 3) * 8 + 2 * ((warp & 7) - 4) + (lane >> 4)) * 4;
+      dst[0] = bias_acc.x; dst[1] = bias_acc.y; dst[2] = bias_acc.z; dst[3] = bias_acc.w;
+    }
+  }
+  if (warp == 1 || warp == 3) {          // lanes 32..63 / 96..127: X_lo rows, only their G_hi columns are used
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int c0 = 0; c0 < NCO; c0 += 16) {
+        float v[16];
+        const uint32_t t = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 64 + c0);
+        if (have) { tmem_ld16(t, v); tmem_ld_wait(); }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) red[((size_t)(c * 2 + (warp >> 1)) * 32 + lane) * NCO + c0 + i] = have ? v[i] : 0.f;
+      }
+  }
+  __syncthreads();
+  if (warp == 0 || warp == 2) {          // lanes 0..31 / 64..95: X_hi rows of tap kx = 2c / 2c + 1
+    const int sub = warp >> 1;
+    for (int c = 0; c < 3; ++c) {
+      const int kx = 2 * c + sub;
+      if (kx > 4) continue;
+#pragma unroll
+      for (int c0 = 0; c0 < NCO; c0 += 16) {
+        float v[16], u[16];
+        const uint32_t t = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 64 + c0);
+        if (have) { tmem_ld16(t, v); tmem_ld16(t + NCO, u); tmem_ld_wait(); }
+        if (lane < cin_pad) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int co = c0 + i;
+            if (co < g_chunks * 4) {
+              const float r = have ? v[i] + u[i] + red[((size_t)(c * 2 + sub) * 32 + lane) * NCO + co] : 0.f;
+              slab[((size_t)(ky * 5 + kx) * cin_pad + lane) * cout_total + co0 + co] = r * inv;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (ky == 0 && tid < g_chunks * 4)
+    slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid] + s_bias[32 + tid];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_LOADERS / 32) tmem_dealloc<256>(tmem_base);
+}
+
 int wg_sets() { return 29; }       // 5 kernel rows x 29 sets = 145 persistent CTAs on 148 SMs
 
 template <int NCO, bool SPLIT3>
@@ -340,6 +626,23 @@ int launch_wgrad_tc(cudaStream_t st, int N, int D, const ConvInput& in, const fl
   return OP3_OK;
 }
 
+int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, int g_planes, int g_chunk0,
+                     int g_chunks, int cout_total, int co0, const uint32_t* xmax, const uint32_t* gmax, float* scratch) {
+  size_t smem = 2 * (size_t)HG_STAGE_BYTES;
+  OP3_REQUIRE(smem <= 226 * 1024, "conv5x5_wgrad_f16: %zu bytes of shared memory", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(wg_sets(), 5);
+  conv5x5_wgrad_f16_kernel<<<grid, WG_THREADS, smem, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total, co0, xmax,
+                                                          gmax, scratch);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
 }  // namespace
 
 size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout) {
@@ -358,8 +661,22 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
   const int planes = cout / 4;
   const int cin_pad = in.total_chunks * 4;
   const size_t slab = (size_t)25 * cin_pad * cout + cout;
-  OP3_CHECK(cudaMemsetAsync(scratch, 0, (size_t)wg_sets() * slab * sizeof(float), st));   // padding entries stay zero
-  if (cout <= 16) {
+  OP3_CHECK(cudaMemsetAsync(scratch, 0, ((size_t)wg_sets() * slab + 8) * sizeof(float), st));   // padding entries stay zero
+  if (precision == OP3_PREC_F16X3 && cout >= 32 && D % 8 == 0) {
+    // per-tensor operand maxima live in the 8 words after the partial slabs (the caller's scratch is sized for the larger
+    // fp32 kernel: conv5x5_wgrad_scratch_floats)
+    uint32_t* mx = reinterpret_cast<uint32_t*>(scratch + (size_t)wg_sets() * slab);
+    wg_absmax_kernel<<<dim3(N, in.total_chunks), 256, 0, st>>>(in, D, mx);
+    OP3_COUNT_LAUNCH();
+    ConvInput gin{};
+    gin.src[0].ptr = dpre; gin.src[0].nchunks = planes; gin.src[0].div = 1;
+    gin.nsrc = 1; gin.total_chunks = planes;
+    wg_absmax_kernel<<<dim3(N, planes), 256, 0, st>>>(gin, D, mx + 4);
+    OP3_COUNT_LAUNCH();
+    OP3_LAUNCH_CHECK();
+    for (int h = 0; h * 32 < cout; ++h)
+      OP3_TRY(launch_wgrad_f16(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, mx, mx + 4, scratch));
+  } else if (cout <= 16) {
     OP3_TRY((s3 ? launch_wgrad_tc<16, true>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)
                 : launch_wgrad_tc<16, false>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)));
   } else {

@@ -1,1 +1,10 @@
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_f16.csv python bench.py --steps 1 --warmup 1 --precision f16x3 --no-cpu-baseline > gpurun_out/ncu7.log 2>&1; echo "ncu rc=$?"
+timeout 900 python -m pytest tests/test_gpu_precision.py tests/test_gpu_scaled.py -x -q -m gpu -s -k "f16x3 or scaled" > gpurun_out/t_f16.log 2>&1; echo "pytest rc=$?"
+grep -E "rel|passed|failed|Error|error" gpurun_out/t_f16.log | head -40
+timeout 300 python bench.py --steps 3 --warmup 3 --precision f16x3 --no-cpu-baseline > gpurun_out/b_f16.json 2> gpurun_out/b_f16.err; echo "bench rc=$?"
+tail -3 gpurun_out/b_f16.err
+python - <<'PY'
+import json
+for f in ['gpurun_out/b_f16.json']:
+    j=json.loads(open(f).read().strip().splitlines()[-1])
+    print(j['config']['precision'], j['value'], j['ms_per_step'], {k:round(v['ms_per_step'],2) for k,v in j['kernel_families'].items()})
+PY
