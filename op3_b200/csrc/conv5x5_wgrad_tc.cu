@@ -328,8 +328,12 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int S,
 //     lanes   0..31  X_0 hi    32..63  X_0 lo    64..95  X_1 hi    96..127 X_1 lo
 //     columns 64*c + [0,32) G_{2c} hi,  64*c + [32,64) G_{2c} lo,   c = 0,1,2
 // =====================================================================================================================
-constexpr int HG_BP = 128;                   // pixels per block (8 K-steps of 16)
-constexpr int HG_CH = HG_BP / 8;             // 16 pixel chunks of 8
+constexpr int HG_BP = 64;                    // pixels per item (4 K-steps of 16)
+constexpr int HG_CH = HG_BP / 8;             // 8 pixel chunks of 8
+constexpr int HG_GROUPS = 3;                 // loader groups = smem stages; group g fills stage g with every third item
+constexpr int HG_GWARPS = 4;                 // warps per group: 2 build X (8 channel chunks x 8 pixel chunks), 2 build G
+constexpr int HG_LOADERS = HG_GROUPS * HG_GWARPS * 32;
+constexpr int HG_THREADS = HG_LOADERS + 32;  // 13 warps: 128 registers per thread are available (16-warp granularity)
 constexpr int HG_A_ROWS = 129;               // 128 + 1 (== 1 mod 8)
 constexpr int HG_B_ROWS = 193;               // 3 copies x (32 hi + 32 lo) + 1 (== 1 mod 8)
 constexpr int HG_A_BYTES = HG_CH * HG_A_ROWS * 16;
@@ -356,7 +360,7 @@ __device__ __forceinline__ void hg_pair(float a, float b, float sc, uint32_t& hi
 // (a.hi16, b.lo16): the pixel pair shifted by one pixel
 __device__ __forceinline__ uint32_t hg_shift1(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5432); }
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(HG_THREADS, 1)
 conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ dpre, int g_planes, int g_chunk0, int g_chunks,
                          int cout_total, int co0, const uint32_t* __restrict__ xmax, const uint32_t* __restrict__ gmax,
                          float* __restrict__ partial) {
@@ -375,32 +379,33 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
   const float sg_scale = __uint_as_float(f16_scale_bits(__ldg(gmax)));
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[2], empty_bar[2], acc_bar;
+  __shared__ uint64_t full_bar[HG_GROUPS], empty_bar[HG_GROUPS], acc_bar;
   __shared__ uint32_t tmem_base_s;
+  constexpr int MMA_WARP = HG_LOADERS / 32;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], WG_LOADERS / 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < HG_GROUPS; ++s) { mbar_init(&full_bar[s], HG_GWARPS * 32); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
   }
-  if (warp == WG_LOADERS / 32) tmem_alloc<256>(&tmem_base_s);
+  if (warp == MMA_WARP) tmem_alloc<256>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  if (warp < WG_LOADERS / 32) {
-    // ===================== loaders: group g fills stage g with every second item =====================
-    const int grp = warp >> 3, wl = warp & 7;
-    const int half = lane >> 4, j = lane & 15;
+  if (warp < MMA_WARP) {
+    // ===================== loaders: group g fills stage g with every third item =====================
+    const int grp = warp / HG_GWARPS, wl = warp % HG_GWARPS;
+    const int t64 = (wl & 1) * 32 + lane;                  // 64 lane tasks per operand: 8 channel chunks x 8 pixel chunks
+    const int cc = t64 >> 3, j = t64 & 7;
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)P - 1) / (uint32_t)P);
     uint8_t* st = smem_raw + (size_t)grp * HG_STAGE_BYTES;
-    const int first = blockIdx.x + grp * gridDim.x, stride = 2 * gridDim.x;
+    const int first = blockIdx.x + grp * gridDim.x, stride = HG_GROUPS * gridDim.x;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (wl < 4) {
-      const int cc = 2 * wl + half;                        // X channel chunk of this half-warp
-      const bool act = cc < cin_chunks;
+    if (wl < 2) {
+      const bool act = cc < cin_chunks;                    // X channel chunk cc, pixel chunk j
       uint4* row = reinterpret_cast<uint4*>(st) + (size_t)j * HG_A_ROWS + 4 * cc;
       auto load_x = [&](int item, float4* xv) {            // pixels q .. q+8 of the padded-linear input space
 #pragma unroll
@@ -452,39 +457,41 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
         for (int e = 0; e < 9; ++e) xv[e] = xn[e];
       }
     } else {
-      const int cc = 2 * (wl - 4) + half;                  // G channel chunk of this half-warp
-      const bool act = cc < g_chunks;
+      const bool act = cc < g_chunks;                      // G channel chunk cc, pixel chunk j
       uint4* row = reinterpret_cast<uint4*>(st + HG_A_BYTES) + (size_t)j * HG_B_ROWS + 4 * cc;
-      int k = 0;
-      for (int item = first; item < n_items; item += stride, ++k) {
-        // pixels p0-4 .. p0+7 of the output-gradient space (chunk j - a0 of this block, plus the 4 pixels before it)
-        float4 gv[12];
+      // pixels p0-4 .. p0+7 of the output-gradient space (chunk j - a0 of this block, plus the 4 pixels before it)
+      auto load_g = [&](int item, float4* gv) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) gv[e] = zero4;
-        if (act) {
-          const int n = item / NBLK, Q0 = (item - n * NBLK) * HG_BP;
-          const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + cc) * D * D;
-          const int p0 = Q0 + 8 * (j - a0);
-          if (p0 >= 0) {
-            const int y = (int)__umulhi((uint32_t)p0, magic), x = p0 - y * P;
-            if (y < D) {
-              const float4* rp = src + (size_t)y * D + x;
+        if (!act) return;
+        const int n = item / NBLK, Q0 = (item - n * NBLK) * HG_BP;
+        const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + cc) * D * D;
+        const int p0 = Q0 + 8 * (j - a0);
+        if (p0 >= 0) {
+          const int y = (int)__umulhi((uint32_t)p0, magic), x = p0 - y * P;
+          if (y < D) {
+            const float4* rp = src + (size_t)y * D + x;
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (x + e < D) gv[4 + e] = __ldg(rp + e);
-            }
-          }
-          const int pm = p0 - 8;                           // the chunk before: only its last 4 pixels are needed
-          if (pm >= 0) {
-            const int y = (int)__umulhi((uint32_t)pm, magic), x = pm - y * P;
-            if (y < D) {
-              const float4* rp = src + (size_t)y * D + x;
-#pragma unroll
-              for (int e = 4; e < 8; ++e)
-                if (x + e < D) gv[e - 4] = __ldg(rp + e);
-            }
+            for (int e = 0; e < 8; ++e)
+              if (x + e < D) gv[4 + e] = __ldg(rp + e);
           }
         }
+        const int pm = p0 - 8;                             // the chunk before: only its last 4 pixels are needed
+        if (pm >= 0) {
+          const int y = (int)__umulhi((uint32_t)pm, magic), x = pm - y * P;
+          if (y < D) {
+            const float4* rp = src + (size_t)y * D + x;
+#pragma unroll
+            for (int e = 4; e < 8; ++e)
+              if (x + e < D) gv[e - 4] = __ldg(rp + e);
+          }
+        }
+      };
+      float4 gv[12], gn[12];
+      if (first < n_items) load_g(first, gv);
+      int k = 0;
+      for (int item = first; item < n_items; item += stride, ++k) {
+        if (item + stride < n_items) load_g(item + stride, gn);      // in flight while this item is converted and stored
         if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
         if (act) {
 #define OP3_HG_G_CHANNEL(C, R)                                                                                   \
@@ -517,6 +524,8 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
         }
         fence_proxy_async();
         mbar_arrive(&full_bar[grp]);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) gv[e] = gn[e];
       }
     }
   } else if (lane == 0) {
@@ -524,8 +533,8 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
     const uint32_t idesc = make_idesc_f16(128, 192);
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      mbar_wait(&full_bar[s], (it >> 1) & 1);
+      const int s = it % HG_GROUPS;
+      mbar_wait(&full_bar[s], (it / HG_GROUPS) & 1);
       tc_fence_after();
       const uint32_t st = smem_u32(smem_raw + (size_t)s * HG_STAGE_BYTES);
       const uint64_t ad = make_smem_desc(st, HG_A_ROWS, 8);
@@ -543,21 +552,22 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
   // ===================== epilogue =====================
   __syncthreads();
   float* red = reinterpret_cast<float*>(smem_raw);         // [3 copies][2 shifts][32 ci][NCO]: the X_lo x G_hi sums
-  float* s_bias = red + 3 * 2 * 32 * NCO;                  // [2 groups][8 chunks][4]
+  float* s_bias = red + 3 * 2 * 32 * NCO;                  // [3 groups][8 chunks][4]
   float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
   const float inv = 1.f / (sx_scale * sg_scale);           // powers of two: exact
-  if (warp < WG_LOADERS / 32 && have) {
+  if (warp < MMA_WARP && have) {
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
   }
-  if (warp < WG_LOADERS / 32 && (warp & 7) >= 4) {
+  if (warp < MMA_WARP && (warp % HG_GWARPS) >= 2) {       // G warps: 8 lanes (pixel chunks) share a channel chunk
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
+    for (int o = 4; o > 0; o >>= 1) {
       bias_acc.x += __shfl_xor_sync(0xffffffffu, bias_acc.x, o); bias_acc.y += __shfl_xor_sync(0xffffffffu, bias_acc.y, o);
       bias_acc.z += __shfl_xor_sync(0xffffffffu, bias_acc.z, o); bias_acc.w += __shfl_xor_sync(0xffffffffu, bias_acc.w, o);
     }
-    if ((lane & 15) == 0) {
-      float* dst = s_bias + ((warp >> 3) * 8 + 2 * ((warp & 7) - 4) + (lane >> 4)) * 4;
+    if ((lane & 7) == 0) {
+      const int cc = ((warp % HG_GWARPS) & 1) * 4 + (lane >> 3);
+      float* dst = s_bias + ((warp / HG_GWARPS) * 8 + cc) * 4;
       dst[0] = bias_acc.x; dst[1] = bias_acc.y; dst[2] = bias_acc.z; dst[3] = bias_acc.w;
     }
   }
@@ -597,10 +607,10 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
     }
   }
   if (ky == 0 && tid < g_chunks * 4)
-    slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid] + s_bias[32 + tid];
+    slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid] + s_bias[32 + tid] + s_bias[64 + tid];
   tc_fence_before();
   __syncthreads();
-  if (warp == WG_LOADERS / 32) tmem_dealloc<256>(tmem_base);
+  if (warp == MMA_WARP) tmem_dealloc<256>(tmem_base);
 }
 
 int wg_sets() { return 29; }       // 5 kernel rows x 29 sets = 145 persistent CTAs on 148 SMs
@@ -628,7 +638,7 @@ int launch_wgrad_tc(cudaStream_t st, int N, int D, const ConvInput& in, const fl
 
 int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, int g_planes, int g_chunk0,
                      int g_chunks, int cout_total, int co0, const uint32_t* xmax, const uint32_t* gmax, float* scratch) {
-  size_t smem = 2 * (size_t)HG_STAGE_BYTES;
+  size_t smem = HG_GROUPS * (size_t)HG_STAGE_BYTES;
   OP3_REQUIRE(smem <= 226 * 1024, "conv5x5_wgrad_f16: %zu bytes of shared memory", smem);
   static bool attr_set = false;
   if (!attr_set) {
@@ -636,7 +646,7 @@ int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const f
     attr_set = true;
   }
   dim3 grid(wg_sets(), 5);
-  conv5x5_wgrad_f16_kernel<<<grid, WG_THREADS, smem, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total, co0, xmax,
+  conv5x5_wgrad_f16_kernel<<<grid, HG_THREADS, smem, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total, co0, xmax,
                                                           gmax, scratch);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
