@@ -500,7 +500,10 @@ int conv5x5_forward(cudaStream_t st, int N, int D, const ConvInput& in, int cout
 }
 
 size_t conv5x5_wgrad_scratch_floats(int cin_pad, int cout) {
-  return (size_t)wgrad_sets(cin_pad / 4) * ((size_t)25 * cin_pad * cout + cout);
+  // also covers the tcgen05 kernels (conv5x5_wgrad_tc.cu): up to 148 per-CTA partial slabs + 8 words of operand maxima
+  const size_t slab = (size_t)25 * cin_pad * cout + cout;
+  const size_t a = (size_t)wgrad_sets(cin_pad / 4) * slab, b = 148 * slab + 8;
+  return a > b ? a : b;
 }
 
 int conv5x5_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,

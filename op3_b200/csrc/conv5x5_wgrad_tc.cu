@@ -613,6 +613,316 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
   if (warp == MMA_WARP) tmem_dealloc<256>(tmem_base);
 }
 
+
+// =====================================================================================================================
+// Ring-buffered fp16 variant: ONE CTA accumulates all five kernel rows, so every X / G element is loaded, scaled, split
+// and staged ONCE instead of once per kernel row (the per-row kernel above spends its time in the loaders: 5x redundant
+// conversions).  The G operand of kernel row ky for X chunk c is G chunk c - 9*ky... in general c - ky*P/8: the last
+// 4*P/8 + 8 G chunks live in a shared-memory ring (57 slots of [G_0hi G_2hi G_4hi | G_0lo G_2lo G_4lo] rows); per 64-pixel
+// block and kernel row the issuer runs 4 K-steps x 2 MMAs (B = the 96 hi rows, then the 96 lo rows, same accumulator
+// columns: D += A*G_hi + A*G_lo), N = 96, accumulators at TMEM columns 96*ky (480 of 512).
+// Work items are (image, segment of blocks); each item first refills the ring with the 5 blocks of G before its first
+// block (steps with no MMAs).  Ring slots are numbered by a running per-CTA counter, so a slot is rewritten 7 steps after
+// it was filled, two steps after its last reader (the same empty barrier that guards the two A stages).
+// =====================================================================================================================
+constexpr int RB_RING = 56;                  // G chunks in the ring (+ 1 guard slot = copy of slot 0 for wrapped K pairs)
+constexpr int RB_PRE = 5;                    // refill steps per item: 5 blocks = 40 chunks >= 4*P/8 = 36 (D = 64)
+constexpr int RB_LOADERS = 2 * 4 * 32;       // two groups (even / odd steps) of 2 X warps + 2 G warps
+constexpr int RB_THREADS = RB_LOADERS + 32;
+constexpr int RB_SLOT_BYTES = HG_B_ROWS * 16;
+constexpr int RB_RING_BYTES = (RB_RING + 1) * RB_SLOT_BYTES;
+constexpr int RB_SMEM = RB_RING_BYTES + 2 * HG_A_BYTES;
+
+__global__ void __launch_bounds__(RB_THREADS, 1)
+conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const float4* __restrict__ dpre, int g_planes,
+                          int g_chunk0, int g_chunks, int cout_total, int co0, const uint32_t* __restrict__ xmax,
+                          const uint32_t* __restrict__ gmax, float* __restrict__ partial) {
+  constexpr int NCO = 32;
+  const int P = D + 8;                                     // multiple of 8
+  const int QN = (D + 4) * P;                              // padded-linear input pixels per image
+  const int NBLK = (QN + HG_BP - 1) / HG_BP;
+  const int n_items = N * SEG;
+  const int cin_chunks = in.total_chunks;
+  const int cin_pad = cin_chunks * 4;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int achunks = P >> 3;                              // G chunk offset per kernel row
+  const float sx_scale = __uint_as_float(f16_scale_bits(__ldg(xmax)));
+  const float sg_scale = __uint_as_float(f16_scale_bits(__ldg(gmax)));
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw;
+  uint8_t* a_stage = smem_raw + RB_RING_BYTES;
+  __shared__ uint64_t full_bar[2], empty_bar[2], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  constexpr int MMA_WARP = RB_LOADERS / 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], RB_LOADERS / 2); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // step sequence of this CTA: for item = blockIdx.x, += gridDim.x: vb = b0 - RB_PRE .. b1 - 1  (vb < b0: ring refill only)
+  auto item_b0 = [&](int item) { return (item % SEG) * L; };
+  auto item_b1 = [&](int item) { int e = (item % SEG) * L + L; return e < NBLK ? e : NBLK; };
+  auto advance = [&](int& item, int& vb) {                 // next step; item >= n_items afterwards means "no more steps"
+    if (++vb >= item_b1(item)) {
+      item += gridDim.x;
+      vb = item_b0(item) - RB_PRE;
+    }
+  };
+
+  if (warp < MMA_WARP) {
+    // ===================== loaders: group g handles the steps t with t % 2 == g =====================
+    const int grp = warp >> 2, wl = warp & 3;
+    const int t64 = (wl & 1) * 32 + lane;                  // 64 lane tasks per operand: 8 channel chunks x 8 pixel chunks
+    const int cc = t64 >> 3, j = t64 & 7;
+    const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)P - 1) / (uint32_t)P);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int item = blockIdx.x, vb = item_b0(item) - RB_PRE, t = 0;
+    if (grp == 1) { advance(item, vb); t = 1; }
+    int nitem = item, nvb = vb;                            // the group's next step (t + 2)
+    auto step2 = [&](int& it_, int& vb_) { advance(it_, vb_); if (it_ < n_items) advance(it_, vb_); };
+    if (wl < 2) {
+      const bool act = cc < cin_chunks;                    // X channel chunk cc, pixel chunk j
+      auto load_x = [&](int item_, int vb_, float4* xv) {  // pixels q .. q+8 of the padded-linear input space
+#pragma unroll
+        for (int e = 0; e < 9; ++e) xv[e] = zero4;
+        if (!act || vb_ < item_b0(item_)) return;
+        const int n = item_ / SEG, q = vb_ * HG_BP + 8 * j;
+        const float4* src = tc_src_chunk_ptr(in, cc, n, D);
+        const int r = (int)__umulhi((uint32_t)q, magic);
+        const int iy = r - 2, ix = q - r * P - 2;          // q..q+7 share a row (q and P are multiples of 8)
+        if (q < QN && (unsigned)iy < (unsigned)D) {
+          const float4* rp = src + (size_t)iy * D + ix;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if ((unsigned)(ix + e) < (unsigned)D) xv[e] = __ldg(rp + e);
+        }
+        int ix8 = ix + 8, iy8 = iy;
+        if (ix8 >= P - 2) { ix8 -= P; ++iy8; }
+        if (q + 8 < QN && (unsigned)iy8 < (unsigned)D && (unsigned)ix8 < (unsigned)D) xv[8] = __ldg(src + (size_t)iy8 * D + ix8);
+      };
+      float4 xv[9], xn[9];
+      if (item < n_items) load_x(item, vb, xv);
+      int k = 0;
+      for (; item < n_items; t += 2, ++k) {
+        nitem = item; nvb = vb;
+        step2(nitem, nvb);
+        if (nitem < n_items) load_x(nitem, nvb, xn);
+        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (act && vb >= item_b0(item)) {
+          uint4* row = reinterpret_cast<uint4*>(a_stage + (size_t)grp * HG_A_BYTES) + (size_t)j * HG_A_ROWS + 4 * cc;
+#define OP3_HG_X_CHANNEL(C, R)                                                                                   \
+          {                                                                                                      \
+            uint32_t h01, l01, h23, l23, h45, l45, h67, l67, h8, l8;                                             \
+            hg_pair(xv[0].C, xv[1].C, sx_scale, h01, l01);                                                       \
+            hg_pair(xv[2].C, xv[3].C, sx_scale, h23, l23);                                                       \
+            hg_pair(xv[4].C, xv[5].C, sx_scale, h45, l45);                                                       \
+            hg_pair(xv[6].C, xv[7].C, sx_scale, h67, l67);                                                       \
+            hg_pair(xv[8].C, 0.f, sx_scale, h8, l8);                                                             \
+            row[R] = make_uint4(h01, h23, h45, h67);                                                             \
+            row[32 + R] = make_uint4(l01, l23, l45, l67);                                                        \
+            row[64 + R] = make_uint4(hg_shift1(h01, h23), hg_shift1(h23, h45), hg_shift1(h45, h67), hg_shift1(h67, h8)); \
+            row[96 + R] = make_uint4(hg_shift1(l01, l23), hg_shift1(l23, l45), hg_shift1(l45, l67), hg_shift1(l67, l8)); \
+          }
+          OP3_HG_X_CHANNEL(x, 0)
+          OP3_HG_X_CHANNEL(y, 1)
+          OP3_HG_X_CHANNEL(z, 2)
+          OP3_HG_X_CHANNEL(w, 3)
+#undef OP3_HG_X_CHANNEL
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[grp]);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) xv[e] = xn[e];
+        item = nitem; vb = nvb;
+      }
+    } else {
+      const bool act = cc < g_chunks;                      // G channel chunk cc, pixel chunk j
+      // pixels p0-4 .. p0+7 of the output-gradient space: G chunk 8*vb + j of the image and the 4 pixels before it
+      auto load_g = [&](int item_, int vb_, float4* gv) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) gv[e] = zero4;
+        if (!act) return;
+        const int n = item_ / SEG;
+        const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + cc) * D * D;
+        const int p0 = vb_ * HG_BP + 8 * j;
+        if (p0 >= 0) {
+          const int y = (int)__umulhi((uint32_t)p0, magic), x = p0 - y * P;
+          if (y < D && x < D) {                            // x and D are multiples of 8: all 8 pixels are valid or none
+            const float4* rp = src + (size_t)y * D + x;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gv[4 + e] = __ldg(rp + e);
+          }
+        }
+        const int pm = p0 - 8;                             // the chunk before: only its last 4 pixels are needed
+        if (pm >= 0) {
+          const int y = (int)__umulhi((uint32_t)pm, magic), x = pm - y * P;
+          if (y < D && x < D) {
+            const float4* rp = src + (size_t)y * D + x;
+#pragma unroll
+            for (int e = 4; e < 8; ++e) gv[e - 4] = __ldg(rp + e);
+          }
+        }
+      };
+      float4 gv[12], gn[12];
+      if (item < n_items) load_g(item, vb, gv);
+      int k = 0;
+      for (; item < n_items; t += 2, ++k) {
+        nitem = item; nvb = vb;
+        step2(nitem, nvb);
+        if (nitem < n_items) load_g(nitem, nvb, gn);
+        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (act) {
+          const int slot = (8 * t + j) % RB_RING;          // running slot counter: 8 new chunks per step
+          uint4* row = reinterpret_cast<uint4*>(ring + (size_t)slot * RB_SLOT_BYTES) + 4 * cc;
+          uint4* guard = reinterpret_cast<uint4*>(ring + (size_t)RB_RING * RB_SLOT_BYTES) + 4 * cc;
+          const bool dup = slot == 0;                      // slot 0 is mirrored behind the ring for K pairs that wrap
+#define OP3_HG_G_CHANNEL(C, R)                                                                                   \
+          {                                                                                                      \
+            uint32_t hm2, lm2, hm1, lm1, h0, l0, h1, l1, h2, l2, h3, l3;                                         \
+            hg_pair(gv[0].C, gv[1].C, sg_scale, hm2, lm2);                                                       \
+            hg_pair(gv[2].C, gv[3].C, sg_scale, hm1, lm1);                                                       \
+            hg_pair(gv[4].C, gv[5].C, sg_scale, h0, l0);                                                         \
+            hg_pair(gv[6].C, gv[7].C, sg_scale, h1, l1);                                                         \
+            hg_pair(gv[8].C, gv[9].C, sg_scale, h2, l2);                                                         \
+            hg_pair(gv[10].C, gv[11].C, sg_scale, h3, l3);                                                       \
+            const uint4 g0h = make_uint4(h0, h1, h2, h3), g0l = make_uint4(l0, l1, l2, l3);       /* p0   .. p0+7 */ \
+            const uint4 g2h = make_uint4(hm1, h0, h1, h2), g2l = make_uint4(lm1, l0, l1, l2);     /* p0-2 .. p0+5 */ \
+            const uint4 g4h = make_uint4(hm2, hm1, h0, h1), g4l = make_uint4(lm2, lm1, l0, l1);   /* p0-4 .. p0+3 */ \
+            row[R] = g0h; row[32 + R] = g2h; row[64 + R] = g4h;                                                  \
+            row[96 + R] = g0l; row[128 + R] = g2l; row[160 + R] = g4l;                                           \
+            if (dup) {                                                                                           \
+              guard[R] = g0h; guard[32 + R] = g2h; guard[64 + R] = g4h;                                          \
+              guard[96 + R] = g0l; guard[128 + R] = g2l; guard[160 + R] = g4l;                                   \
+            }                                                                                                    \
+          }
+          OP3_HG_G_CHANNEL(x, 0)
+          OP3_HG_G_CHANNEL(y, 1)
+          OP3_HG_G_CHANNEL(z, 2)
+          OP3_HG_G_CHANNEL(w, 3)
+#undef OP3_HG_G_CHANNEL
+          if (vb >= item_b0(item)) {                       // refill chunks belong to the previous segment's sum
+#pragma unroll
+            for (int e = 4; e < 12; ++e) {
+              bias_acc.x += gv[e].x; bias_acc.y += gv[e].y; bias_acc.z += gv[e].z; bias_acc.w += gv[e].w;
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[grp]);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) gv[e] = gn[e];
+        item = nitem; vb = nvb;
+      }
+    }
+  } else if (lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_f16(128, 96);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint64_t bd0 = make_smem_desc(ring_u32, HG_B_ROWS, 8);
+    const uint32_t b_lo0 = (uint32_t)bd0, b_hi32 = (uint32_t)(bd0 >> 32);
+    int item = blockIdx.x, vb = item_b0(item) - RB_PRE, t = 0;
+    bool first = true;
+    for (; item < n_items; ++t) {
+      const int s = t & 1;
+      mbar_wait(&full_bar[s], (t >> 1) & 1);
+      tc_fence_after();
+      if (vb >= item_b0(item)) {
+        const uint64_t ad = make_smem_desc(smem_u32(a_stage + (size_t)s * HG_A_BYTES), HG_A_ROWS, 8);
+        const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
+        const int c0 = (8 * t) % RB_RING;                  // slot of this block's first G chunk
+#pragma unroll 1
+        for (int ky = 0; ky < 5; ++ky) {
+          const uint32_t dcol = tmem_base + (uint32_t)(96 * ky);
+          int slot = c0 - achunks * ky;
+          slot = ((slot % RB_RING) + RB_RING) % RB_RING;
+#pragma unroll
+          for (int ks = 0; ks < HG_CH / 2; ++ks) {
+            const uint32_t boff = (uint32_t)(slot * HG_B_ROWS);                 // 16-byte units
+            const uint32_t aoff = (uint32_t)(2 * ks * HG_A_ROWS);
+            mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo0 + boff, b_hi32, idesc, (first && ks == 0) ? 0u : 1u);
+            mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo0 + boff + 96u, b_hi32, idesc, 1u);
+            slot += 2;
+            if (slot >= RB_RING) slot -= RB_RING;
+          }
+        }
+        first = false;
+      }
+      tc_commit(&empty_bar[s]);
+      advance(item, vb);
+    }
+    tc_commit(&acc_bar);
+  }
+  // ===================== epilogue =====================
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem_raw);         // [2 shifts][32 ci][480]: the X_lo rows
+  float* s_bias = red + 2 * 32 * 480;                      // [2 groups][8 chunks][4]
+  float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
+  const float inv = 1.f / (sx_scale * sg_scale);           // powers of two: exact
+  if (warp < MMA_WARP) {
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+  }
+  if (warp < MMA_WARP && (warp & 3) >= 2) {                // G warps: 8 lanes (pixel chunks) share a channel chunk
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      bias_acc.x += __shfl_xor_sync(0xffffffffu, bias_acc.x, o); bias_acc.y += __shfl_xor_sync(0xffffffffu, bias_acc.y, o);
+      bias_acc.z += __shfl_xor_sync(0xffffffffu, bias_acc.z, o); bias_acc.w += __shfl_xor_sync(0xffffffffu, bias_acc.w, o);
+    }
+    if ((lane & 7) == 0) {
+      const int cc = (warp & 1) * 4 + (lane >> 3);
+      float* dst = s_bias + ((warp >> 2) * 8 + cc) * 4;
+      dst[0] = bias_acc.x; dst[1] = bias_acc.y; dst[2] = bias_acc.z; dst[3] = bias_acc.w;
+    }
+  }
+  if (warp == 1 || warp == 3) {          // lanes 32..63 / 96..127: X_lo rows
+    for (int c0 = 0; c0 < 480; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) red[((size_t)(warp >> 1) * 32 + lane) * 480 + c0 + i] = v[i];
+    }
+  }
+  __syncthreads();
+  if (warp == 0 || warp == 2) {          // lanes 0..31 / 64..95: X_hi rows; columns 96*ky + 32*c + co, tap kx = 2c + sub
+    const int sub = warp >> 1;
+    for (int ky = 0; ky < 5; ++ky)
+      for (int c = 0; c < 3; ++c) {
+        const int kx = 2 * c + sub;
+        if (kx > 4) continue;
+#pragma unroll
+        for (int c0 = 0; c0 < NCO; c0 += 16) {
+          float v[16];
+          const int col = 96 * ky + 32 * c + c0;
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
+          tmem_ld_wait();
+          if (lane < cin_pad) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int co = c0 + i;
+              if (co < g_chunks * 4)
+                slab[((size_t)(ky * 5 + kx) * cin_pad + lane) * cout_total + co0 + co] =
+                    (v[i] + red[((size_t)sub * 32 + lane) * 480 + col + i]) * inv;
+            }
+          }
+        }
+      }
+  }
+  if (tid < g_chunks * 4) slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid] + s_bias[32 + tid];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
+}
+
 int wg_sets() { return 29; }       // 5 kernel rows x 29 sets = 145 persistent CTAs on 148 SMs
 
 template <int NCO, bool SPLIT3>
@@ -653,6 +963,47 @@ int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const f
   return OP3_OK;
 }
 
+int g_wg_sms = 0;
+
+// returns the number of per-CTA partial slabs written (the grid size)
+int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, int g_planes, int g_chunk0,
+                      int g_chunks, int cout_total, int co0, const uint32_t* xmax, const uint32_t* gmax, float* scratch,
+                      int* grid_out) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  if (g_wg_sms == 0) {
+    int dev = 0;
+    OP3_CHECK(cudaGetDevice(&dev));
+    OP3_CHECK(cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (g_wg_sms > 148) g_wg_sms = 148;                     // scratch is sized for 148 slabs
+  }
+  const int P = D + 8, NBLK = ((D + 4) * P + HG_BP - 1) / HG_BP;
+  // segments per image: the split with the best last-round occupancy (refill steps are cheap: no MMAs)
+  int best_seg = 1;
+  double best = 0.0;
+  for (int seg = 1; seg <= 8; ++seg) {
+    const int L = (NBLK + seg - 1) / seg;
+    if ((L - 1) * seg >= NBLK) continue;                   // would leave an empty segment
+    const long long items = (long long)N * seg;
+    const int grid = items < g_wg_sms ? (int)items : g_wg_sms;
+    const double rounds = (double)((items + grid - 1) / grid);
+    const double eff = (double)items / (rounds * grid) * ((double)L / (L + 0.3 * RB_PRE));
+    if (eff > best) { best = eff; best_seg = seg; }
+  }
+  const int SEG = best_seg, L = (NBLK + SEG - 1) / SEG;
+  const long long items = (long long)N * SEG;
+  const int grid = items < g_wg_sms ? (int)items : g_wg_sms;
+  conv5x5_wgrad_ring_kernel<<<grid, RB_THREADS, RB_SMEM, st>>>(in, N, D, SEG, L, dpre, g_planes, g_chunk0, g_chunks, cout_total,
+                                                              co0, xmax, gmax, scratch);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  *grid_out = grid;
+  return OP3_OK;
+}
+
 }  // namespace
 
 size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout) {
@@ -671,11 +1022,14 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
   const int planes = cout / 4;
   const int cin_pad = in.total_chunks * 4;
   const size_t slab = (size_t)25 * cin_pad * cout + cout;
-  OP3_CHECK(cudaMemsetAsync(scratch, 0, ((size_t)wg_sets() * slab + 8) * sizeof(float), st));   // padding entries stay zero
-  if (precision == OP3_PREC_F16X3 && cout >= 32 && D % 8 == 0) {
-    // per-tensor operand maxima live in the 8 words after the partial slabs (the caller's scratch is sized for the larger
-    // fp32 kernel: conv5x5_wgrad_scratch_floats)
-    uint32_t* mx = reinterpret_cast<uint32_t*>(scratch + (size_t)wg_sets() * slab);
+  int n_slabs = wg_sets();
+  const bool f16 = precision == OP3_PREC_F16X3 && cout >= 32 && D % 8 == 0;
+  const bool use_ring = f16 && 4 * ((D + 8) / 8) <= 8 * RB_PRE;
+  const size_t zero_slabs = use_ring ? 148 : (size_t)wg_sets();
+  OP3_CHECK(cudaMemsetAsync(scratch, 0, (zero_slabs * slab + 8) * sizeof(float), st));   // padding entries stay zero
+  if (f16) {
+    // per-tensor operand maxima live in the 8 words after the partial slabs (scratch: conv5x5_wgrad_scratch_floats)
+    uint32_t* mx = reinterpret_cast<uint32_t*>(scratch + zero_slabs * slab);
     wg_absmax_kernel<<<dim3(N, in.total_chunks), 256, 0, st>>>(in, D, mx);
     OP3_COUNT_LAUNCH();
     ConvInput gin{};
@@ -684,8 +1038,15 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
     wg_absmax_kernel<<<dim3(N, planes), 256, 0, st>>>(gin, D, mx + 4);
     OP3_COUNT_LAUNCH();
     OP3_LAUNCH_CHECK();
-    for (int h = 0; h * 32 < cout; ++h)
-      OP3_TRY(launch_wgrad_f16(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, mx, mx + 4, scratch));
+    if (4 * ((D + 8) / 8) <= 8 * RB_PRE) {               // ring kernel: its refill covers the 4-row halo of G chunks
+      int grid = 0;
+      for (int h = 0; h * 32 < cout; ++h)
+        OP3_TRY(launch_wgrad_ring(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, mx, mx + 4, scratch, &grid));
+      n_slabs = grid;
+    } else {
+      for (int h = 0; h * 32 < cout; ++h)
+        OP3_TRY(launch_wgrad_f16(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, mx, mx + 4, scratch));
+    }
   } else if (cout <= 16) {
     OP3_TRY((s3 ? launch_wgrad_tc<16, true>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)
                 : launch_wgrad_tc<16, false>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)));
@@ -697,7 +1058,7 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
     }
   }
   const int n_w = 25 * cin_pad * cout;
-  wgrad_tc_reduce_kernel<<<ceil_div(n_w + cout, 256), 256, 0, st>>>(scratch, wg_sets(), n_w, cout, dwt, dbias);
+  wgrad_tc_reduce_kernel<<<ceil_div(n_w + cout, 256), 256, 0, st>>>(scratch, n_slabs, n_w, cout, dwt, dbias);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
