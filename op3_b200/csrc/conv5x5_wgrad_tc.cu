@@ -629,9 +629,16 @@ constexpr int RB_RING = 56;                  // G chunks in the ring (+ 1 guard 
 constexpr int RB_PRE = 5;                    // refill steps per item: 5 blocks = 40 chunks >= 4*P/8 = 36 (D = 64)
 constexpr int RB_LOADERS = 2 * 4 * 32;       // two groups (even / odd steps) of 2 X warps + 2 G warps
 constexpr int RB_THREADS = RB_LOADERS + 32;
-constexpr int RB_SLOT_BYTES = HG_B_ROWS * 16;
+// Operand chunks are DENSE (128 / 192 rows of 16 bytes): every 8-row core matrix is one aligned 128-byte line, so the
+// tensor core fetches it in one shared-memory wavefront (a padded row count would make most core matrices straddle two
+// lines and double the operand-fetch time).  Store conflicts are avoided by the row order instead: channel 4*cc + r of a
+// 32-channel block lives in row 8*r + cc, so the 8 lanes of a quarter warp (cc = 0..7, same pixel chunk) write 8
+// consecutive rows = one 128-byte line per store instruction.
+constexpr int RB_A_ROWS = 128, RB_B_ROWS = 192;
+constexpr int RB_A_BYTES = HG_CH * RB_A_ROWS * 16;
+constexpr int RB_SLOT_BYTES = RB_B_ROWS * 16;
 constexpr int RB_RING_BYTES = (RB_RING + 1) * RB_SLOT_BYTES;
-constexpr int RB_SMEM = RB_RING_BYTES + 2 * HG_A_BYTES;
+constexpr int RB_SMEM = RB_RING_BYTES + 2 * RB_A_BYTES;
 
 __global__ void __launch_bounds__(RB_THREADS, 1)
 conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const float4* __restrict__ dpre, int g_planes,
@@ -681,8 +688,8 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
   if (warp < MMA_WARP) {
     // ===================== loaders: group g handles the steps t with t % 2 == g =====================
     const int grp = warp >> 2, wl = warp & 3;
-    const int t64 = (wl & 1) * 32 + lane;                  // 64 lane tasks per operand: 8 channel chunks x 8 pixel chunks
-    const int cc = t64 >> 3, j = t64 & 7;
+    const int t64 = (wl & 1) * 32 + lane;                  // 64 lane tasks per operand: 8 pixel chunks x 8 channel chunks
+    const int j = t64 >> 3, cc = t64 & 7;                  // a quarter warp shares the pixel chunk (see the row order above)
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)P - 1) / (uint32_t)P);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     int item = blockIdx.x, vb = item_b0(item) - RB_PRE, t = 0;
@@ -718,7 +725,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
         if (nitem < n_items) load_x(nitem, nvb, xn);
         if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
         if (act && vb >= item_b0(item)) {
-          uint4* row = reinterpret_cast<uint4*>(a_stage + (size_t)grp * HG_A_BYTES) + (size_t)j * HG_A_ROWS + 4 * cc;
+          uint4* row = reinterpret_cast<uint4*>(a_stage + (size_t)grp * RB_A_BYTES) + (size_t)j * RB_A_ROWS + cc;
 #define OP3_HG_X_CHANNEL(C, R)                                                                                   \
           {                                                                                                      \
             uint32_t h01, l01, h23, l23, h45, l45, h67, l67, h8, l8;                                             \
@@ -727,10 +734,10 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
             hg_pair(xv[4].C, xv[5].C, sx_scale, h45, l45);                                                       \
             hg_pair(xv[6].C, xv[7].C, sx_scale, h67, l67);                                                       \
             hg_pair(xv[8].C, 0.f, sx_scale, h8, l8);                                                             \
-            row[R] = make_uint4(h01, h23, h45, h67);                                                             \
-            row[32 + R] = make_uint4(l01, l23, l45, l67);                                                        \
-            row[64 + R] = make_uint4(hg_shift1(h01, h23), hg_shift1(h23, h45), hg_shift1(h45, h67), hg_shift1(h67, h8)); \
-            row[96 + R] = make_uint4(hg_shift1(l01, l23), hg_shift1(l23, l45), hg_shift1(l45, l67), hg_shift1(l67, l8)); \
+            row[8 * R] = make_uint4(h01, h23, h45, h67);                                                         \
+            row[32 + 8 * R] = make_uint4(l01, l23, l45, l67);                                                    \
+            row[64 + 8 * R] = make_uint4(hg_shift1(h01, h23), hg_shift1(h23, h45), hg_shift1(h45, h67), hg_shift1(h67, h8)); \
+            row[96 + 8 * R] = make_uint4(hg_shift1(l01, l23), hg_shift1(l23, l45), hg_shift1(l45, l67), hg_shift1(l67, l8)); \
           }
           OP3_HG_X_CHANNEL(x, 0)
           OP3_HG_X_CHANNEL(y, 1)
@@ -782,8 +789,8 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
         if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
         if (act) {
           const int slot = (8 * t + j) % RB_RING;          // running slot counter: 8 new chunks per step
-          uint4* row = reinterpret_cast<uint4*>(ring + (size_t)slot * RB_SLOT_BYTES) + 4 * cc;
-          uint4* guard = reinterpret_cast<uint4*>(ring + (size_t)RB_RING * RB_SLOT_BYTES) + 4 * cc;
+          uint4* row = reinterpret_cast<uint4*>(ring + (size_t)slot * RB_SLOT_BYTES) + cc;
+          uint4* guard = reinterpret_cast<uint4*>(ring + (size_t)RB_RING * RB_SLOT_BYTES) + cc;
           const bool dup = slot == 0;                      // slot 0 is mirrored behind the ring for K pairs that wrap
 #define OP3_HG_G_CHANNEL(C, R)                                                                                   \
           {                                                                                                      \
@@ -797,11 +804,11 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
             const uint4 g0h = make_uint4(h0, h1, h2, h3), g0l = make_uint4(l0, l1, l2, l3);       /* p0   .. p0+7 */ \
             const uint4 g2h = make_uint4(hm1, h0, h1, h2), g2l = make_uint4(lm1, l0, l1, l2);     /* p0-2 .. p0+5 */ \
             const uint4 g4h = make_uint4(hm2, hm1, h0, h1), g4l = make_uint4(lm2, lm1, l0, l1);   /* p0-4 .. p0+3 */ \
-            row[R] = g0h; row[32 + R] = g2h; row[64 + R] = g4h;                                                  \
-            row[96 + R] = g0l; row[128 + R] = g2l; row[160 + R] = g4l;                                           \
+            row[8 * R] = g0h; row[32 + 8 * R] = g2h; row[64 + 8 * R] = g4h;                                      \
+            row[96 + 8 * R] = g0l; row[128 + 8 * R] = g2l; row[160 + 8 * R] = g4l;                               \
             if (dup) {                                                                                           \
-              guard[R] = g0h; guard[32 + R] = g2h; guard[64 + R] = g4h;                                          \
-              guard[96 + R] = g0l; guard[128 + R] = g2l; guard[160 + R] = g4l;                                   \
+              guard[8 * R] = g0h; guard[32 + 8 * R] = g2h; guard[64 + 8 * R] = g4h;                              \
+              guard[96 + 8 * R] = g0l; guard[128 + 8 * R] = g2l; guard[160 + 8 * R] = g4l;                       \
             }                                                                                                    \
           }
           OP3_HG_G_CHANNEL(x, 0)
@@ -827,32 +834,46 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_f16(128, 96);
     const uint32_t ring_u32 = smem_u32(ring);
-    const uint64_t bd0 = make_smem_desc(ring_u32, HG_B_ROWS, 8);
+    const uint64_t bd0 = make_smem_desc(ring_u32, RB_B_ROWS, 8);
     const uint32_t b_lo0 = (uint32_t)bd0, b_hi32 = (uint32_t)(bd0 >> 32);
     int item = blockIdx.x, vb = item_b0(item) - RB_PRE, t = 0;
     bool first = true;
+    int koff[5];                                           // (-achunks * ky) mod RING
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) koff[ky] = (5 * RB_RING - achunks * ky) % RB_RING;
     for (; item < n_items; ++t) {
       const int s = t & 1;
       mbar_wait(&full_bar[s], (t >> 1) & 1);
       tc_fence_after();
       if (vb >= item_b0(item)) {
-        const uint64_t ad = make_smem_desc(smem_u32(a_stage + (size_t)s * HG_A_BYTES), HG_A_ROWS, 8);
+        const uint64_t ad = make_smem_desc(smem_u32(a_stage + (size_t)s * RB_A_BYTES), RB_A_ROWS, 8);
         const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
-        const int c0 = (8 * t) % RB_RING;                  // slot of this block's first G chunk
-#pragma unroll 1
+        int c0 = 8 * (t % (RB_RING / 8));                  // slot of this block's first G chunk = (8 t) mod 56
+        // slots of the 5 x 4 K-pair operands first (wrapped), then 40 back-to-back MMAs with precomputed descriptors
+        uint32_t boff[5][HG_CH / 2];
+#pragma unroll
         for (int ky = 0; ky < 5; ++ky) {
-          const uint32_t dcol = tmem_base + (uint32_t)(96 * ky);
-          int slot = c0 - achunks * ky;
-          slot = ((slot % RB_RING) + RB_RING) % RB_RING;
+          int slot = c0 + koff[ky];
+          if (slot >= RB_RING) slot -= RB_RING;
 #pragma unroll
           for (int ks = 0; ks < HG_CH / 2; ++ks) {
-            const uint32_t boff = (uint32_t)(slot * HG_B_ROWS);                 // 16-byte units
-            const uint32_t aoff = (uint32_t)(2 * ks * HG_A_ROWS);
-            mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo0 + boff, b_hi32, idesc, (first && ks == 0) ? 0u : 1u);
-            mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo0 + boff + 96u, b_hi32, idesc, 1u);
+            boff[ky][ks] = b_lo0 + (uint32_t)(slot * RB_B_ROWS);                // 16-byte units
             slot += 2;
             if (slot >= RB_RING) slot -= RB_RING;
           }
+        }
+        // consecutive MMAs go to DIFFERENT accumulators (kernel rows): back-to-back MMAs on one accumulator serialise
+#pragma unroll
+        for (int ks = 0; ks < HG_CH / 2; ++ks) {
+          const uint32_t aoff = a_lo32 + (uint32_t)(2 * ks * RB_A_ROWS);
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+              const uint32_t dcol = tmem_base + (uint32_t)(96 * ky);
+              if (ks == 0 && hl == 0) mma_f16(dcol, aoff, a_hi32, boff[ky][ks], b_hi32, idesc, first ? 0u : 1u);
+              else mma_f16_acc(dcol, aoff, a_hi32, boff[ky][ks] + (hl ? 96u : 0u), b_hi32, idesc);
+            }
         }
         first = false;
       }
@@ -864,7 +885,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
   // ===================== epilogue =====================
   __syncthreads();
   float* red = reinterpret_cast<float*>(smem_raw);         // [2 shifts][32 ci][480]: the X_lo rows
-  float* s_bias = red + 2 * 32 * 480;                      // [2 groups][8 chunks][4]
+  float* s_bias = red + 2 * 32 * 480;                      // [4 G warps][8 chunks][4]
   float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
   const float inv = 1.f / (sx_scale * sg_scale);           // powers of two: exact
   if (warp < MMA_WARP) {
@@ -873,13 +894,12 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
   }
   if (warp < MMA_WARP && (warp & 3) >= 2) {                // G warps: 8 lanes (pixel chunks) share a channel chunk
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = 16; o >= 8; o >>= 1) {
       bias_acc.x += __shfl_xor_sync(0xffffffffu, bias_acc.x, o); bias_acc.y += __shfl_xor_sync(0xffffffffu, bias_acc.y, o);
       bias_acc.z += __shfl_xor_sync(0xffffffffu, bias_acc.z, o); bias_acc.w += __shfl_xor_sync(0xffffffffu, bias_acc.w, o);
     }
-    if ((lane & 7) == 0) {
-      const int cc = (warp & 1) * 4 + (lane >> 3);
-      float* dst = s_bias + ((warp >> 2) * 8 + cc) * 4;
+    if (lane < 8) {                                        // lane = channel chunk; one partial per G warp
+      float* dst = s_bias + (((warp >> 2) * 2 + (warp & 1)) * 8 + lane) * 4;
       dst[0] = bias_acc.x; dst[1] = bias_acc.y; dst[2] = bias_acc.z; dst[3] = bias_acc.w;
     }
   }
@@ -905,19 +925,21 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
           const int col = 96 * ky + 32 * c + c0;
           tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
           tmem_ld_wait();
-          if (lane < cin_pad) {
+          const int ci = 4 * (lane & 7) + (lane >> 3);     // row 8*r + cc holds channel 4*cc + r
+          if (ci < cin_pad) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int co = c0 + i;
+              const int pc = c0 + i, co = 4 * (pc & 7) + (pc >> 3);
               if (co < g_chunks * 4)
-                slab[((size_t)(ky * 5 + kx) * cin_pad + lane) * cout_total + co0 + co] =
+                slab[((size_t)(ky * 5 + kx) * cin_pad + ci) * cout_total + co0 + co] =
                     (v[i] + red[((size_t)sub * 32 + lane) * 480 + col + i]) * inv;
             }
           }
         }
       }
   }
-  if (tid < g_chunks * 4) slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = s_bias[tid] + s_bias[32 + tid];
+  if (tid < g_chunks * 4)
+    slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = (s_bias[tid] + s_bias[32 + tid]) + (s_bias[64 + tid] + s_bias[96 + tid]);
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);

@@ -54,6 +54,14 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t alo, uint32_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
       :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// accumulating form without the predicate set-up (shorter issue sequence)
+__device__ __forceinline__ void mma_f16_acc(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                            uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t}\n"
+      :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
 // Power-of-two scale that brings a tensor whose largest magnitude has the fp32 bit pattern `maxbits` into [2^13, 2^14)
 // (fp16 overflows at 2^16; products are accumulated in fp32).  Zero / denormal maxima get scale 1.
 __host__ __device__ __forceinline__ uint32_t f16_scale_bits(uint32_t maxbits) {
