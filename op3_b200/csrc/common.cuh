@@ -102,6 +102,11 @@ struct ConvInput {
   int nsrc;
   int total_chunks;
   int real_cin;           // channels that carry data (0 = 4*total_chunks); only used for FLOP accounting
+  // fp16 mode only (see conv5x5_tc.cu): per-image largest magnitudes (fp32 bit patterns).  `maxbits` != NULL: already
+  // known for this input (written by its producer), the consumer skips its own reduction pass.  `out_maxbits` != NULL:
+  // the tensor-core kernel atomically maxes the magnitudes of the tensor it writes into it (the caller zeroes it).
+  const uint32_t* maxbits;
+  uint32_t* out_maxbits;
 };
 enum { EPI_NONE = 0, EPI_ELU = 1, EPI_MUL_ELUGRAD = 2 };
 // out[n][cout/4][D][D] = epi( conv5x5_pad2(in, wt) + bias ); wt layout [25][cin_pad][cout] (cout fastest)

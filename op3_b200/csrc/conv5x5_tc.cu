@@ -214,6 +214,7 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
       const int ntile = min(G, tiles_img - grp * G);
       const int q0 = grp * G * 128;
       const int buf = j & 1;
+      float omax = 0.f;
       float inv_scale = 1.f;
       if (F16) inv_scale = 1.f / (__uint_as_float(f16_scale_bits(maxbits[n])) * __ldg(wscale));   // powers of two: exact
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
@@ -258,8 +259,14 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
               r.z *= elu_grad_from_out(ra[c4].z); r.w *= elu_grad_from_out(ra[c4].w);
             }
             out[obase + c4 * plane] = r;
+            if (F16) omax = fmaxf(omax, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
           }
         }
+      }
+      if (F16 && in.out_maxbits != nullptr) {             // magnitudes of the written tensor, for its consumer's operand scale
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+        if (lane == 0 && omax > 0.f) atomicMax(&in.out_maxbits[n], __float_as_uint(omax));
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);                      // this thread is done reading the buffer
@@ -337,7 +344,7 @@ size_t conv5x5_tc_f16_slab_floats(int cin_pad, int nout) {
   return (size_t)groups16 * 25 * 2 * (2 * nout) * 4 + 4;
 }
 
-size_t tc_scratch_floats(int N) { return ((size_t)N + 3) & ~(size_t)3; }
+size_t tc_scratch_floats(int N) { return 8 * tc_slot_floats(N); }
 
 // Weight slab layout consumed by the kernel (built by op3_prepare): [K group of 8 ci][tap 25][k-chunk 2][row NB][4 ci]
 // with NB = nout rows (1xTF32: rn_tf32(w)) or 2*nout rows (3xTF32: hi rows, then lo rows).  cout = 64 in the split modes is
@@ -352,11 +359,15 @@ int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvI
   const int planes = cout / 4;
   if (precision == OP3_PREC_F16X3) {
     OP3_REQUIRE(tc_scratch != nullptr, "conv5x5_tc: the fp16 mode needs tc_scratch");
-    uint32_t* maxbits = reinterpret_cast<uint32_t*>(tc_scratch);
-    OP3_CHECK(cudaMemsetAsync(maxbits, 0, (size_t)N * sizeof(uint32_t), st));
-    tc_absmax_kernel<<<dim3(N, in.total_chunks), 256, 0, st>>>(in, D, maxbits);
-    OP3_COUNT_LAUNCH();
-    OP3_LAUNCH_CHECK();
+    const uint32_t* maxbits = in.maxbits;
+    if (maxbits == nullptr) {                              // the producer did not record them: reduce here (slot 0)
+      uint32_t* mb = reinterpret_cast<uint32_t*>(tc_scratch);
+      OP3_CHECK(cudaMemsetAsync(mb, 0, (size_t)N * sizeof(uint32_t), st));
+      tc_absmax_kernel<<<dim3(N, in.total_chunks), 256, 0, st>>>(in, D, mb);
+      OP3_COUNT_LAUNCH();
+      OP3_LAUNCH_CHECK();
+      maxbits = mb;
+    }
     const int h_nout = nout == 64 ? 32 : nout;
     const size_t slab = conv5x5_tc_f16_slab_floats(in.total_chunks * 4, h_nout);
     if (nout == 16) return launch_tc<16, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);

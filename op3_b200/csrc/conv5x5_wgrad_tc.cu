@@ -355,6 +355,15 @@ __global__ void __launch_bounds__(256) wg_absmax_kernel(ConvInput in, int D, uin
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
+// largest of n per-image maxima (every thread computes the same value; n is a few hundred words, L1/L2 resident)
+__device__ __forceinline__ uint32_t wg_tensor_max(const uint32_t* __restrict__ m, int n) {
+  uint32_t v = 0u;
+  for (int i = (int)(threadIdx.x & 31); i < n; i += 32) v = max(v, __ldg(m + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 // two scaled floats -> packed fp16 pair hi and the pair lo = rn(value - hi)
 __device__ __forceinline__ void hg_pair(float a, float b, float sc, uint32_t& hi, uint32_t& lo) { f16_split2(a * sc, b * sc, hi, lo); }
 // (a.hi16, b.lo16): the pixel pair shifted by one pixel
@@ -362,8 +371,8 @@ __device__ __forceinline__ uint32_t hg_shift1(uint32_t a, uint32_t b) { return _
 
 __global__ void __launch_bounds__(HG_THREADS, 1)
 conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ dpre, int g_planes, int g_chunk0, int g_chunks,
-                         int cout_total, int co0, const uint32_t* __restrict__ xmax, const uint32_t* __restrict__ gmax,
-                         float* __restrict__ partial) {
+                         int cout_total, int co0, const uint32_t* __restrict__ xmax, int xmax_n,
+                         const uint32_t* __restrict__ gmax, int gmax_n, float* __restrict__ partial) {
   constexpr int NCO = 32;
   const int P = D + 8;                                     // multiple of 8
   const int QN = (D + 4) * P;                              // padded-linear input pixels per image
@@ -375,8 +384,8 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int a0 = (ky * P) >> 3;                            // chunk offset of this kernel row
   const bool have = n_items > (int)blockIdx.x;
-  const float sx_scale = __uint_as_float(f16_scale_bits(__ldg(xmax)));
-  const float sg_scale = __uint_as_float(f16_scale_bits(__ldg(gmax)));
+  const float sx_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(xmax, xmax_n)));     // one scale per TENSOR: the sum runs
+  const float sg_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(gmax, gmax_n)));     // over all images
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[HG_GROUPS], empty_bar[HG_GROUPS], acc_bar;
@@ -642,8 +651,8 @@ constexpr int RB_SMEM = RB_RING_BYTES + 2 * RB_A_BYTES;
 
 __global__ void __launch_bounds__(RB_THREADS, 1)
 conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const float4* __restrict__ dpre, int g_planes,
-                          int g_chunk0, int g_chunks, int cout_total, int co0, const uint32_t* __restrict__ xmax,
-                          const uint32_t* __restrict__ gmax, float* __restrict__ partial) {
+                          int g_chunk0, int g_chunks, int cout_total, int co0, const uint32_t* __restrict__ xmax, int xmax_n,
+                          const uint32_t* __restrict__ gmax, int gmax_n, float* __restrict__ partial) {
   constexpr int NCO = 32;
   const int P = D + 8;                                     // multiple of 8
   const int QN = (D + 4) * P;                              // padded-linear input pixels per image
@@ -653,8 +662,8 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
   const int cin_pad = cin_chunks * 4;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int achunks = P >> 3;                              // G chunk offset per kernel row
-  const float sx_scale = __uint_as_float(f16_scale_bits(__ldg(xmax)));
-  const float sg_scale = __uint_as_float(f16_scale_bits(__ldg(gmax)));
+  const float sx_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(xmax, xmax_n)));     // one scale per TENSOR: the sum runs
+  const float sg_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(gmax, gmax_n)));     // over all images
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* ring = smem_raw;
@@ -969,7 +978,8 @@ int launch_wgrad_tc(cudaStream_t st, int N, int D, const ConvInput& in, const fl
 }
 
 int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, int g_planes, int g_chunk0,
-                     int g_chunks, int cout_total, int co0, const uint32_t* xmax, const uint32_t* gmax, float* scratch) {
+                     int g_chunks, int cout_total, int co0, const uint32_t* xmax, int xmax_n, const uint32_t* gmax,
+                     int gmax_n, float* scratch) {
   size_t smem = HG_GROUPS * (size_t)HG_STAGE_BYTES;
   OP3_REQUIRE(smem <= 226 * 1024, "conv5x5_wgrad_f16: %zu bytes of shared memory", smem);
   static bool attr_set = false;
@@ -979,7 +989,7 @@ int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const f
   }
   dim3 grid(wg_sets(), 5);
   conv5x5_wgrad_f16_kernel<<<grid, HG_THREADS, smem, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total, co0, xmax,
-                                                          gmax, scratch);
+                                                          xmax_n, gmax, gmax_n, scratch);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
@@ -989,8 +999,8 @@ int g_wg_sms = 0;
 
 // returns the number of per-CTA partial slabs written (the grid size)
 int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, int g_planes, int g_chunk0,
-                      int g_chunks, int cout_total, int co0, const uint32_t* xmax, const uint32_t* gmax, float* scratch,
-                      int* grid_out) {
+                      int g_chunks, int cout_total, int co0, const uint32_t* xmax, int xmax_n, const uint32_t* gmax,
+                      int gmax_n, float* scratch, int* grid_out) {
   static bool attr_set = false;
   if (!attr_set) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -1019,7 +1029,7 @@ int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const 
   const long long items = (long long)N * SEG;
   const int grid = items < g_wg_sms ? (int)items : g_wg_sms;
   conv5x5_wgrad_ring_kernel<<<grid, RB_THREADS, RB_SMEM, st>>>(in, N, D, SEG, L, dpre, g_planes, g_chunk0, g_chunks, cout_total,
-                                                              co0, xmax, gmax, scratch);
+                                                              co0, xmax, xmax_n, gmax, gmax_n, scratch);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   *grid_out = grid;
@@ -1034,7 +1044,7 @@ size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout) {
 
 // dwt [25][cin_pad][cout] and dbias [cout] are ACCUMULATED (same contract as conv5x5_wgrad).
 int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float4* dpre,
-                     float* scratch, float* dwt, float* dbias) {
+                     float* scratch, float* dwt, float* dbias, const uint32_t* dpre_maxbits) {
   if (N <= 0) return OP3_OK;
   OP3_REQUIRE(cout % 4 == 0 && cout <= 64 && in.total_chunks <= 8 && D % 4 == 0,
               "conv5x5_wgrad_tc: unsupported cin chunks %d / cout %d / D %d", in.total_chunks, cout, D);
@@ -1051,23 +1061,32 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
   OP3_CHECK(cudaMemsetAsync(scratch, 0, (zero_slabs * slab + 8) * sizeof(float), st));   // padding entries stay zero
   if (f16) {
     // per-tensor operand maxima live in the 8 words after the partial slabs (scratch: conv5x5_wgrad_scratch_floats)
+    // operand maxima: per-image arrays recorded by the producers (n = N entries), else one word reduced here (n = 1)
     uint32_t* mx = reinterpret_cast<uint32_t*>(scratch + zero_slabs * slab);
-    wg_absmax_kernel<<<dim3(N, in.total_chunks), 256, 0, st>>>(in, D, mx);
-    OP3_COUNT_LAUNCH();
-    ConvInput gin{};
-    gin.src[0].ptr = dpre; gin.src[0].nchunks = planes; gin.src[0].div = 1;
-    gin.nsrc = 1; gin.total_chunks = planes;
-    wg_absmax_kernel<<<dim3(N, planes), 256, 0, st>>>(gin, D, mx + 4);
-    OP3_COUNT_LAUNCH();
+    const uint32_t *xmax = in.maxbits, *gmax = dpre_maxbits;
+    int xmax_n = N, gmax_n = N;
+    if (xmax == nullptr) {
+      wg_absmax_kernel<<<dim3(N, in.total_chunks), 256, 0, st>>>(in, D, mx);
+      OP3_COUNT_LAUNCH();
+      xmax = mx; xmax_n = 1;
+    }
+    if (gmax == nullptr) {
+      ConvInput gin{};
+      gin.src[0].ptr = dpre; gin.src[0].nchunks = planes; gin.src[0].div = 1;
+      gin.nsrc = 1; gin.total_chunks = planes;
+      wg_absmax_kernel<<<dim3(N, planes), 256, 0, st>>>(gin, D, mx + 4);
+      OP3_COUNT_LAUNCH();
+      gmax = mx + 4; gmax_n = 1;
+    }
     OP3_LAUNCH_CHECK();
     if (4 * ((D + 8) / 8) <= 8 * RB_PRE) {               // ring kernel: its refill covers the 4-row halo of G chunks
       int grid = 0;
       for (int h = 0; h * 32 < cout; ++h)
-        OP3_TRY(launch_wgrad_ring(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, mx, mx + 4, scratch, &grid));
+        OP3_TRY(launch_wgrad_ring(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, xmax, xmax_n, gmax, gmax_n, scratch, &grid));
       n_slabs = grid;
     } else {
       for (int h = 0; h * 32 < cout; ++h)
-        OP3_TRY(launch_wgrad_f16(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, mx, mx + 4, scratch));
+        OP3_TRY(launch_wgrad_f16(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, xmax, xmax_n, gmax, gmax_n, scratch));
     }
   } else if (cout <= 16) {
     OP3_TRY((s3 ? launch_wgrad_tc<16, true>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)
@@ -1087,10 +1106,10 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
 }
 
 int conv5x5_wgrad_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
-                       float* dwt, float* dbias) {
+                       float* dwt, float* dbias, const uint32_t* dpre_maxbits) {
   const int prec = op3_get_precision();
   if (prec == OP3_PREC_FP32 || cout == 4) return conv5x5_wgrad(st, N, D, in, cout, dpre, scratch, dwt, dbias);   // see conv5x5_auto
-  return conv5x5_wgrad_tc(st, prec, N, D, in, cout, dpre, scratch, dwt, dbias);
+  return conv5x5_wgrad_tc(st, prec, N, D, in, cout, dpre, scratch, dwt, dbias, dpre_maxbits);
 }
 
 }  // namespace op3

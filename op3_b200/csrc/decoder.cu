@@ -11,17 +11,26 @@ namespace {
 __device__ __forceinline__ int border_class(int v, int D) { return v < 2 ? v : (v >= D - 2 ? 4 - (D - 1 - v) : 2); }
 
 // a1[n][c4][y][x] = ELU(T[n][cls(y,x)*32 + c4*4 ..] + cmap[c4][y][x])
+// maxbits (optional): per-image largest magnitude of a1 for the fp16 conv mode (zeroed by the caller)
 __global__ void __launch_bounds__(256) dec_l1_expand_kernel(const float* __restrict__ T, const float4* __restrict__ cmap,
-                                                            int D, float4* __restrict__ a1) {
+                                                            int D, float4* __restrict__ a1, uint32_t* __restrict__ maxbits) {
   const int n = blockIdx.y;
   int i = blockIdx.x * 256 + threadIdx.x;  // over 8*D*D
-  if (i >= 8 * D * D) return;
-  int x = i % D, y = (i / D) % D, c4 = i / (D * D);
-  int cls = border_class(y, D) * 5 + border_class(x, D);
-  float4 t = *reinterpret_cast<const float4*>(T + (size_t)n * (NCLS * 32) + cls * 32 + c4 * 4);
-  float4 m = cmap[i];
-  float4 v = make_float4(elu_f(t.x + m.x), elu_f(t.y + m.y), elu_f(t.z + m.z), elu_f(t.w + m.w));
-  a1[(size_t)n * 8 * D * D + i] = v;
+  float mx = 0.f;
+  if (i < 8 * D * D) {
+    int x = i % D, y = (i / D) % D, c4 = i / (D * D);
+    int cls = border_class(y, D) * 5 + border_class(x, D);
+    float4 t = *reinterpret_cast<const float4*>(T + (size_t)n * (NCLS * 32) + cls * 32 + c4 * 4);
+    float4 m = cmap[i];
+    float4 v = make_float4(elu_f(t.x + m.x), elu_f(t.y + m.y), elu_f(t.z + m.z), elu_f(t.w + m.w));
+    a1[(size_t)n * 8 * D * D + i] = v;
+    mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (maxbits != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&maxbits[n], __float_as_uint(mx));
+  }
 }
 
 // dT[n][cls*32 + co] = sum over pixels of class cls of g1[n][co][y][x]; one CTA per (chunk, n); deterministic.
@@ -131,13 +140,20 @@ extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const
   // T[n][cls*32+co] = b[co] + sum_c z[n][c] * Wsum[cls*32+co][c]
   OP3_TRY(gemm(st, N, NCLS * 32, R, z, R, 0, prep + L.wsum, R, 1, A.T, NCLS * 32, prep + L.biasT, ACT_NONE, 0));
   dim3 grid(ceil_div(8 * D * D, 256), N);
-  dec_l1_expand_kernel<<<grid, 256, 0, st>>>(A.T, reinterpret_cast<const float4*>(prep + L.cmap), D, A.a[0]);
+  // fp16 mode: slots 1..4 of tcs keep the per-image maxima of a1..a4 (written by their producers, reused by backward)
+  const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
+  if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
+  dec_l1_expand_kernel<<<grid, 256, 0, st>>>(A.T, reinterpret_cast<const float4*>(prep + L.cmap), D, A.a[0],
+                                             f16 ? tc_slot(tcs, N, 1) : nullptr);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   // layers 2-4 are the implicit-GEMM hot spot (M = N*D*D pixels, N = 32, K = 800); layer 5 has 4 outputs
-  for (int i = 0; i < 3; ++i)
-    OP3_TRY(conv5x5_auto(st, N, D, single_src(A.a[i], 8), 32, prep + L.dec_wf[i], prep + L.dec_tf[i], prep + L.dec_bf[i],
-                         A.a[i + 1], EPI_ELU, nullptr, tcs));
+  for (int i = 0; i < 3; ++i) {
+    ConvInput in = single_src(A.a[i], 8);
+    if (f16) { in.maxbits = tc_slot(tcs, N, 1 + i); in.out_maxbits = tc_slot(tcs, N, 2 + i); }
+    OP3_TRY(conv5x5_auto(st, N, D, in, 32, prep + L.dec_wf[i], prep + L.dec_tf[i], prep + L.dec_bf[i], A.a[i + 1], EPI_ELU,
+                         nullptr, tcs));
+  }
   OP3_TRY(conv5x5_auto(st, N, D, single_src(A.a[3], 8), 4, prep + L.dec_wf[3], prep + L.dec_tf[3], prep + L.dec_bf[3],
                        reinterpret_cast<float4*>(out), EPI_NONE, nullptr, tcs));
   return OP3_OK;
@@ -158,17 +174,29 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
   float* wscr = dT + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3);
   float* tcs = wscr + conv5x5_wgrad_scratch_floats(32, 32);
 
+  // fp16 mode: the forward pass left the maxima of a1..a4 in slots 1..4 of the acts' scratch; the dgrad kernels record
+  // the maxima of the gradients they write in slots 1..4 of this call's scratch
+  const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
+  const float* atcs = acts + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) + 4 * (size_t)N * 32 * D * D;
+  if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
   // layer 5 (32 -> 4, no activation): g5 = d_out
   const float4* g = reinterpret_cast<const float4*>(d_out);
+  const uint32_t* gmax = nullptr;  // maxima of g (NULL: not recorded)
   int gch = 1;  // chunks of g
   for (int i = 3; i >= 0; --i) {  // conv layer i+2, input a[i], output gradient g (dPre of that layer)
     const int cout = i == 3 ? 4 : 32;
-    if (pg) OP3_TRY(conv5x5_wgrad_auto(st, N, D, single_src(A.a[i], 8), cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i]));
+    if (pg) {
+      ConvInput xin = single_src(A.a[i], 8);
+      if (f16) xin.maxbits = tc_slot(atcs, N, 1 + i);
+      OP3_TRY(conv5x5_wgrad_auto(st, N, D, xin, cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i], gmax));
+    }
     float4* gn = gbuf[i & 1];
     // dgrad: conv over g with flipped/transposed weights, times ELU'(a[i]) -> dPre of the layer below
-    OP3_TRY(conv5x5_auto(st, N, D, single_src(g, gch), 32, prep + L.dec_wd[i], prep + L.dec_td[i], nullptr, gn,
-                         EPI_MUL_ELUGRAD, A.a[i], tcs));
+    ConvInput gin = single_src(g, gch);
+    if (f16) { gin.maxbits = gmax; gin.out_maxbits = tc_slot(tcs, N, 1 + i); }
+    OP3_TRY(conv5x5_auto(st, N, D, gin, 32, prep + L.dec_wd[i], prep + L.dec_td[i], nullptr, gn, EPI_MUL_ELUGRAD, A.a[i], tcs));
     g = gn;
+    gmax = f16 ? gin.out_maxbits : nullptr;
     gch = 8;
   }
   // layer 1: g = dPre1 [N][8][D][D]

@@ -125,17 +125,28 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const float4* __restrict__
 }
 
 // g3[n][c4][p] = dpooled[n][c4*4..] / DD * ELU'(r3)
+// maxbits (optional): per-image largest magnitude of g3 for the fp16 conv mode (zeroed by the caller)
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dpooled, const float4* __restrict__ r3,
-                                                          int chunks, int DD, float4* __restrict__ g3) {
+                                                          int chunks, int DD, float4* __restrict__ g3,
+                                                          uint32_t* __restrict__ maxbits) {
   const int n = blockIdx.y;
   int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= chunks * DD) return;
-  int c4 = i / DD;
-  float inv = 1.f / (float)DD;
-  float4 d = *reinterpret_cast<const float4*>(dpooled + (size_t)n * chunks * 4 + c4 * 4);
-  float4 a = r3[(size_t)n * chunks * DD + i];
-  g3[(size_t)n * chunks * DD + i] = make_float4(d.x * inv * elu_grad_from_out(a.x), d.y * inv * elu_grad_from_out(a.y),
-                                                d.z * inv * elu_grad_from_out(a.z), d.w * inv * elu_grad_from_out(a.w));
+  float mx = 0.f;
+  if (i < chunks * DD) {
+    int c4 = i / DD;
+    float inv = 1.f / (float)DD;
+    float4 d = *reinterpret_cast<const float4*>(dpooled + (size_t)n * chunks * 4 + c4 * 4);
+    float4 a = r3[(size_t)n * chunks * DD + i];
+    float4 v = make_float4(d.x * inv * elu_grad_from_out(a.x), d.y * inv * elu_grad_from_out(a.y),
+                           d.z * inv * elu_grad_from_out(a.z), d.w * inv * elu_grad_from_out(a.w));
+    g3[(size_t)n * chunks * DD + i] = v;
+    mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (maxbits != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&maxbits[n], __float_as_uint(mx));
+  }
 }
 
 __global__ void lstm_fwd_kernel(int N, const float* __restrict__ gates, const float* __restrict__ c, float* __restrict__ h2,
@@ -299,9 +310,20 @@ extern "C" int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float*
   RefActs A = ref_acts(d, io->acts);
   float* tcs = ref_acts_tcs(d, io->acts);
   // conv stack 17(20) -> 32 -> 32 -> Rs, ELU each (refinement_network.py:195)
-  OP3_TRY(conv5x5_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr, tcs));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr, tcs));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr, tcs));
+  {
+    // fp16 mode: slots 1..3 of tcs keep the per-image maxima of r1..r3 (recorded by their producers, reused by backward)
+    const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
+    if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
+    ConvInput i1 = refine_l1_input(d, io, prep, L), i2 = one_src(A.r1, 8), i3 = one_src(A.r2, 8);
+    if (f16) {
+      i1.out_maxbits = tc_slot(tcs, N, 1);
+      i2.maxbits = tc_slot(tcs, N, 1); i2.out_maxbits = tc_slot(tcs, N, 2);
+      i3.maxbits = tc_slot(tcs, N, 2); i3.out_maxbits = tc_slot(tcs, N, 3);
+    }
+    OP3_TRY(conv5x5_auto(st, N, D, i1, 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr, tcs));
+    OP3_TRY(conv5x5_auto(st, N, D, i2, 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr, tcs));
+    OP3_TRY(conv5x5_auto(st, N, D, i3, Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr, tcs));
+  }
   avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
@@ -338,9 +360,20 @@ extern "C" int op3_refine_net_fwd(const Op3Dims* d, const Op3Params* p, const fl
   float* tcs = ref_acts_tcs(d, acts);
   ConvInput in = one_src(reinterpret_cast<const float4*>(in_chunks), 5);
   in.real_cin = 17;
-  OP3_TRY(conv5x5_auto(st, N, D, in, 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr, tcs));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r1, 8), 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr, tcs));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(A.r2, 8), Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr, tcs));
+  {
+    // fp16 mode: slots 1..3 of tcs keep the per-image maxima of r1..r3 (recorded by their producers, reused by backward)
+    const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
+    if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
+    ConvInput i1 = in, i2 = one_src(A.r1, 8), i3 = one_src(A.r2, 8);
+    if (f16) {
+      i1.out_maxbits = tc_slot(tcs, N, 1);
+      i2.maxbits = tc_slot(tcs, N, 1); i2.out_maxbits = tc_slot(tcs, N, 2);
+      i3.maxbits = tc_slot(tcs, N, 2); i3.out_maxbits = tc_slot(tcs, N, 3);
+    }
+    OP3_TRY(conv5x5_auto(st, N, D, i1, 32, prep + L.ref_wf[0], prep + L.ref_tf[0], prep + L.ref_bf[0], A.r1, EPI_ELU, nullptr, tcs));
+    OP3_TRY(conv5x5_auto(st, N, D, i2, 32, prep + L.ref_wf[1], prep + L.ref_tf[1], prep + L.ref_bf[1], A.r2, EPI_ELU, nullptr, tcs));
+    OP3_TRY(conv5x5_auto(st, N, D, i3, Rs, prep + L.ref_wf[2], prep + L.ref_tf[2], prep + L.ref_bf[2], A.r3, EPI_ELU, nullptr, tcs));
+  }
   avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
@@ -432,15 +465,29 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   OP3_TRY(gemm(st, HID, Rs, N, dX, XW, 1, A.pooled, Rs, 0, g->ref_fc.w, Rs, nullptr, ACT_NONE, 1));
   OP3_TRY(colsum(st, N, HID, dX, XW, g->ref_fc.b, 1));
   // conv stack
-  avgpool_bwd_kernel<<<dim3(ceil_div(Rs / 4 * DD, 256), N), 256, 0, st>>>(dpool, A.r3, Rs / 4, DD, g3);
+  // fp16 mode: maxima of r1, r2 come from the forward pass (acts), those of g3, g2, g1 are recorded in slots 1..3 here
+  const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
+  const float* atcs = ref_acts_tcs(d, io->acts);
+  if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
+  avgpool_bwd_kernel<<<dim3(ceil_div(Rs / 4 * DD, 256), N), 256, 0, st>>>(dpool, A.r3, Rs / 4, DD, g3,
+                                                                         f16 ? tc_slot(tcs, N, 1) : nullptr);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
-  OP3_TRY(conv5x5_wgrad_auto(st, N, D, one_src(A.r2, 8), Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2]));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(g3, Rs / 4), 32, prep + L.ref_wd[2], prep + L.ref_td[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2, tcs));
-  OP3_TRY(conv5x5_wgrad_auto(st, N, D, one_src(A.r1, 8), 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1]));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(g2, 8), 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1, tcs));
-  OP3_TRY(conv5x5_wgrad_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0]));
-  OP3_TRY(conv5x5_auto(st, N, D, one_src(g1, 8), REF_CIN_PAD, prep + L.ref_wd[0], prep + L.ref_td[0], nullptr,
+  ConvInput x2 = one_src(A.r2, 8), x1 = one_src(A.r1, 8), gi3 = one_src(g3, Rs / 4), gi2 = one_src(g2, 8), gi1 = one_src(g1, 8);
+  const uint32_t *m3 = nullptr, *m2 = nullptr, *m1 = nullptr;
+  if (f16) {
+    x2.maxbits = tc_slot(atcs, N, 2); x1.maxbits = tc_slot(atcs, N, 1);
+    m3 = tc_slot(tcs, N, 1); m2 = tc_slot(tcs, N, 2); m1 = tc_slot(tcs, N, 3);
+    gi3.maxbits = m3; gi3.out_maxbits = tc_slot(tcs, N, 2);
+    gi2.maxbits = m2; gi2.out_maxbits = tc_slot(tcs, N, 3);
+    gi1.maxbits = m1;
+  }
+  OP3_TRY(conv5x5_wgrad_auto(st, N, D, x2, Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2], m3));
+  OP3_TRY(conv5x5_auto(st, N, D, gi3, 32, prep + L.ref_wd[2], prep + L.ref_td[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2, tcs));
+  OP3_TRY(conv5x5_wgrad_auto(st, N, D, x1, 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1], m2));
+  OP3_TRY(conv5x5_auto(st, N, D, gi2, 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1, tcs));
+  OP3_TRY(conv5x5_wgrad_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0], m1));
+  OP3_TRY(conv5x5_auto(st, N, D, gi1, REF_CIN_PAD, prep + L.ref_wd[0], prep + L.ref_td[0], nullptr,
                        reinterpret_cast<float4*>(d_in), EPI_NONE, nullptr, tcs));
   return OP3_OK;
 }

@@ -149,16 +149,20 @@ __device__ __forceinline__ const float4* tc_src_chunk_ptr(const ConvInput& in, i
 int tc_nout(int cout);
 size_t conv5x5_tc_weight_floats(int cin_pad, int cout);
 size_t conv5x5_tc_f16_slab_floats(int cin_pad, int nout);   // one fp16 slab (+ its scale word), in floats
-size_t tc_scratch_floats(int N);                             // per-image operand maxima of the fp16 mode
+size_t tc_scratch_floats(int N);                             // 8 slots of per-image operand maxima (fp16 mode)
+inline size_t tc_slot_floats(int N) { return ((size_t)N + 3) & ~(size_t)3; }
+inline uint32_t* tc_slot(float* base, int N, int slot) { return reinterpret_cast<uint32_t*>(base + slot * tc_slot_floats(N)); }
+inline const uint32_t* tc_slot(const float* base, int N, int slot) { return reinterpret_cast<const uint32_t*>(base + slot * tc_slot_floats(N)); }
 int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float* wt,
                        const float* bias, float4* out, int epi, const float4* elu_ref, float* tc_scratch);
 
 // conv5x5_wgrad_tc.cu
 size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout);
+// dpre_maxbits: per-image maxima of dpre if its producer recorded them (fp16 mode), else NULL
 int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInput& in, int cout, const float4* dpre,
-                     float* scratch, float* dwt, float* dbias);
+                     float* scratch, float* dwt, float* dbias, const uint32_t* dpre_maxbits);
 int conv5x5_wgrad_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
-                       float* dwt, float* dbias);
+                       float* dwt, float* dbias, const uint32_t* dpre_maxbits);
 // tc_scratch: tc_scratch_floats(N) floats of caller scratch (only touched in the fp16 mode)
 int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
                  const float* bias, float4* out, int epi, const float4* elu_ref, float* tc_scratch);
