@@ -266,7 +266,7 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
       if (F16 && in.out_maxbits != nullptr) {             // magnitudes of the written tensor, for its consumer's operand scale
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
-        if (lane == 0 && omax > 0.f) atomicMax(&in.out_maxbits[n], __float_as_uint(omax));
+        if (lane == 0 && __float_as_uint(omax) > __ldcg(&in.out_maxbits[n])) atomicMax(&in.out_maxbits[n], __float_as_uint(omax));
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);                      // this thread is done reading the buffer

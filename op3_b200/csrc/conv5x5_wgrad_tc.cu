@@ -1055,7 +1055,7 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
   const int cin_pad = in.total_chunks * 4;
   const size_t slab = (size_t)25 * cin_pad * cout + cout;
   int n_slabs = wg_sets();
-  const bool f16 = precision == OP3_PREC_F16X3 && cout >= 32 && D % 8 == 0;
+  const bool f16 = precision == OP3_PREC_F16X3 && (cout >= 32 || cout == 4) && D % 8 == 0;
   const bool use_ring = f16 && 4 * ((D + 8) / 8) <= 8 * RB_PRE;
   const size_t zero_slabs = use_ring ? 148 : (size_t)wg_sets();
   OP3_CHECK(cudaMemsetAsync(scratch, 0, (zero_slabs * slab + 8) * sizeof(float), st));   // padding entries stay zero
@@ -1082,11 +1082,13 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
     if (4 * ((D + 8) / 8) <= 8 * RB_PRE) {               // ring kernel: its refill covers the 4-row halo of G chunks
       int grid = 0;
       for (int h = 0; h * 32 < cout; ++h)
-        OP3_TRY(launch_wgrad_ring(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, xmax, xmax_n, gmax, gmax_n, scratch, &grid));
+        OP3_TRY(launch_wgrad_ring(st, N, D, in, dpre, planes, 8 * h, planes - 8 * h < 8 ? planes - 8 * h : 8, cout, 32 * h, xmax, xmax_n,
+                                  gmax, gmax_n, scratch, &grid));
       n_slabs = grid;
     } else {
       for (int h = 0; h * 32 < cout; ++h)
-        OP3_TRY(launch_wgrad_f16(st, N, D, in, dpre, planes, 8 * h, 8, cout, 32 * h, xmax, xmax_n, gmax, gmax_n, scratch));
+        OP3_TRY(launch_wgrad_f16(st, N, D, in, dpre, planes, 8 * h, planes - 8 * h < 8 ? planes - 8 * h : 8, cout, 32 * h, xmax, xmax_n,
+                                 gmax, gmax_n, scratch));
     }
   } else if (cout <= 16) {
     OP3_TRY((s3 ? launch_wgrad_tc<16, true>(st, N, D, in, dpre, planes, 0, planes, cout, 0, scratch)
@@ -1108,7 +1110,9 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
 int conv5x5_wgrad_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float4* dpre, float* scratch,
                        float* dwt, float* dbias, const uint32_t* dpre_maxbits) {
   const int prec = op3_get_precision();
-  if (prec == OP3_PREC_FP32 || cout == 4) return conv5x5_wgrad(st, N, D, in, cout, dpre, scratch, dwt, dbias);   // see conv5x5_auto
+  // the 4-channel layer stays on the FMA pipe in the TF32 modes (see conv5x5_auto); the fp16 ring kernel beats it (0.31 vs
+  // 0.44 ms) because its cost does not depend on the number of output channels
+  if (prec == OP3_PREC_FP32 || (cout == 4 && prec != OP3_PREC_F16X3)) return conv5x5_wgrad(st, N, D, in, cout, dpre, scratch, dwt, dbias);
   return conv5x5_wgrad_tc(st, prec, N, D, in, cout, dpre, scratch, dwt, dbias, dpre_maxbits);
 }
 

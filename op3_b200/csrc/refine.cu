@@ -142,10 +142,18 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
     g3[(size_t)n * chunks * DD + i] = v;
     mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
-  if (maxbits != nullptr) {
+  if (maxbits != nullptr) {                                // one atomic per block, and only if it can raise the maximum
+    __shared__ float s_mx[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&maxbits[n], __float_as_uint(mx));
+    if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_mx[w]);
+      const uint32_t b = __float_as_uint(mx);
+      if (b > __ldcg(&maxbits[n])) atomicMax(&maxbits[n], b);
+    }
   }
 }
 
