@@ -1,25 +1,32 @@
-// Batched small-GEMM + elementwise helpers (fp32 CUDA-core path) used by the refinement head and the
-// pairwise dynamics network.  These are < 1 % of the step FLOPs; shapes are
-// M = B*K or B*K*(K-1) rows, widths 1..576.
+// Small-GEMM + elementwise helpers (fp32 CUDA-core path) used by the refinement head, the pairwise dynamics network
+//  and the collapsed decoder layer 1.  These are < 1 % of the step FLOPs; shapes are
+// M = B*K or B*K*(K-1) rows, widths 1..800.
 #include "common.cuh"
 
 namespace op3 {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 32;
+constexpr int BM = 32, BN = 32, BK = 16, KG = 4;
 
-// 64x64x32 tiles, 4x4 micro-tiles; the next K-slab is fetched into registers while the current one is multiplied
-// (double-buffered smem, one barrier per slab) so the global-load latency of these small, latency-bound GEMMs overlaps.
+// These GEMMs are tiny (M = B*K or B*K*(K-1) rows, widths <= 800, K <= 800) and latency bound: a 64x64 tiling gives 2..50
+// CTAs whose serial K loop pays one global-load latency per slab.  So: 32x32 output tiles (4x the CTAs) and the K range
+// split over the four 64-thread groups of the CTA (4x shorter serial chain), each group register-prefetching its next
+// 16-deep slab while it multiplies the current one; the four partial tiles are added in a fixed order through shared memory.
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                    const float* __restrict__ B, int ldb, float* __restrict__ C,
                                                    int ldc, const float* __restrict__ bias, int act, int accumulate) {
-  __shared__ float As[2][BK][BM + 4];
-  __shared__ float Bs[2][BK][BN + 4];
+  static_assert(BM == BN, "square tiles");
+  __shared__ float sm[2 * KG * BK * (BM + 4)];
+  float (*As)[BK][BM + 4] = reinterpret_cast<float (*)[BK][BM + 4]>(sm);
+  float (*Bs)[BK][BN + 4] = reinterpret_cast<float (*)[BK][BN + 4]>(sm + KG * BK * (BM + 4));
   const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;
+  const int kg = tid >> 6, t = tid & 63;
+  const int tx = t & 7, ty = t >> 3;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int Kq = ((K + KG * BK - 1) / (KG * BK)) * BK;      // K range of one group (multiple of BK)
+  const int kbeg = kg * Kq, kend = min(K, kbeg + Kq);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -30,67 +37,77 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      int e = tid + r * 256;
+      int e = t + r * 64;
       int mm, kk;
       if (TA == 0) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
       int gm = m0 + mm, gk = k0 + kk;
-      ra[r] = (gm < M && gk < K) ? (TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm]) : 0.f;
+      ra[r] = (gm < M && gk < kend) ? (TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm]) : 0.f;
       int nn;
       if (TB == 0) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
       int gn = n0 + nn;
       gk = k0 + kk;
-      rb[r] = (gn < N && gk < K) ? (TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk]) : 0.f;
+      rb[r] = (gn < N && gk < kend) ? (TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk]) : 0.f;
     }
   };
-  auto stash = [&](int buf) {
+  auto stash = [&]() {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      int e = tid + r * 256;
+      int e = t + r * 64;
       int mm, kk;
       if (TA == 0) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
-      As[buf][kk][mm] = ra[r];
+      As[kg][kk][mm] = ra[r];
       int nn;
       if (TB == 0) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
-      Bs[buf][kk][nn] = rb[r];
+      Bs[kg][kk][nn] = rb[r];
     }
   };
 
-  fetch(0);
-  stash(0);
-  __syncthreads();
-  int buf = 0;
-  for (int k0 = 0; k0 < K; k0 += BK, buf ^= 1) {
-    const bool more = k0 + BK < K;
-    if (more) fetch(k0 + BK);
+  fetch(kbeg);
+  for (int it = 0; it < Kq / BK; ++it) {                   // same trip count for every group: barriers stay uniform
+    const int k0 = kbeg + it * BK;
+    stash();
+    __syncthreads();
+    if (it + 1 < Kq / BK) fetch(k0 + BK);                  // in flight while this slab is multiplied
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[buf][kk][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = As[kg][kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][kk][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kg][kk][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    if (more) stash(buf ^ 1);
     __syncthreads();
   }
+  // partial tiles of groups 1..3 -> shared memory (aliasing the operand buffers), summed by group 0 in a fixed order
+  float (*part)[BM][BN + 1] = reinterpret_cast<float (*)[BM][BN + 1]>(sm);
+  static_assert(sizeof(sm) >= 3 * BM * (BN + 1) * sizeof(float), "reduction buffer does not fit");
+  if (kg > 0) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int gm = m0 + ty * 4 + i;
-    if (gm >= M) continue;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      float v = acc[i][j];
-      if (bias) v += bias[gn];
-      if (accumulate) v += C[(size_t)gm * ldc + gn];
-      if (act == ACT_ELU) v = elu_f(v);
-      else if (act == ACT_SIGMOID) v = sigmoid_f(v);
-      C[(size_t)gm * ldc + gn] = v;
+      for (int j = 0; j < 4; ++j) part[kg - 1][ty * 4 + i][tx * 4 + j] = acc[i][j];
+  }
+  __syncthreads();
+  if (kg == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int gm = m0 + ty * 4 + i;
+      if (gm >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int gn = n0 + tx * 4 + j;
+        if (gn >= N) continue;
+        float v = ((acc[i][j] + part[0][ty * 4 + i][tx * 4 + j]) + part[1][ty * 4 + i][tx * 4 + j]) + part[2][ty * 4 + i][tx * 4 + j];
+        if (bias) v += bias[gn];
+        if (accumulate) v += C[(size_t)gm * ldc + gn];
+        if (act == ACT_ELU) v = elu_f(v);
+        else if (act == ACT_SIGMOID) v = sigmoid_f(v);
+        C[(size_t)gm * ldc + gn] = v;
+      }
     }
   }
 }

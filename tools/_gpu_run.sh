@@ -1,5 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_precision.py tests/test_gpu_kernels.py -x -q -m gpu -s > gpurun_out/t_f16.log 2>&1; echo "pytest rc=$?"
-grep -E "f16x3.*rel|passed|failed|Error" gpurun_out/t_f16.log | head
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -x -q -m gpu > gpurun_out/t_km.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/t_km.log
 timeout 300 python bench.py --steps 3 --warmup 3 --precision f16x3 --no-cpu-baseline > gpurun_out/b_f16.json 2> gpurun_out/b_f16.err; echo "bench rc=$?"
 python - <<'PY'
 import json
