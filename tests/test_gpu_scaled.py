@@ -23,7 +23,7 @@ def build_scaled(K, D, action_dim, seed=0):
     return m.cuda(), p
 
 
-@pytest.mark.parametrize("K,precision", [(14, "fp32"), (8, "tf32x3")])
+@pytest.mark.parametrize("K,precision", [(14, "fp32"), (8, "tf32x3"), (8, "f16x3")])
 def test_scaled_128_matches_oracle(K, precision):
     D, B, T, sched = 128, 1, 2, [0, 0, 1]
     op3_b200.set_precision(precision)
