@@ -295,6 +295,12 @@ def main():
         return
     hbm, bf16, bf16_sus, which = peaks()
     tf32_peak = bf16_sus / 2.0           # dense TF32 tensor-pipe peak ~ 1/2 of the measured (sustained) bf16 figure
+    # the tensor-pipe peak of the mode's operand type (fp16 runs at the bf16 rate), and how many tensor products the mode
+    # issues per algorithmic FLOP (hi*hi + hi*lo + lo*hi)
+    mode_peak = {"fp32": tf32_peak, "tf32x3": tf32_peak, "tf32": tf32_peak, "f16x3": bf16_sus}[args.precision]
+    mode_products = {"fp32": 1.0, "tf32x3": 3.0, "tf32": 1.0, "f16x3": 3.0}[args.precision]
+    kind = {"fp32": "fp32 CUDA cores", "tf32x3": "tcgen05 kind::tf32, 3xTF32 split", "tf32": "tcgen05 kind::tf32",
+            "f16x3": "tcgen05 kind::f16, fp16 hi/lo split"}[args.precision]
     fam = ["conv5x5 forward/dgrad", "conv5x5 wgrad", "mixture", "small GEMM"]
     fams = {fam[i]: {"ms_per_step": pms[i] / args.steps, "calls_per_step": pn[i] / args.steps,
                      "tflops": (pwork[i] / (pms[i] * 1e-3) / 1e12) if (pms[i] > 0 and i != 2) else None}
@@ -305,19 +311,20 @@ def main():
         "metric": "train_sequences_per_sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split on tcgen05)", "tf32": "tf32",
-                                       "f16x3": "f32 (fp16 hi/lo split fwd/dgrad + 3xTF32 wgrad on tcgen05)"}[args.precision],
+                                       "f16x3": "f32 (fp16 hi/lo operand split on tcgen05, fp32 accumulate)"}[args.precision],
         "data": "synthetic", "config": dict(CONFIG, precision=args.precision),
         "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(B_PER_GPU * T * 3 * D * D + B_PER_GPU * T * 4 * 4), "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": fam[dom] + (" (fp32 CUDA cores)" if args.precision == "fp32" else " (tcgen05 kind::tf32, %s)" % args.precision),
-                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "roofline": {"bound": "tensor", "kernel": "%s (%s)" % (fam[dom], kind),
+                     "achieved": achieved, "peak": mode_peak, "unit": "TFLOP/s", "frac": achieved / mode_peak,
                      "traffic": ncu_traffic(("conv_fwd", "conv_wgrad")[dom], args.precision),
                      "avg_launch_ms": pms[dom] / max(pn[dom], 1),
                      "share_of_step": pms[dom] / ms_total,
-                     "peak_source": "%s bf16_tflops_sustained / 2 (dense TF32)" % which,
-                     # 3xTF32 issues three tensor-core products per algorithmic FLOP: its own ceiling is peak / 3
-                     "frac_of_mode_ceiling": achieved / (tf32_peak / (3.0 if args.precision == "tf32x3" else (1.5 if args.precision == "f16x3" and dom == 0 else (3.0 if args.precision == "f16x3" else 1.0))))},
+                     "peak_source": ("%s bf16_tflops_sustained (dense fp16/bf16)" if args.precision == "f16x3"
+                                     else "%s bf16_tflops_sustained / 2 (dense TF32)") % which,
+                     # the split modes issue three tensor-core products per algorithmic FLOP: their own ceiling is peak / 3
+                     "frac_of_mode_ceiling": achieved / (mode_peak / mode_products)},
         "roofline_mixture": mixture_roofline(model, dev, hbm, which),
         "kernel_families": fams,
     }
