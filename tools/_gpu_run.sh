@@ -1,6 +1,9 @@
-timeout 600 python bench.py > gpurun_out/bench_f16x3_full.json 2> gpurun_out/bench_f16x3_full.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"
-timeout 300 python bench.py --precision tf32x3 --no-cpu-baseline > gpurun_out/bench_tf32x3_final.json 2>/dev/null; echo "rc=$?"
-timeout 300 python bench.py --precision tf32 --no-cpu-baseline > gpurun_out/bench_tf32_final.json 2>/dev/null; echo "rc=$?"
-timeout 300 python bench.py --precision fp32 --no-cpu-baseline > gpurun_out/bench_fp32_final.json 2>/dev/null; echo "rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv5x5_tc_kernel|conv5x5_wgrad_ring_kernel" -s 6 -c 6 -o gpurun_out/prof_r01_f16 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu12.log 2>&1; echo "ncu rc=$?"
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py tests/test_gpu_scaled.py -x -q -m gpu > gpurun_out/t_km.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/t_km.log
+timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_f16.json 2> gpurun_out/b_f16.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+for f in ['gpurun_out/b_f16.json']:
+    j=json.loads(open(f).read().strip().splitlines()[-1])
+    print(j['config']['precision'], j['value'], j['ms_per_step'], {k:round(v['ms_per_step'],2) for k,v in j['kernel_families'].items()}, j['roofline_mixture']['ms_per_call'], j['roofline_mixture']['frac'])
+PY
