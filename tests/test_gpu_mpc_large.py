@@ -35,7 +35,17 @@ def _costs(m, info, cand, noise, goal_image, chunk=None):
     return c[0]
 
 
-def test_mpc_4096_candidates_properties():
+@pytest.fixture(params=["fp32", "f16x3"])
+def precision(request):
+    import op3_b200
+    op3_b200.set_precision(request.param)
+    try:
+        yield request.param
+    finally:
+        op3_b200.set_precision("fp32")
+
+
+def test_mpc_4096_candidates_properties(precision):
     K, Na = 4, 4096
     m, p, info = _setup(K)
     cand = orc.synth_actions(Na, 1, seed=33)[:, :, [0, 1, 3, 4]].cuda()
@@ -63,15 +73,16 @@ def test_mpc_4096_candidates_properties():
     ref_order, ref_sorted = g["order"].astype(np.int64), g["sorted"]
     ours_sorted, ours_order = c1.cpu().numpy()[order.cpu().numpy()], order.cpu().numpy()
     assert ours_order[0] == ref_order[0], "argmin differs from the reference: %d vs %d" % (ours_order[0], ref_order[0])
-    assert np.allclose(ours_sorted, ref_sorted, rtol=2e-5, atol=0)
+    rt = 2e-5 if precision == "fp32" else 1e-4           # the fp16-split tensor-core mode: 2e-5 on images, ~5e-5 on their mse
+    assert np.allclose(ours_sorted, ref_sorted, rtol=rt, atol=0)
     elites = Na // 10                                            # CEM keeps the top 10 % (mpc_pickplace.py:376-410)
     assert set(ours_order[:elites].tolist()) == set(ref_order[:elites].tolist())
     diff = np.nonzero(ours_order != ref_order)[0]
     ours_cost = c1.cpu().numpy()
     for i in diff:
         a, b = ours_cost[ours_order[i]], ours_cost[ref_order[i]]
-        assert abs(a - b) <= 2e-5 * abs(a), "rank %d: candidates %d / %d are not a near tie" % (i, ours_order[i], ref_order[i])
-    print("vs reference: %d of %d ranks differ (all near ties <= 2e-5 rel)" % (len(diff), Na))
+        assert abs(a - b) <= rt * abs(a), "rank %d: candidates %d / %d are not a near tie" % (i, ours_order[i], ref_order[i])
+    print("%s vs reference: %d of %d ranks differ (all near ties <= %.0e rel)" % (precision, len(diff), Na, rt))
     # a small subset against the CPU oracle (same weights, state and noise)
     sub = 16
     st = info["state"]
@@ -84,5 +95,5 @@ def test_mpc_4096_candidates_properties():
     with torch.no_grad():
         o = orc.run_schedule(p, None, cand[:sub].cpu(), [1], [0], [noise[:sub]], K, init_state=state)
     oc = ((goal_image.cpu().view(1, 3, 64, 64) - o["final_recon"]) ** 2).mean((1, 2, 3))
-    assert torch.allclose(c1[:sub].cpu(), oc, rtol=2e-5, atol=1e-8)
+    assert torch.allclose(c1[:sub].cpu(), oc, rtol=2e-5 if precision == "fp32" else 1e-4, atol=1e-8)
     assert torch.equal(torch.argsort(c1[:sub].cpu()), torch.argsort(oc))
