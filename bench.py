@@ -22,7 +22,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SCHEDULE = [0, 0, 0, 0, 1, 1, 1, 1, 0]
 B_PER_GPU, K, T, A, D = 64, 4, 5, 4, 64
@@ -215,18 +214,20 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
 
-    from gpu_util import VARIANT
     from op3_b200 import _lib
     from op3_b200.torch.op3_modules.op3_model import create_model_v2
     from op3_b200.torch.op3_modules.op3_trainer import OP3Trainer, TrainingScheduler
-    from oracle import op3_oracle as orc       # weights only (deterministic synthetic init); not on the timed path
     lib = _lib.load()
     import op3_b200
     op3_b200.set_precision(args.precision)
-    torch.manual_seed(1234 + rank)
-    model = create_model_v2(dict(VARIANT, K=K), 64, 64, A)
-    model.load_state_dict(orc.make_params(A, seed=0, generic=False))
+    # random-init weights of the pickplace architecture (the reference's own initialisers, variants.py / train_op3.py);
+    # the same seed on every rank so that the data-parallel replicas start identical
+    torch.manual_seed(0)
+    variant = dict(refinement_model_type="size_dependent_conv", decoder_model_type="reg", dynamics_model_type="reg_ac32",
+                   sto_repsize=64, det_repsize=64, K=K, extra_args=dict(beta=1e-2, deterministic_sampling=False))
+    model = create_model_v2(variant, 64, 64, A)
     model.to(dev)
+    torch.manual_seed(1234 + rank)
     trainer = OP3Trainer(None, None, model, TrainingScheduler(4, "curriculum", T, T), B_PER_GPU, lr=3e-4)
     sched = np.array(SCHEDULE, dtype=np.float64)
     lw = np.arange(1, len(SCHEDULE) + 1)

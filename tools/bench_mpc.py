@@ -8,22 +8,25 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import op3_b200
 from op3_b200.mpc import Cost
-from gpu_util import build_model
-from oracle import op3_oracle as orc   # only for the synthetic input generators
+from op3_b200.torch.op3_modules.op3_model import create_model_v2
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
 op3_b200.set_precision(prec)
 K, Na = 4, 4096
-m, p = build_model(4, K, seed=7)
+torch.manual_seed(7)
+variant = dict(refinement_model_type="size_dependent_conv", decoder_model_type="reg", dynamics_model_type="reg_ac32",
+               sto_repsize=64, det_repsize=64, K=K, extra_args=dict(beta=1e-2, deterministic_sampling=False))
+m = create_model_v2(variant, 64, 64, 4).cuda()
 m.eval_mode = True
-frames = orc.synth_frames(1, 2, seed=31).cuda()
-acts = orc.synth_actions(1, 2, seed=32)[:, :, [0, 1, 3, 4]].cuda()
+g = torch.Generator().manual_seed(31)
+frames = (torch.randint(0, 256, (1, 2, 3, 64, 64), generator=g, dtype=torch.uint8).float() / 255.0).cuda()
+acts = (torch.rand(1, 2, 4, generator=g) * 2 - 1).cuda()
 info = m.batch_internal_inference(frames, acts, None, np.array([0., 0., 1., 0.]))
-cand = orc.synth_actions(Na, 1, seed=33)[:, :, [0, 1, 3, 4]].cuda()
-goal = orc.synth_frames(1, 1, seed=34)[:, 0].cuda()
+cand = (torch.rand(Na, 1, 4, generator=g) * 2 - 1).cuda()
+goal = (torch.randint(0, 256, (1, 3, 64, 64), generator=g, dtype=torch.uint8).float() / 255.0).cuda()
 cost = Cost(None, core_type="final_recon", aggregate="sum")
 
 
