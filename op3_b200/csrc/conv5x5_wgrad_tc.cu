@@ -852,25 +852,27 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
     for (int ky = 0; ky < 5; ++ky) koff[ky] = (5 * RB_RING - achunks * ky) % RB_RING;
     for (; item < n_items; ++t) {
       const int s = t & 1;
+      const bool real = vb >= item_b0(item);
+      // everything that does not depend on the operands is computed BEFORE the wait, so that the MMAs follow the barrier
+      // immediately: slots of the 5 x 4 K-pair operands (wrapped) and the A descriptor
+      const uint64_t ad = make_smem_desc(smem_u32(a_stage + (size_t)s * RB_A_BYTES), RB_A_ROWS, 8);
+      const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
+      const int c0 = 8 * (t % (RB_RING / 8));              // slot of this block's first G chunk = (8 t) mod 56
+      uint32_t boff[5][HG_CH / 2];
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) {
+        int slot = c0 + koff[ky];
+        if (slot >= RB_RING) slot -= RB_RING;
+#pragma unroll
+        for (int ks = 0; ks < HG_CH / 2; ++ks) {
+          boff[ky][ks] = b_lo0 + (uint32_t)(slot * RB_B_ROWS);                  // 16-byte units
+          slot += 2;
+          if (slot >= RB_RING) slot -= RB_RING;
+        }
+      }
       mbar_wait(&full_bar[s], (t >> 1) & 1);
       tc_fence_after();
-      if (vb >= item_b0(item)) {
-        const uint64_t ad = make_smem_desc(smem_u32(a_stage + (size_t)s * RB_A_BYTES), RB_A_ROWS, 8);
-        const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
-        int c0 = 8 * (t % (RB_RING / 8));                  // slot of this block's first G chunk = (8 t) mod 56
-        // slots of the 5 x 4 K-pair operands first (wrapped), then 40 back-to-back MMAs with precomputed descriptors
-        uint32_t boff[5][HG_CH / 2];
-#pragma unroll
-        for (int ky = 0; ky < 5; ++ky) {
-          int slot = c0 + koff[ky];
-          if (slot >= RB_RING) slot -= RB_RING;
-#pragma unroll
-          for (int ks = 0; ks < HG_CH / 2; ++ks) {
-            boff[ky][ks] = b_lo0 + (uint32_t)(slot * RB_B_ROWS);                // 16-byte units
-            slot += 2;
-            if (slot >= RB_RING) slot -= RB_RING;
-          }
-        }
+      if (real) {
         // consecutive MMAs go to DIFFERENT accumulators (kernel rows): back-to-back MMAs on one accumulator serialise
 #pragma unroll
         for (int ks = 0; ks < HG_CH / 2; ++ks) {

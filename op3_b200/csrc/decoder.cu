@@ -11,32 +11,50 @@ namespace {
 __device__ __forceinline__ int border_class(int v, int D) { return v < 2 ? v : (v >= D - 2 ? 4 - (D - 1 - v) : 2); }
 
 // a1[n][c4][y][x] = ELU(T[n][cls(y,x)*32 + c4*4 ..] + cmap[c4][y][x])
-// maxbits (optional): per-image largest magnitude of a1 for the fp16 conv mode (zeroed by the caller)
+// One thread owns one float4 position of the coordinate map and streams EXP_NG images through it (the position's border
+// class and map value are computed once).  maxbits (optional): per-image largest magnitude of a1 for the fp16 conv mode
+// (zeroed by the caller).
+constexpr int EXP_NG = 8;
 __global__ void __launch_bounds__(256) dec_l1_expand_kernel(const float* __restrict__ T, const float4* __restrict__ cmap,
-                                                            int D, float4* __restrict__ a1, uint32_t* __restrict__ maxbits) {
-  const int n = blockIdx.y;
-  int i = blockIdx.x * 256 + threadIdx.x;  // over 8*D*D
-  float mx = 0.f;
-  if (i < 8 * D * D) {
-    int x = i % D, y = (i / D) % D, c4 = i / (D * D);
-    int cls = border_class(y, D) * 5 + border_class(x, D);
-    float4 t = *reinterpret_cast<const float4*>(T + (size_t)n * (NCLS * 32) + cls * 32 + c4 * 4);
-    float4 m = cmap[i];
-    float4 v = make_float4(elu_f(t.x + m.x), elu_f(t.y + m.y), elu_f(t.z + m.z), elu_f(t.w + m.w));
-    a1[(size_t)n * 8 * D * D + i] = v;
-    mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+                                                            int N, int D, float4* __restrict__ a1, uint32_t* __restrict__ maxbits) {
+  const int n0 = blockIdx.y * EXP_NG;
+  const int i = blockIdx.x * 256 + threadIdx.x;  // over 8*D*D
+  const int tot = 8 * D * D;
+  const bool live = i < tot;
+  __shared__ float s_mx[EXP_NG][8];
+  int cls = 0, c4 = 0;
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const int x = i % D, y = (i / D) % D;
+    c4 = i / (D * D);
+    cls = border_class(y, D) * 5 + border_class(x, D);
+    m = cmap[i];
   }
-  if (maxbits != nullptr) {                                // one atomic per block, and only if it can raise the maximum
-    __shared__ float s_mx[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+  for (int g = 0; g < EXP_NG; ++g) {
+    const int n = n0 + g;
+    float mx = 0.f;
+    if (n >= N) { if ((threadIdx.x & 31) == 0) s_mx[g][threadIdx.x >> 5] = 0.f; continue; }
+    if (live) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(T + (size_t)n * (NCLS * 32) + cls * 32 + c4 * 4));
+      const float4 v = make_float4(elu_f(t.x + m.x), elu_f(t.y + m.y), elu_f(t.z + m.z), elu_f(t.w + m.w));
+      a1[(size_t)n * tot + i] = v;
+      mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (maxbits != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if ((threadIdx.x & 31) == 0) s_mx[g][threadIdx.x >> 5] = mx;
+    }
+  }
+  if (maxbits != nullptr) {                                // one conditional atomic per block and image
     __syncthreads();
-    if (threadIdx.x == 0) {
+    const int g = threadIdx.x;
+    if (g < EXP_NG && n0 + g < N) {
+      float mx = s_mx[g][0];
 #pragma unroll
-      for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_mx[w]);
-      const uint32_t b = __float_as_uint(mx);
-      if (b > __ldcg(&maxbits[n])) atomicMax(&maxbits[n], b);
+      for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_mx[g][w]);
+      if (__float_as_uint(mx) > __ldcg(&maxbits[n0 + g])) atomicMax(&maxbits[n0 + g], __float_as_uint(mx));
     }
   }
 }
@@ -83,21 +101,32 @@ __global__ void __launch_bounds__(256) dec_l1_class_reduce_kernel(const float4* 
   }
 }
 
-// dcmap[i] += sum_n g1[n][i]   (i over 8*D*D float4)
+// dcmap[i] += sum_n g1[n][i]   (i over 8*D*D float4).  A block covers 64 positions; its four 64-thread groups sum a quarter
+// of the images each (4x the blocks and a 4x shorter serial chain), partial sums are added in a fixed order.
 __global__ void __launch_bounds__(256) dec_l1_dcmap_kernel(const float4* __restrict__ g1, int N, int D,
                                                            float4* __restrict__ dcmap) {
-  int i = blockIdx.x * 256 + threadIdx.x;
-  int tot = 8 * D * D;
-  if (i >= tot) return;
+  __shared__ float4 part[3][64];
+  const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int i = blockIdx.x * 64 + t;
+  const int tot = 8 * D * D;
+  const int nq = (N + 3) / 4, nb = grp * nq, ne = min(N, nb + nq);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < tot) {
 #pragma unroll 4
-  for (int n = 0; n < N; ++n) {
-    float4 v = g1[(size_t)n * tot + i];
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    for (int n = nb; n < ne; ++n) {
+      float4 v = g1[(size_t)n * tot + i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
-  float4 o = dcmap[i];
-  o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
-  dcmap[i] = o;
+  if (grp > 0) part[grp - 1][t] = s;
+  __syncthreads();
+  if (grp == 0 && i < tot) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) { float4 p = part[g][t]; s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w; }
+    float4 o = dcmap[i];
+    o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+    dcmap[i] = o;
+  }
 }
 
 struct DecActs {
@@ -147,12 +176,11 @@ extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const
   float* tcs = acts + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) + 4 * (size_t)N * 32 * D * D;   // fp16-mode operand maxima
   // T[n][cls*32+co] = b[co] + sum_c z[n][c] * Wsum[cls*32+co][c]
   OP3_TRY(gemm(st, N, NCLS * 32, R, z, R, 0, prep + L.wsum, R, 1, A.T, NCLS * 32, prep + L.biasT, ACT_NONE, 0));
-  dim3 grid(ceil_div(8 * D * D, 256), N);
   // fp16 mode: slots 1..4 of tcs keep the per-image maxima of a1..a4 (written by their producers, reused by backward)
   const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
   if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
-  dec_l1_expand_kernel<<<grid, 256, 0, st>>>(A.T, reinterpret_cast<const float4*>(prep + L.cmap), D, A.a[0],
-                                             f16 ? tc_slot(tcs, N, 1) : nullptr);
+  dec_l1_expand_kernel<<<dim3(ceil_div(8 * D * D, 256), ceil_div(N, EXP_NG)), 256, 0, st>>>(
+      A.T, reinterpret_cast<const float4*>(prep + L.cmap), N, D, A.a[0], f16 ? tc_slot(tcs, N, 1) : nullptr);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   // layers 2-4 are the implicit-GEMM hot spot (M = N*D*D pixels, N = 32, K = 800); layer 5 has 4 outputs
@@ -217,7 +245,7 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
     // d Wsum[cls*32+co][c] += sum_n dT[n][.] z[n][c] ; d biasT += column sums of dT ; d cmap += sum_n g
     OP3_TRY(gemm(st, NCLS * 32, R, N, dT, NCLS * 32, 1, z, R, 0, pg + L.wsum, R, nullptr, ACT_NONE, 1));
     OP3_TRY(colsum(st, N, NCLS * 32, dT, NCLS * 32, pg + L.biasT, 1));
-    dec_l1_dcmap_kernel<<<ceil_div(8 * D * D, 256), 256, 0, st>>>(g, N, D, reinterpret_cast<float4*>(pg + L.cmap));
+    dec_l1_dcmap_kernel<<<ceil_div(8 * D * D, 64), 256, 0, st>>>(g, N, D, reinterpret_cast<float4*>(pg + L.cmap));
     OP3_COUNT_LAUNCH();
     OP3_LAUNCH_CHECK();
   }

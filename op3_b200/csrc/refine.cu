@@ -125,24 +125,28 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const float4* __restrict__
 }
 
 // g3[n][c4][p] = dpooled[n][c4*4..] / DD * ELU'(r3)
-// maxbits (optional): per-image largest magnitude of g3 for the fp16 conv mode (zeroed by the caller)
+// One thread owns one pixel of one image and streams the channel chunks through it.  maxbits (optional): per-image largest
+// magnitude of g3 for the fp16 conv mode (zeroed by the caller): one conditional atomic per block.
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dpooled, const float4* __restrict__ r3,
                                                           int chunks, int DD, float4* __restrict__ g3,
                                                           uint32_t* __restrict__ maxbits) {
   const int n = blockIdx.y;
-  int i = blockIdx.x * 256 + threadIdx.x;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const float inv = 1.f / (float)DD;
   float mx = 0.f;
-  if (i < chunks * DD) {
-    int c4 = i / DD;
-    float inv = 1.f / (float)DD;
-    float4 d = *reinterpret_cast<const float4*>(dpooled + (size_t)n * chunks * 4 + c4 * 4);
-    float4 a = r3[(size_t)n * chunks * DD + i];
-    float4 v = make_float4(d.x * inv * elu_grad_from_out(a.x), d.y * inv * elu_grad_from_out(a.y),
-                           d.z * inv * elu_grad_from_out(a.z), d.w * inv * elu_grad_from_out(a.w));
-    g3[(size_t)n * chunks * DD + i] = v;
-    mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+  if (p < DD) {
+#pragma unroll 4
+    for (int c4 = 0; c4 < chunks; ++c4) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dpooled + (size_t)n * chunks * 4 + c4 * 4));
+      const size_t o = ((size_t)n * chunks + c4) * DD + p;
+      const float4 a = r3[o];
+      const float4 v = make_float4(d.x * inv * elu_grad_from_out(a.x), d.y * inv * elu_grad_from_out(a.y),
+                                   d.z * inv * elu_grad_from_out(a.z), d.w * inv * elu_grad_from_out(a.w));
+      g3[o] = v;
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
   }
-  if (maxbits != nullptr) {                                // one atomic per block, and only if it can raise the maximum
+  if (maxbits != nullptr) {
     __shared__ float s_mx[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -477,7 +481,7 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
   const float* atcs = ref_acts_tcs(d, io->acts);
   if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
-  avgpool_bwd_kernel<<<dim3(ceil_div(Rs / 4 * DD, 256), N), 256, 0, st>>>(dpool, A.r3, Rs / 4, DD, g3,
+  avgpool_bwd_kernel<<<dim3(ceil_div(DD, 256), N), 256, 0, st>>>(dpool, A.r3, Rs / 4, DD, g3,
                                                                          f16 ? tc_slot(tcs, N, 1) : nullptr);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
