@@ -149,6 +149,10 @@ typedef struct Op3MixtureIO {
   float* mix2;              /* [N][D][D] float4 (LN(x_hat_grad) rgb, 0)                               out */
   float* smp;               /* [B][D][D] float4 (image rgb, LN(pixel likelihood))                     out */
   float* seed;              /* [N][D][D] float4 d total / d dec_out (x_hat_grad rgb, dlogit)          out */
+  unsigned* sync;           /* optional: ONE device word, zero before the first call and left zero by every call, private
+                               to the calling stream.  When given (and the decode of one sample fits the shared memory of
+                               an 8-CTA cluster) the forward is ONE launch: statistics, losses and refinement inputs from
+                               pixels staged once in shared memory.  NULL: statistics + emit kernels (two passes).   */
 } Op3MixtureIO;
 size_t op3_mixture_stats_floats(const Op3Dims* d);
 int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3MixtureIO* io, int want_loss, void* stream);
@@ -246,6 +250,16 @@ size_t op3_get_loss_scratch_floats(const Op3Dims* d);
 int op3_get_loss(const Op3Dims* d, const float* colors, const float* mask, const float* image, const float* post_l1,
                  const float* post_l2, const float* prior_l1, const float* prior_l2, float* color_probs, float* pixel_ll,
                  float* losses, float* scratch, void* stream);
+
+/* CEM refit of the action distribution on the F best candidates (mpc_stack.py:283-288, mpc_pickplace.py:376-389):
+ * mean[j], std[j] = numpy mean / population std (ddof 0) of actions[order[0..F)][j], std += min_std (0.05 in pickplace).
+ * actions [Na][TA] (TA = T*A flattened), order = candidate indices sorted by cost (int64, as torch.sort returns). */
+int op3_cem_refit(int Na, int TA, int F, const float* actions, const long long* order, float min_std, float* mean,
+                  float* std, void* stream);
+/* out[a][j] = clip(mean[j] + std[j]*noise[a][j], lo[j], hi[j]) -- env.sample_multiple_action_gaussian
+ * (op3/envs/blocks/mujoco/block_pick_and_place.py:390-407) with caller-provided standard-normal noise; lo/hi NULL = no clip */
+int op3_cem_resample(int Na, int TA, const float* mean, const float* std, const float* noise, const float* lo,
+                     const float* hi, float* out, void* stream);
 
 /* sub_images[a][k][c] = colors*mask (op3_model.py:612) from planar colours / masks */
 int op3_sub_images(long long n_slots, int D, const float* colors, const float* mask, float* out, void* stream);

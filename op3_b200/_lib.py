@@ -43,7 +43,7 @@ class Op3MixtureIO(C.Structure):
         ("dec_out", c_fp), ("image", c_fp), ("image_bstride", C.c_longlong), ("mse_image", c_fp),
         ("mse_image_bstride", C.c_longlong), ("post_l1", c_fp), ("post_l2", c_fp), ("prior_l1", c_fp),
         ("prior_l2", c_fp), ("mask", c_fp), ("colors", c_fp), ("final_recon", c_fp), ("stats", c_fp), ("losses", c_fp),
-        ("mix1", c_fp), ("mix2", c_fp), ("smp", c_fp), ("seed", c_fp),
+        ("mix1", c_fp), ("mix2", c_fp), ("smp", c_fp), ("seed", c_fp), ("sync", c_fp),
     ]
 
 
@@ -98,6 +98,8 @@ SIGNATURES = {
     "op3_get_loss_scratch_floats": (C.c_size_t, [_P(Op3Dims)]),
     "op3_get_loss": (C.c_int, [_P(Op3Dims), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "op3_sub_images": (C.c_int, [C.c_longlong, C.c_int, c_fp, c_fp, c_fp, c_fp]),
+    "op3_cem_refit": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp, C.c_float, c_fp, c_fp, c_fp]),
+    "op3_cem_resample": (C.c_int, [C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
 }
 
 _lib = None

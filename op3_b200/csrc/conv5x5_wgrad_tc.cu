@@ -311,8 +311,15 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int S,
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int tot = n_w + n_b;
   if (i >= tot) return;
-  float s = 0.f;
-  for (int k = 0; k < S; ++k) s += partial[(size_t)k * tot + i];
+  // fixed summation order (deterministic); four independent chains keep enough loads in flight
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= S; k += 4) {
+    s0 += partial[(size_t)k * tot + i]; s1 += partial[(size_t)(k + 1) * tot + i];
+    s2 += partial[(size_t)(k + 2) * tot + i]; s3 += partial[(size_t)(k + 3) * tot + i];
+  }
+  for (; k < S; ++k) s0 += partial[(size_t)k * tot + i];
+  const float s = (s0 + s1) + (s2 + s3);
   if (i < n_w) dwt[i] += s;
   else if (dbias) dbias[i - n_w] += s;
 }

@@ -7,7 +7,10 @@
 // HBM-bound.  One thread owns one pixel of one sample and keeps its K slot float4s in registers (coalesced 16-byte
 // loads, slot-major planes), LN statistics are reduced warp-shuffle -> smem -> per-tile fp64 partials (fixed order,
 // run-to-run deterministic) with sums centred on the value at pixel 0 to avoid cancellation.
+#include <cooperative_groups.h>
 #include "layout.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace op3 {
 
@@ -15,6 +18,9 @@ namespace {
 
 constexpr int MIX_THREADS = 256;
 constexpr int STATS_PPT = 2;  // pixels per thread in the statistics pass
+constexpr float MIX_INV_2S2 = 1.f / 0.06f;     // 1 / (channels * 2 sigma^2), sigma = 0.1 (op3_model.py:79,126)
+constexpr float MIX_INV_NORM = 1.f / 0.24805f;  // 1 / (sqrt(sigma^6) * 248.05)
+constexpr float MIX_INV_S2 = 1.f / 0.03f;       // d(-S/0.06)/dc = -(c - x)/0.03
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -27,6 +33,7 @@ struct Pixel {
   float P;          // mixture likelihood
   float sp;         // sum_k p_k
   float gP;         // d clog / d P = (-1/B)/(P+1e-12)
+  float rsp;        // 1 / (sum_k p_k + 1e-8)
 
   __device__ __forceinline__ void load(const float* dec, const float* img, int b, int K, int DD, int pix) {
 #pragma unroll
@@ -44,24 +51,26 @@ struct Pixel {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) { m[k] = expf(v[k].w - mx); se += m[k]; }
+    const float rse = 1.f / se;                        // one reciprocal per pixel; products are within 1 ulp of the quotients
     P = 0.f; sp = 0.f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) {
-        m[k] = m[k] / se;
+        m[k] = m[k] * rse;
         float d0 = v[k].x - x0, d1 = v[k].y - x1, d2 = v[k].z - x2;
         float S = d0 * d0 + d1 * d1 + d2 * d2;
-        p[k] = expf(-S / 0.06f) / 0.24805f;          // op3_model.py:126 (ch*2*sigma^2 = 0.06, sqrt(sigma^6)*248.05)
+        p[k] = expf(-S * MIX_INV_2S2) * MIX_INV_NORM;  // op3_model.py:126 (ch*2*sigma^2 = 0.06, sqrt(sigma^6)*248.05)
         P += m[k] * p[k];
         sp += p[k];
       }
     gP = (-invB) / (P + 1e-12f);
+    rsp = 1.f / (sp + 1e-8f);
   }
   __device__ __forceinline__ float mask_grad(int k) const { return gP * p[k]; }
   __device__ __forceinline__ float leave_out(int k) const { return P - m[k] * p[k]; }
-  __device__ __forceinline__ float post_mask(int k) const { return p[k] / (sp + 1e-8f); }
+  __device__ __forceinline__ float post_mask(int k) const { return p[k] * rsp; }
   // x_hat_grad = d clog / d colors = -gP * m * p * (c - x) / 0.03
-  __device__ __forceinline__ float xh_coef(int k) const { return -gP * m[k] * p[k] / 0.03f; }
+  __device__ __forceinline__ float xh_coef(int k) const { return -gP * m[k] * p[k] * MIX_INV_S2; }
 };
 
 // stats buffer layout (in floats; the fp64 regions are 8-byte aligned because every count below is even)
@@ -317,6 +326,281 @@ mix_emit_kernel(Op3MixtureIO io, const float* __restrict__ g0, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Single-launch forward (statistics + losses + refinement inputs) for the sizes whose decode fits in shared memory.
+// One thread-block CLUSTER of MIXF_CL CTAs owns one sample: every CTA stages its DD/MIXF_CL pixels of the K slot planes
+// and of the target frame in shared memory with 1-D bulk copies (one elected thread, one mbarrier), so each input byte
+// crosses HBM exactly once.  Pass 1 reads the staged pixels, writes masks / colours / final_recon and accumulates the
+// LayerNorm2D sums (same warp-centred fp32 -> raw fp64 scheme as mix_stats_kernel); the per-CTA fp64 partials are
+// exchanged through distributed shared memory (fixed rank order => deterministic, every CTA derives identical
+// statistics); pass 2 re-reads the staged pixels from shared memory and writes the normalised refinement inputs and
+// the gradient seed.  The loss scalars are reduced by rank 0 of each cluster; the last sample (self-resetting counter
+// `sync`, zero before the first call, left zero by every call) sums the samples in index order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MIXF_CL = 8;
+constexpr int MIXF_THREADS = 128;
+constexpr int MIXF_WARPS = MIXF_THREADS / 32;
+constexpr int MIXF_NQMAX = 6 * 16 + 4;
+
+constexpr int MIXF_MAXIT = 16;          // pixels per thread (= staging sub-chunks, one mbarrier each)
+struct MixfSmem {                       // fixed part of the dynamic shared memory; the pixel staging area follows
+  unsigned long long mbar[MIXF_MAXIT];
+  double part[MIXF_NQMAX];              // this CTA's raw fp64 sums (read by the other CTAs of the cluster)
+  double red[MIXF_WARPS][MIXF_NQMAX];
+  float2 ln[3 * 16 + 1];
+  int last;
+};
+__host__ __device__ inline size_t mixf_stage_offset() { return (sizeof(MixfSmem) + 127) & ~(size_t)127; }
+// staging per pixel: K float4 (r,g,b,logit -> mask after pass 1) + 3 floats of the target + K floats of p_k
+__host__ __device__ inline size_t mixf_smem_bytes(int K, int px) { return mixf_stage_offset() + (size_t)px * (20 * K + 12); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int KMAX>
+__global__ void __cluster_dims__(MIXF_CL, 1, 1) __launch_bounds__(MIXF_THREADS)
+mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long mse_bstride,
+                 const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ g2,
+                 const float* __restrict__ g3, const float* __restrict__ b0, const float* __restrict__ b1,
+                 const float* __restrict__ b2, const float* __restrict__ b3, int B, int K, int D, int emit, int Rs,
+                 float beta, unsigned* __restrict__ sync) {
+  extern __shared__ __align__(128) unsigned char mixf_raw[];
+  MixfSmem& sm = *reinterpret_cast<MixfSmem*>(mixf_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int DD = D * D, PX = DD / MIXF_CL;
+  const int b = blockIdx.y, rank = blockIdx.x;                 // cluster = the MIXF_CL CTAs of one sample
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+  const int pix0 = rank * PX;
+  const float invB = 1.f / (float)B;
+  const int nq = 6 * K + 4;
+  StatsLayout L = stats_layout(B, K, D);
+  float4* s_dec = reinterpret_cast<float4*>(mixf_raw + mixf_stage_offset());          // [K][PX]
+  float* s_img = reinterpret_cast<float*>(s_dec + (size_t)K * PX);                    // [3][PX]
+
+  float* s_p = s_img + 3 * PX;                                                        // [K][PX]
+  const int npix = PX / MIXF_THREADS;
+  if (tid == 0) {
+    for (int it = 0; it < npix; ++it) mbar_init(reinterpret_cast<uint64_t*>(&sm.mbar[it]), 1);
+    fence_mbar_init();
+    // one sub-chunk of MIXF_THREADS pixels per pass-1 iteration: compute starts when the first 1/npix of the bytes landed
+    const uint32_t sub = (uint32_t)MIXF_THREADS * (16u * K + 12u);
+    const float* img = io.image + (size_t)b * io.image_bstride + pix0;
+    for (int it = 0; it < npix; ++it) {
+      unsigned long long* bar = &sm.mbar[it];
+      const int o = it * MIXF_THREADS;
+      asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
+                   :: "r"(smem_u32(bar)), "r"(sub) : "memory");
+      for (int c = 0; c < 3; ++c) bulk_g2s(s_img + c * PX + o, img + (size_t)c * DD + o, MIXF_THREADS * 4, bar);
+      for (int k = 0; k < K; ++k)
+        bulk_g2s(s_dec + (size_t)k * PX + o, io.dec_out + ((size_t)(b * K + k) * DD + pix0 + o) * 4, MIXF_THREADS * 16, bar);
+    }
+  }
+  // KL of this sample (rank 0 only) while the copies are in flight
+  double kl = 0.0;
+  if (rank == 0) {
+    for (int i = tid; i < K * Rs; i += MIXF_THREADS) {
+      size_t o = (size_t)b * K * Rs + i;
+      float sq_ = softplus_std(io.post_l2[o]), spv = softplus_std(io.prior_l2[o]);
+      float dm = io.post_l1[o] - io.prior_l1[o];
+      kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
+    }
+    kl = warp_sum_d(kl);
+  }
+  __syncthreads();                                             // mbarriers initialised before anyone polls them
+
+  // ---------------- pass 1: outputs + statistics
+  Pixel<KMAX> px;
+  float acc[6 * KMAX], shift[3 * KMAX];
+  float accP = 0.f, accP2 = 0.f, shiftP = 0.f, accLog = 0.f, accSq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6 * KMAX; ++i) acc[i] = 0.f;
+#pragma unroll 1
+  for (int it = 0; it < npix; ++it) {
+    const int lp = it * MIXF_THREADS + tid, pix = pix0 + lp;
+    mbar_wait(reinterpret_cast<uint64_t*>(&sm.mbar[it]), 0);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) px.v[k] = s_dec[(size_t)k * PX + lp];
+    px.x0 = s_img[lp]; px.x1 = s_img[PX + lp]; px.x2 = s_img[2 * PX + lp];
+    px.compute(K, invB);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        if (emit) {                                              // pass 2 reuses the mask and the colour likelihood
+          reinterpret_cast<float*>(s_dec + (size_t)k * PX + lp)[3] = px.m[k];
+          s_p[(size_t)k * PX + lp] = px.p[k];
+        }
+        if (io.mask) io.mask[(size_t)(b * K + k) * DD + pix] = px.m[k];
+        if (io.colors) {
+          float* c = io.colors + (size_t)(b * K + k) * 3 * DD + pix;
+          c[0] = px.v[k].x; c[DD] = px.v[k].y; c[2 * DD] = px.v[k].z;
+        }
+        r0 += px.v[k].x * px.m[k]; r1 += px.v[k].y * px.m[k]; r2 += px.v[k].z * px.m[k];
+        if (emit) {
+          float mg = px.mask_grad(k), lo = px.leave_out(k), cf = px.xh_coef(k);
+          float x0 = cf * (px.v[k].x - px.x0), x1 = cf * (px.v[k].y - px.x1), x2 = cf * (px.v[k].z - px.x2);
+          if (it == 0) {
+            shift[3 * k] = __shfl_sync(0xffffffffu, mg, 0);
+            shift[3 * k + 1] = __shfl_sync(0xffffffffu, lo, 0);
+            shift[3 * k + 2] = __shfl_sync(0xffffffffu, x0, 0);
+          }
+          float d = mg - shift[3 * k];
+          acc[6 * k] += d; acc[6 * k + 1] += d * d;
+          d = lo - shift[3 * k + 1];
+          acc[6 * k + 2] += d; acc[6 * k + 3] += d * d;
+          float sh = shift[3 * k + 2];
+          float e0 = x0 - sh, e1 = x1 - sh, e2 = x2 - sh;
+          acc[6 * k + 4] += e0 + e1 + e2; acc[6 * k + 5] += e0 * e0 + e1 * e1 + e2 * e2;
+        }
+      }
+    if (io.final_recon) {
+      float* fr = io.final_recon + (size_t)b * 3 * DD + pix;
+      fr[0] = r0; fr[DD] = r1; fr[2 * DD] = r2;
+    }
+    if (emit) {
+      if (it == 0) shiftP = __shfl_sync(0xffffffffu, px.P, 0);
+      float d = px.P - shiftP;
+      accP += d; accP2 += d * d;
+    }
+    accLog += -logf(px.P + 1e-12f);
+    if (mse_image) {
+      const float* mi = mse_image + (size_t)b * mse_bstride;
+      float q0 = r0 - __ldg(mi + pix), q1 = r1 - __ldg(mi + DD + pix), q2 = r2 - __ldg(mi + 2 * DD + pix);
+      accSq += q0 * q0 + q1 * q1 + q2 * q2;
+    }
+  }
+  const double n1 = 32.0 * npix, n3 = 96.0 * npix;
+  if (emit) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float S1 = warp_sum(acc[6 * k + 2 * g]), S2 = warp_sum(acc[6 * k + 2 * g + 1]);
+          if (lane == 0) {
+            double sft = (double)shift[3 * k + g], nn = g == 2 ? n3 : n1;
+            sm.red[warp][6 * k + 2 * g] = (double)S1 + nn * sft;
+            sm.red[warp][6 * k + 2 * g + 1] = (double)S2 + 2.0 * sft * (double)S1 + nn * sft * sft;
+          }
+        }
+      }
+  }
+  {
+    float S1 = warp_sum(accP), S2 = warp_sum(accP2), S3 = warp_sum(accLog), S4 = warp_sum(accSq);
+    if (lane == 0) {
+      double sft = (double)shiftP;
+      sm.red[warp][6 * K] = (double)S1 + n1 * sft;
+      sm.red[warp][6 * K + 1] = (double)S2 + 2.0 * sft * (double)S1 + n1 * sft * sft;
+      sm.red[warp][6 * K + 2] = (double)S3;
+      sm.red[warp][6 * K + 3] = (double)S4;
+    }
+  }
+  __syncthreads();
+  if (tid < nq && (emit || tid >= 6 * K)) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < MIXF_WARPS; ++w) s += sm.red[w][tid];
+    sm.part[tid] = s;
+  }
+  cluster.sync();                                              // every CTA's partials are visible cluster-wide
+
+  // ---------------- cluster-wide statistics (fixed rank order), loss scalars
+  if (emit && tid < 3 * K + 1) {
+    const int q = tid, k = q / 3, g = q % 3;
+    const int qi = q == 3 * K ? 6 * K : 6 * k + 2 * g;
+    double s = 0.0, s2 = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < MIXF_CL; ++r) {
+      const double* rp = cluster.map_shared_rank(sm.part, r);
+      s += rp[qi]; s2 += rp[qi + 1];
+    }
+    const double n = (q != 3 * K && g == 2) ? 3.0 * DD : (double)DD;
+    const double mean = s / n;
+    double var = (s2 - s * s / n) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    const float2 st = make_float2((float)mean, 1.f / ((float)sqrt(var) + 1e-5f));
+    sm.ln[q] = st;
+    if (rank == 0) {                                           // kept for the backward pass
+      size_t o = q == 3 * K ? L.ln + (size_t)B * K * 6 + (size_t)b * 2 : L.ln + ((size_t)(b * K + k) * 3 + g) * 2;
+      io.stats[o] = st.x; io.stats[o + 1] = st.y;
+    }
+  }
+  if (rank == 0) {
+    if (lane == 0) sm.red[warp][0] = kl;                       // red[][] is free again (all reads precede cluster.sync)
+    __syncthreads();
+    if (tid == 0) {
+      double klv = 0.0, cl = 0.0, sq = 0.0;
+#pragma unroll
+      for (int w = 0; w < MIXF_WARPS; ++w) klv += sm.red[w][0];
+#pragma unroll 1
+      for (int r = 0; r < MIXF_CL; ++r) {
+        const double* rp = cluster.map_shared_rank(sm.part, r);
+        cl += rp[6 * K + 2]; sq += rp[6 * K + 3];
+      }
+      double* samp = reinterpret_cast<double*>(io.stats + L.sample);
+      samp[b * 3] = cl; samp[b * 3 + 1] = klv; samp[b * 3 + 2] = sq;
+      __threadfence();
+      if (atomicAdd(sync, 1u) == (unsigned)B - 1) {
+        __threadfence();
+        cl = 0.0; klv = 0.0; sq = 0.0;
+        for (int i = 0; i < B; ++i) { cl += __ldcg(samp + i * 3); klv += __ldcg(samp + i * 3 + 1); sq += __ldcg(samp + i * 3 + 2); }
+        const float clog = (float)(cl / B), klf = (float)(klv / B);
+        io.losses[0] = clog;
+        io.losses[1] = klf;
+        io.losses[2] = clog + beta * klf;
+        io.losses[3] = mse_image ? (float)(sq / ((double)B * 3.0 * D * D)) : 0.f;
+        *sync = 0u;                                            // ready for the next call on this stream
+      }
+    }
+  }
+  cluster.barrier_arrive();                                    // this CTA no longer reads remote shared memory
+  if (emit) {
+    __syncthreads();                                           // sm.ln
+    // ---------------- pass 2: refinement inputs + gradient seed from the staged pixels
+    const float ga0 = __ldg(g0), be0 = __ldg(b0), ga1 = __ldg(g1), be1 = __ldg(b1), ga2 = __ldg(g2), be2 = __ldg(b2);
+    const float ga3x = __ldg(g3), ga3y = __ldg(g3 + 1), ga3z = __ldg(g3 + 2);
+    const float be3x = __ldg(b3), be3y = __ldg(b3 + 1), be3z = __ldg(b3 + 2);
+    const float2 lP = sm.ln[3 * K];
+#pragma unroll 1
+    for (int it = 0; it < npix; ++it) {
+      const int lp = it * MIXF_THREADS + tid, pix = pix0 + lp;
+      const float x0 = s_img[lp], x1 = s_img[PX + lp], x2 = s_img[2 * PX + lp];
+      float4 v[KMAX];                                            // (r, g, b, mask)
+      float pk[KMAX];
+      float P = 0.f, sp = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+          v[k] = s_dec[(size_t)k * PX + lp];
+          pk[k] = s_p[(size_t)k * PX + lp];
+          P += v[k].w * pk[k];
+          sp += pk[k];
+        }
+      const float gP = (-invB) / (P + 1e-12f), rsp = 1.f / (sp + 1e-8f);
+      const float gPP = gP * P;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+          const float2 l0 = sm.ln[3 * k], l1 = sm.ln[3 * k + 1], l2 = sm.ln[3 * k + 2];
+          const size_t o = ((size_t)(b * K + k) * DD + pix);
+          const float mk = v[k].w, mp = mk * pk[k];
+          const float mg = gP * pk[k], lo = P - mp, cf = -gP * mk * pk[k] * MIX_INV_S2;
+          const float xh0 = cf * (v[k].x - x0), xh1 = cf * (v[k].y - x1), xh2 = cf * (v[k].z - x2);
+          reinterpret_cast<float4*>(io.mix1)[o] =
+              make_float4(mk, pk[k] * rsp, (mg - l0.x) * l0.y * ga0 + be0, (lo - l1.x) * l1.y * ga2 + be2);
+          reinterpret_cast<float4*>(io.mix2)[o] = make_float4((xh0 - l2.x) * l2.y * ga3x + be3x, (xh1 - l2.x) * l2.y * ga3y + be3y,
+                                                              (xh2 - l2.x) * l2.y * ga3z + be3z, 0.f);
+          if (io.seed) reinterpret_cast<float4*>(io.seed)[o] = make_float4(xh0, xh1, xh2, mk * (mg - gPP));
+        }
+      reinterpret_cast<float4*>(io.smp)[(size_t)b * DD + pix] = make_float4(x0, x1, x2, (P - lP.x) * lP.y * ga1 + be1);
+    }
+  }
+  cluster.barrier_wait();                                      // nobody exits while a peer may still read its partials
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // backward w.r.t. dec_out (+ LayerNorm2D gamma/beta gradient partials)
 // ---------------------------------------------------------------------------------------------------------
 template <int KMAX>
@@ -338,7 +622,6 @@ mix_bwd_kernel(Op3MixtureIO io, float w_clog, const float4* __restrict__ d_in, f
     Pixel<KMAX> px;
     px.load(io.dec_out, img, b, K, DD, pix);
     px.compute(K, invB);
-    const float Sp = px.sp + 1e-8f;
     float gm[KMAX], dpm[KMAX];
     float4 u0[KMAX];
     float sum_mg = 0.f, sum_dpm_p = 0.f;
@@ -368,8 +651,8 @@ mix_bwd_kernel(Op3MixtureIO io, float w_clog, const float4* __restrict__ d_in, f
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) {
-        float dp = dpm[k] / Sp - sum_dpm_p / (Sp * Sp);        // through posterior_mask = p/(sum p + 1e-8)
-        float cc = w_clog * px.xh_coef(k) - dp * px.p[k] / 0.03f;
+        float dp = (dpm[k] - sum_dpm_p * px.rsp) * px.rsp;     // through posterior_mask = p/(sum p + 1e-8)
+        float cc = w_clog * px.xh_coef(k) - dp * px.p[k] * MIX_INV_S2;
         float4 o;
         o.x = u0[k].x + cc * (px.v[k].x - px.x0);
         o.y = u0[k].y + cc * (px.v[k].y - px.x1);
@@ -536,6 +819,32 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
   StatsLayout L = stats_layout(B, K, D);
   // algorithmic bytes: full forward (11K+4)*4 per pixel-sample, outputs-only (8K+3... see DESIGN.md)
   ProfScope prof(st, KID_MIXTURE, (emit ? (11.0 * K + 4) : (8.0 * K + 6)) * 4.0 * B * D * D);
+  // single-launch cluster kernel whenever one sample's decode fits the shared memory of MIXF_CL CTAs
+  const int DD = D * D, PX = DD / MIXF_CL;
+  const size_t fused_smem = mixf_smem_bytes(K, PX);
+  if (want_stats && io->sync && DD % (MIXF_CL * MIXF_THREADS) == 0 && PX / MIXF_THREADS <= MIXF_MAXIT && fused_smem <= 200 * 1024 &&
+      ((uintptr_t)io->image & 15) == 0 && (io->image_bstride & 3) == 0 && ((uintptr_t)io->dec_out & 15) == 0) {
+    dim3 gf(MIXF_CL, B);
+    const float* nul = nullptr;
+#define OP3_MIX_FUSED(KM)                                                                                              \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      OP3_CHECK(cudaFuncSetAttribute(mix_fused_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    mix_fused_kernel<KM><<<gf, MIXF_THREADS, fused_smem, st>>>(                                                        \
+        *io, io->mse_image, io->mse_image_bstride, emit ? p->ln2d_gamma[0] : nul, emit ? p->ln2d_gamma[1] : nul,       \
+        emit ? p->ln2d_gamma[2] : nul, emit ? p->ln2d_gamma[3] : nul, emit ? p->ln2d_beta[0] : nul,                    \
+        emit ? p->ln2d_beta[1] : nul, emit ? p->ln2d_beta[2] : nul, emit ? p->ln2d_beta[3] : nul, B, K, D,             \
+        emit ? 1 : 0, d->Rs, d->beta, io->sync);                                                                       \
+  } while (0)
+    if (K <= 4) OP3_MIX_FUSED(4); else if (K <= 8) OP3_MIX_FUSED(8); else OP3_MIX_FUSED(16);
+#undef OP3_MIX_FUSED
+    OP3_COUNT_LAUNCH();
+    OP3_LAUNCH_CHECK();
+    return OP3_OK;
+  }
   dim3 gs(L.tiles, B);
   if (want_stats) OP3_CHECK(cudaMemsetAsync(io->stats + L.counter, 0, (size_t)(B + 1) * sizeof(unsigned), st));
 #define OP3_MIX_STATS(KM) \

@@ -110,10 +110,59 @@ __global__ void sub_images_kernel(long long n_slots, int DD, const float* __rest
   out[i] = colors[i] * mask[s * DD + pix];
 }
 
+// CEM refit: one thread per action coordinate walks the F elite rows in rank order (fp64, fixed order => the refit is
+// bit-reproducible and identical on every rank of a sharded rollout).
+__global__ void cem_refit_kernel(int TA, int F, const float* __restrict__ actions, const long long* __restrict__ order,
+                                 float min_std, float* __restrict__ mean, float* __restrict__ stdv) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= TA) return;
+  double s = 0.0;
+  for (int f = 0; f < F; ++f) s += (double)actions[(size_t)order[f] * TA + j];
+  const double m = s / F;
+  double v = 0.0;
+  for (int f = 0; f < F; ++f) {
+    const double dlt = (double)actions[(size_t)order[f] * TA + j] - m;
+    v += dlt * dlt;
+  }
+  mean[j] = (float)m;
+  stdv[j] = (float)(sqrt(v / F) + (double)min_std);          // numpy .std(): population std (ddof = 0)
+}
+
+__global__ void cem_resample_kernel(long long n, int TA, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                    const float* __restrict__ noise, const float* __restrict__ lo,
+                                    const float* __restrict__ hi, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = (int)(i % TA);
+  float v = fmaf(stdv[j], noise[i], mean[j]);
+  if (lo) v = fmaxf(v, lo[j]);
+  if (hi) v = fminf(v, hi[j]);
+  out[i] = v;
+}
+
 }  // namespace
 }  // namespace op3
 
 using namespace op3;
+
+extern "C" int op3_cem_refit(int Na, int TA, int F, const float* actions, const long long* order, float min_std,
+                             float* mean, float* stdv, void* stream) {
+  OP3_REQUIRE(Na > 0 && TA > 0 && F > 0 && F <= Na && actions && order && mean && stdv, "op3_cem_refit: bad argument");
+  cem_refit_kernel<<<ceil_div(TA, 64), 64, 0, (cudaStream_t)stream>>>(TA, F, actions, order, min_std, mean, stdv);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+extern "C" int op3_cem_resample(int Na, int TA, const float* mean, const float* stdv, const float* noise, const float* lo,
+                                const float* hi, float* out, void* stream) {
+  OP3_REQUIRE(Na > 0 && TA > 0 && mean && stdv && noise && out, "op3_cem_resample: bad argument");
+  const long long n = (long long)Na * TA;
+  cem_resample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, TA, mean, stdv, noise, lo, hi, out);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
 
 extern "C" int op3_adam_clip(long long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step,
                              float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale,

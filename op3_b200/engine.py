@@ -125,6 +125,7 @@ class Engine:
         self._prep = None
         self._prep_key = None
         self.manual_version = 0         # bumped by the fused optimizer (writes through raw pointers)
+        self._mix_sync = {}             # (device, stream) -> zeroed device word of the single-launch mixture forward
         self.last_flat_grad = None
 
     # ------------------------------------------------------------------ parameters
@@ -171,6 +172,14 @@ class Engine:
                 raise RuntimeError("op3_b200: unexpected parameter %r (only the shared-weight 'reg' networks are built)" % name)
             _set_field(s, fmap[name], base + 4 * off)
         return s
+
+    def mix_sync(self, dev, stream):
+        """The self-resetting 'samples done' word of op3_mixture_fwd's single-launch path (Op3MixtureIO.sync)."""
+        key = (dev.index, stream)
+        t = self._mix_sync.get(key)
+        if t is None:
+            t = self._mix_sync[key] = torch.zeros(4, device=dev, dtype=torch.int32)
+        return t
 
     def dims(self, B):
         m = self.model
@@ -290,6 +299,7 @@ class Engine:
         final_recon = torch.empty(B, 3, D, D, **f32)
         loss_rows = torch.zeros(max(T1, 1), 4, **f32)
 
+        mix_sync = self.mix_sync(dev, st)
         n_dec_acts = lib.op3_decoder_acts_floats(C.byref(d), N)
         n_stats = lib.op3_mixture_stats_floats(C.byref(d))
         n_ref_acts = lib.op3_refine_acts_floats(C.byref(d))
@@ -325,6 +335,7 @@ class Engine:
                 stats = torch.empty(n_stats, **f32)
                 rec.losses = loss_rows[t_index] if t_index is not None else torch.empty(4, **f32)
                 io.stats, io.losses = ptr(stats), rec.losses.data_ptr()
+                io.sync = mix_sync.data_ptr()
                 keep += [stats, rec.losses]
             if refine_after:
                 mix1 = torch.empty(N, DD, 4, **f32)

@@ -47,3 +47,65 @@ class Cost:
         min_costs, goal_idx = costs.min(0)
         sorted_costs, order = min_costs.sort()
         return sorted_costs.cpu().numpy(), order.cpu().numpy(), goal_idx.cpu().numpy()
+
+
+def cem_refit(actions, order, n_elite, min_std=0.0):
+    """Mean and (population) std of the `n_elite` best candidates, on the device (the reference does this in numpy on
+    the host after a D2H copy: mpc_stack.py:283-288 with min_std 0, mpc_pickplace.py:376-381 with min_std 0.05).
+    actions (Na, ...) float32 cuda, order (>= n_elite,) int64 candidate indices sorted by cost."""
+    lib = _lib.load()
+    a = actions.detach().contiguous().float()
+    if a.device.type != "cuda":
+        raise RuntimeError("op3_b200: cem_refit needs CUDA tensors (no CPU fallback)")
+    Na, TA = a.shape[0], a[0].numel()
+    order = order.to(device=a.device, dtype=torch.int64).contiguous()
+    if not 0 < n_elite <= min(Na, order.numel()):
+        raise ValueError("n_elite=%d out of range for %d candidates" % (n_elite, Na))
+    mean = torch.empty(a.shape[1:], device=a.device)
+    std = torch.empty(a.shape[1:], device=a.device)
+    st = torch.cuda.current_stream(a.device).cuda_stream
+    check(lib.op3_cem_refit(Na, TA, int(n_elite), ptr(a), ptr(order), float(min_std), ptr(mean), ptr(std), st), "op3_cem_refit")
+    return mean, std
+
+
+def cem_resample(mean, std, noise, low=None, high=None):
+    """actions = clip(mean + std * noise, low, high): env.sample_multiple_action_gaussian
+    (op3/envs/blocks/mujoco/block_pick_and_place.py:390-407) with the standard-normal `noise` (Na, *mean.shape) supplied
+    by the caller (same noise on every rank => identical candidates without a broadcast)."""
+    lib = _lib.load()
+    noise = noise.detach().contiguous().float()
+    if noise.device.type != "cuda":
+        raise RuntimeError("op3_b200: cem_resample needs CUDA tensors (no CPU fallback)")
+    Na, TA = noise.shape[0], mean.numel()
+    if tuple(noise.shape[1:]) != tuple(mean.shape) or tuple(std.shape) != tuple(mean.shape):
+        raise ValueError("noise %s does not match mean %s / std %s" % (tuple(noise.shape), tuple(mean.shape), tuple(std.shape)))
+    dev = noise.device
+    as_vec = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32, device=dev).expand(mean.shape).contiguous()
+    lo, hi = as_vec(low), as_vec(high)
+    out = torch.empty_like(noise)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    check(lib.op3_cem_resample(Na, TA, ptr(mean.contiguous().float()), ptr(std.contiguous().float()), ptr(noise), ptr(lo),
+                               ptr(hi), ptr(out), st), "op3_cem_resample")
+    return out
+
+
+def cem_plan(model, cost, goal_info, initial_hidden_state, actions, cem_steps, noise_fn, low=None, high=None,
+             elite_frac=0.1, min_std=0.05, schedule=None):
+    """Device-resident CEM loop of Stage3_CEM._cem (mpc_pickplace.py:362-374, action_type None): roll the candidate
+    action sequences out through dynamics + decoder, rank them with `cost`, refit a Gaussian on the best 10 % and
+    resample -- candidates, costs, ranking and refit stay on the GPU; with torch.distributed initialised the candidate
+    set is sharded across ranks (op3_b200.parallel.sharded_rollout_costs) and every rank refits the same distribution.
+    actions (Na,T,A) initial candidates (identical on every rank); noise_fn(step) -> (Na,T,A) standard-normal noise
+    (identical on every rank).  Returns (best action sequence (T,A), its cost, final candidates, final order)."""
+    from op3_b200 import parallel as par
+    Na, T = actions.shape[0], actions.shape[1]
+    schedule = [1] * T if schedule is None else schedule
+    n_elite = int(Na * elite_frac)
+    best, best_cost, order = None, None, None
+    for i in range(cem_steps):
+        sorted_costs, order = par.sharded_rollout_costs(model, cost, goal_info, actions, initial_hidden_state, schedule)
+        best, best_cost = actions[order[0]].clone(), sorted_costs[0]
+        if i + 1 < cem_steps:
+            mean, std = cem_refit(actions, order, n_elite, min_std)
+            actions = cem_resample(mean, std, noise_fn(i), low, high)
+    return best, best_cost, actions, order

@@ -156,11 +156,14 @@ def test_dynamics_backward_matches_autograd():
         compare_grads(views, ref, tn, 5e-5)
 
 
-def test_mixture_forward_pieces_match_oracle():
-    """masks, losses, LayerNorm'd refinement inputs and the gradient seed of one decode."""
+@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_launch"])
+def test_mixture_forward_pieces_match_oracle(fused):
+    """masks, losses, LayerNorm'd refinement inputs and the gradient seed of one decode, through the two-pass kernels
+    (Op3MixtureIO.sync = NULL) and through the single-launch cluster kernel (sync word given)."""
     lib = _lib().load()
     from op3_b200._lib import check, ptr, Op3MixtureIO
-    for K, B in ((3, 2), (7, 2), (11, 1)):
+    sync = torch.zeros(4, device="cuda", dtype=torch.int32)
+    for K, B in ((3, 2), (4, 5), (7, 2), (11, 1)):
         m, p = build_model(0, K, seed=2)
         eng = m.engine
         N, D, Rs = B * K, 64, 64
@@ -199,8 +202,20 @@ def test_mixture_forward_pieces_match_oracle():
         io.mask, io.colors, io.final_recon = ptr(keep["mask"]), ptr(keep["colors"]), ptr(keep["recon"])
         io.stats, io.losses = ptr(keep["stats"]), ptr(keep["losses"])
         io.mix1, io.mix2, io.smp, io.seed = ptr(keep["mix1"]), ptr(keep["mix2"]), ptr(keep["smp"]), ptr(keep["seed"])
+        if fused:
+            io.sync = ptr(sync)
+            # loss-only call first (no refinement inputs): same scalars, and the sync word must come back to zero
+            io2 = Op3MixtureIO.from_buffer_copy(io)
+            io2.mix1 = io2.mix2 = io2.smp = io2.seed = None
+            l2 = torch.zeros(4, device="cuda")
+            io2.losses = ptr(l2)
+            check(lib.op3_mixture_fwd(C.byref(d), C.byref(ps), C.byref(io2), 1, st))
+            assert int(sync[0].item()) == 0
         check(lib.op3_mixture_fwd(C.byref(d), C.byref(ps), C.byref(io), 1, st))
         L = keep["losses"].cpu()
+        if fused:
+            assert int(sync[0].item()) == 0
+            assert torch.equal(l2.cpu(), L), (l2, L)
         assert abs(L[0] - clog.item()) <= 2e-6 * abs(clog.item()), (L, clog)
         assert abs(L[1] - kl.item()) <= 1e-5 * abs(kl.item())
         assert abs(L[2] - total.item()) <= 2e-6 * abs(total.item())
@@ -244,3 +259,33 @@ def test_mpc_cost_kernel_matches_oracle_ranking():
         # bit-reproducible run to run
         s3, o3, _ = c.get_action_rankings(None, goal.cuda(), gimg.cuda(), None, pred.cuda(), final.cuda(), plot_actions=0)
         assert np.array_equal(s2, s3) and np.array_equal(o2, o3)
+
+
+def test_cem_refit_and_resample_match_numpy():
+    """CEM refit (mpc_pickplace.py:376-381: mean, population std + 0.05 of the best 10 %) and the clipped Gaussian
+    resampling (block_pick_and_place.py:390-399) against the reference's numpy formulas on the same numbers."""
+    from op3_b200.mpc import cem_refit, cem_resample
+    rng = np.random.RandomState(0)
+    for Na, T, A, min_std in ((4096, 1, 4, 0.05), (500, 3, 4, 0.05), (30, 1, 6, 0.0)):
+        acts = rng.uniform(-2.5, 4.0, size=(Na, T, A)).astype(np.float32)
+        costs = rng.rand(Na).astype(np.float32)
+        order = np.argsort(costs, kind="stable")
+        F = max(int(Na * 0.1), 1)
+        best = acts[order][:F].astype(np.float64)
+        mean_ref, std_ref = best.mean(0), best.std(0) + min_std
+        mean, std = cem_refit(torch.from_numpy(acts).cuda(), torch.from_numpy(order).cuda(), F, min_std)
+        assert mean.shape == (T, A) and std.shape == (T, A)
+        assert np.allclose(mean.cpu().numpy(), mean_ref, rtol=1e-6, atol=1e-7)
+        assert np.allclose(std.cpu().numpy(), std_ref, rtol=1e-6, atol=1e-7)
+        noise = rng.randn(Na, T, A).astype(np.float32)
+        lo = np.array([-2.5, 1.0, -2.5, 1.0] + [0.0] * (A - 4), dtype=np.float32)
+        hi = np.array([2.5, 4.0, 2.5, 4.0] + [9.0] * (A - 4), dtype=np.float32)
+        out = cem_resample(mean, std, torch.from_numpy(noise).cuda(), torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda())
+        ref = np.clip(mean.cpu().numpy()[None] + std.cpu().numpy()[None] * noise, lo, hi)
+        assert np.allclose(out.cpu().numpy(), ref, rtol=1e-6, atol=1e-6)
+        assert out.min().item() >= -2.5 and out.max().item() <= 9.0
+        # bit-reproducible
+        mean2, std2 = cem_refit(torch.from_numpy(acts).cuda(), torch.from_numpy(order).cuda(), F, min_std)
+        assert torch.equal(mean, mean2) and torch.equal(std, std2)
+    with pytest.raises(ValueError):
+        cem_refit(torch.zeros(8, 1, 4, device="cuda"), torch.arange(8, device="cuda"), 9)

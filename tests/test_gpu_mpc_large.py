@@ -97,3 +97,42 @@ def test_mpc_4096_candidates_properties(precision):
     oc = ((goal_image.cpu().view(1, 3, 64, 64) - o["final_recon"]) ** 2).mean((1, 2, 3))
     assert torch.allclose(c1[:sub].cpu(), oc, rtol=2e-5 if precision == "fp32" else 1e-4, atol=1e-8)
     assert torch.equal(torch.argsort(c1[:sub].cpu()), torch.argsort(oc))
+
+
+def test_cem_plan_device_loop():
+    """Device-resident CEM (Stage3_CEM._cem, mpc_pickplace.py:362-374): candidates, costs, ranking, refit and resampling
+    stay on the GPU.  Checks: step 0 ranks exactly like a direct rollout + Cost, the refit equals the numpy formula on
+    the ranked candidates, the loop is bit-reproducible, and the best cost never gets worse than step 0's."""
+    from op3_b200.mpc import cem_plan, cem_refit
+    K, Na, steps = 4, 256, 3
+    m, p, info = _setup(K)
+    m.inference_chunk = 128
+    cand = orc.synth_actions(Na, 1, seed=35)[:, :, [0, 1, 3, 4]].cuda()
+    goal_image = orc.synth_frames(1, 1, seed=34)[:, 0].cuda()
+    goal_info = {"goal_image": goal_image}
+    cost = Cost(None, core_type="final_recon", aggregate="sum")
+    lo = torch.tensor([-2.5, 1.0, -2.5, 1.0], device="cuda")
+    hi = torch.tensor([2.5, 4.0, 2.5, 4.0], device="cuda")
+    noise_fn = lambda i: torch.randn(Na, 1, 4, generator=torch.Generator().manual_seed(100 + i)).cuda()
+
+    def run(n_steps):
+        # rollout noise: one (chunk, K, 64) draw per chunk and CEM step
+        draws = [t for s in range(n_steps) for t in orc.make_noise(128, K, 64, Na // 128, seed=60 + s)]
+        with NoiseInjector(draws):
+            return cem_plan(m, cost, goal_info, info["state"], cand, n_steps, noise_fn, lo, hi)
+
+    best1, c1, acts1, order1 = run(1)
+    # step 0 == direct rollout
+    direct = _costs(m, info, cand, torch.cat(orc.make_noise(128, K, 64, Na // 128, seed=60)), goal_image, chunk=128)
+    assert torch.equal(torch.argsort(direct, stable=True), order1)
+    assert torch.equal(best1, cand[order1[0]]) and c1.item() == direct[order1[0]].item()
+    # refit on the ranked candidates == numpy
+    mean, std = cem_refit(cand, order1, Na // 10, 0.05)
+    el = cand.cpu().numpy()[order1.cpu().numpy()][:Na // 10].astype(np.float64)
+    assert np.allclose(mean.cpu().numpy(), el.mean(0), rtol=1e-6) and np.allclose(std.cpu().numpy(), el.std(0) + 0.05, rtol=1e-6)
+    best3, c3, acts3, order3 = run(steps)
+    best3b, c3b, acts3b, order3b = run(steps)
+    assert torch.equal(best3, best3b) and torch.equal(acts3, acts3b) and torch.equal(order3, order3b) and c3.item() == c3b.item()
+    assert (acts3 >= lo).all() and (acts3 <= hi).all()
+    assert not torch.equal(acts3, cand)
+    print("CEM: best cost step0 %.6e -> step%d %.6e" % (c1.item(), steps - 1, c3.item()))
