@@ -181,6 +181,57 @@ def mixture_roofline(model, dev, hbm_peak, which):
             "algorithmic_bytes_per_call": alg_bytes, "peak_source": which}
 
 
+def mixture_bwd_roofline(model, dev, hbm_peak, which):
+    """Achieved HBM GB/s of the mixture backward (d total / d dec_out from the refinement-input gradients + the loss
+    weight; SURVEY.md section 8d: (14K+3)*4 bytes per sample-pixel), same rotating buffer sets as the forward."""
+    from op3_b200 import _lib
+    from op3_b200._lib import Op3MixtureIO, check, ptr
+    lib = _lib.load()
+    eng = model.engine
+    B, N = B_PER_GPU, B_PER_GPU * K
+    d = eng.dims(B)
+    ps = eng.params_struct()
+    gflat = torch.zeros_like(eng.flat_params())
+    gs = eng._struct_for(gflat)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    g = torch.Generator(device=dev).manual_seed(4)
+    f = lambda *s: torch.rand(*s, device=dev, generator=g)
+    R = 4
+    sets = []
+    for _ in range(R):
+        keep = dict(dec=f(N, D, D, 4), img=f(B, 3, D, D), l=[f(B, K, 64) for _ in range(4)],
+                    stats=torch.empty(lib.op3_mixture_stats_floats(C.byref(d)), device=dev), losses=torch.zeros(4, device=dev),
+                    mix1=torch.empty(N, D, D, 4, device=dev), mix2=torch.empty(N, D, D, 4, device=dev),
+                    smp=torch.empty(B, D, D, 4, device=dev), d_in=f(N, 5, D, D, 4) - 0.5, d_dec=torch.empty(N, D, D, 4, device=dev))
+        io = Op3MixtureIO()
+        io.dec_out, io.image, io.image_bstride = ptr(keep["dec"]), ptr(keep["img"]), 3 * D * D
+        io.post_l1, io.post_l2, io.prior_l1, io.prior_l2 = [ptr(t) for t in keep["l"]]
+        io.stats, io.losses = ptr(keep["stats"]), ptr(keep["losses"])
+        io.mix1, io.mix2, io.smp = ptr(keep["mix1"]), ptr(keep["mix2"]), ptr(keep["smp"])
+        io.sync = eng.mix_sync(dev, st).data_ptr()
+        check(lib.op3_mixture_fwd(C.byref(d), C.byref(ps), C.byref(io), 1, st), "mixture_fwd")
+        sets.append((keep, io))
+    n_it, groups = 40, []
+    for g_i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_it):
+            keep, io = sets[i % R]
+            check(lib.op3_mixture_bwd(C.byref(d), C.byref(io), 0.2, ptr(keep["d_in"]), ptr(keep["d_dec"]), C.byref(gs), None, st),
+                  "mixture_bwd")
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if g_i:
+            groups.append(e0.elapsed_time(e1) / n_it)
+    ms = float(np.median(groups))
+    alg_bytes = (14 * K + 3) * 4.0 * B * D * D
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "mixture backward (mix_bwd_kernel + LayerNorm2D parameter-gradient reduction)",
+            "l2": "4 rotating buffer sets >> 126 MB L2", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": ncu_traffic("mixture_bwd", "any"), "ms_per_call": ms,
+            "algorithmic_bytes_per_call": alg_bytes, "peak_source": which}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +384,7 @@ def main():
                      # the split modes issue three tensor-core products per algorithmic FLOP: their own ceiling is peak / 3
                      "frac_of_mode_ceiling": achieved / (mode_peak / mode_products)},
         "roofline_mixture": mixture_roofline(model, dev, hbm, which),
+        "roofline_mixture_bwd": mixture_bwd_roofline(model, dev, hbm, which),
         "kernel_families": fams,
     }
     if not args.no_cpu_baseline:

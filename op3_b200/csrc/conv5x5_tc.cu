@@ -27,8 +27,9 @@ namespace op3 {
 
 namespace {
 
-constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_THREADS = 128;
-constexpr int TC_THREADS = (LOAD_WARP0 + 4) * 32;
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 7, LOAD_THREADS = LOAD_WARPS * 32;
+constexpr int TC_THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;
+constexpr int TC_LD_U = 4;   // pixels per loader thread and pass in the fp16 mode (x 4 channel chunks = 16 loads in flight)
 
 // MODE: 0 = 1xTF32, 1 = 3xTF32 (hi/lo split), 2 = fp16 hi/lo split (K = 16 per MMA, per-image operand scaling)
 template <int NOUT, int MODE>
@@ -98,32 +99,35 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
           const float sc = __uint_as_float(f16_scale_bits(maxbits[n]));
           uint4* a_hi16 = reinterpret_cast<uint4*>(st);
           uint4* a_lo16 = reinterpret_cast<uint4*>(st + a_bytes);
-          for (int kc = 0; kc < 2; ++kc) {
-            const int c = cg * 4 + 2 * kc;
-            const float4* src0 = c < in.total_chunks ? tc_src_chunk_ptr(in, c, n, D) : nullptr;
-            const float4* src1 = c + 1 < in.total_chunks ? tc_src_chunk_ptr(in, c + 1, n, D) : nullptr;
-            int q = q0 + lt;
-            int iy = q / P - 2, ix = q % P - 2;
-            for (int h0 = lt; h0 < PH; h0 += 4 * LOAD_THREADS) {
-              float4 v0[4], v1[4];
+          // all loads of a pass (both 8-channel k-chunks x TC_LD_U pixels) are in flight before the first conversion: one
+          // exposed memory latency per pass instead of one per k-chunk
+          const float4* src[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const bool ok = h0 + u * LOAD_THREADS < PH && iy >= 0 && iy < D && ix >= 0 && ix < D;
-                const size_t off = (size_t)iy * D + ix;
-                v0[u] = (ok && src0) ? __ldg(src0 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v1[u] = (ok && src1) ? __ldg(src1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-                ix += LOAD_THREADS;
-                while (ix >= P - 2) { ix -= P; ++iy; }
-              }
+          for (int j = 0; j < 4; ++j) src[j] = cg * 4 + j < in.total_chunks ? tc_src_chunk_ptr(in, cg * 4 + j, n, D) : nullptr;
+          int q = q0 + lt;
+          int iy = q / P - 2, ix = q % P - 2;
+          for (int h0 = lt; h0 < PH; h0 += TC_LD_U * LOAD_THREADS) {
+            float4 v[TC_LD_U][4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int h = h0 + u * LOAD_THREADS;
-                if (h < PH) {
+            for (int u = 0; u < TC_LD_U; ++u) {
+              const bool ok = h0 + u * LOAD_THREADS < PH && iy >= 0 && iy < D && ix >= 0 && ix < D;
+              const size_t off = (size_t)iy * D + ix;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[u][j] = (ok && src[j]) ? __ldg(src[j] + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+              ix += LOAD_THREADS;
+              while (ix >= P - 2) { ix -= P; ++iy; }
+            }
+#pragma unroll
+            for (int u = 0; u < TC_LD_U; ++u) {
+              const int h = h0 + u * LOAD_THREADS;
+              if (h < PH) {
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
                   uint4 hi, lo;
-                  f16_split2(v0[u].x * sc, v0[u].y * sc, hi.x, lo.x);
-                  f16_split2(v0[u].z * sc, v0[u].w * sc, hi.y, lo.y);
-                  f16_split2(v1[u].x * sc, v1[u].y * sc, hi.z, lo.z);
-                  f16_split2(v1[u].z * sc, v1[u].w * sc, hi.w, lo.w);
+                  f16_split2(v[u][2 * kc].x * sc, v[u][2 * kc].y * sc, hi.x, lo.x);
+                  f16_split2(v[u][2 * kc].z * sc, v[u][2 * kc].w * sc, hi.y, lo.y);
+                  f16_split2(v[u][2 * kc + 1].x * sc, v[u][2 * kc + 1].y * sc, hi.z, lo.z);
+                  f16_split2(v[u][2 * kc + 1].z * sc, v[u][2 * kc + 1].w * sc, hi.w, lo.w);
                   a_hi16[kc * PH + h] = hi;
                   a_lo16[kc * PH + h] = lo;
                 }
