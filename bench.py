@@ -299,8 +299,7 @@ def main():
 
     def step_e2e(i):
         fr, ac = host[i % n_batches]
-        frd = fr.to(dev, non_blocking=True).float() / 255.0
-        acd = ac.to(dev, non_blocking=True)
+        frd, acd = trainer.prepare_tensors((fr, ac))      # pinned uint8 -> H2D as bytes -> op3_prepare_frames (/255)
         vals = trainer.train_step(frd, acd, sched, lw)
         out4.copy_(torch.stack(vals), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()

@@ -261,6 +261,11 @@ int op3_cem_refit(int Na, int TA, int F, const float* actions, const long long* 
 int op3_cem_resample(int Na, int TA, const float* mean, const float* std, const float* noise, const float* lo,
                      const float* hi, float* out, void* stream);
 
+/* Data feed: uint8 frames -> planar fp32 / 255 on the device (OP3Trainer.prepare_tensors, op3_trainer.py:148-153, fused
+ * with load_dataset's channels-last -> channels-first move, train_op3.py:27-28,46-47).  in: [n_frames][3][D][D]
+ * (channels_last = 0) or [n_frames][D][D][3] (channels_last = 1) bytes; out: [n_frames][3][D][D] floats. */
+int op3_prepare_frames(long long n_frames, int D, int channels_last, const unsigned char* in, float* out, void* stream);
+
 /* sub_images[a][k][c] = colors*mask (op3_model.py:612) from planar colours / masks */
 int op3_sub_images(long long n_slots, int D, const float* colors, const float* mask, float* out, void* stream);
 

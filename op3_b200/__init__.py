@@ -19,6 +19,7 @@ _ALIASES = {
     "op3.torch.op3_modules.decoder_network": "op3_b200.torch.op3_modules.decoder_network",
     "op3.torch.op3_modules.refinement_network": "op3_b200.torch.op3_modules.refinement_network",
     "op3.torch.op3_modules.physics_network": "op3_b200.torch.op3_modules.physics_network",
+    "op3.torch.data_management.dataset": "op3_b200.torch.data_management.dataset",
 }
 
 

@@ -10,7 +10,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libop3_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-diag-suppress", "550"]
+         "--expt-relaxed-constexpr", "-diag-suppress", "550"] + os.environ.get("OP3_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -32,6 +32,12 @@ constexpr int TC_THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;
 constexpr int TC_LD_U = 4;   // pixels per loader thread and pass in the fp16 mode (x 4 channel chunks = 16 loads in flight)
 
 // MODE: 0 = 1xTF32, 1 = 3xTF32 (hi/lo split), 2 = fp16 hi/lo split (K = 16 per MMA, per-image operand scaling)
+#ifdef OP3_TC_TRACE
+// debug timeline of the MMA issuer thread: [sm][0] cycles waiting for operand stages, [1] waiting for a free
+// accumulator buffer, [2] total cycles in the item loop, [3] number of MMAs issued
+__device__ unsigned long long g_tc_trace[256][4];
+#endif
+
 template <int NOUT, int MODE>
 struct TcCfg {
   static constexpr bool SPLIT3 = MODE != 0;
@@ -171,16 +177,33 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
       const uint32_t idesc1 = F16 ? make_idesc_f16(128, NB) : make_idesc_tf32(128, NB);
       const uint32_t idesc2 = F16 ? make_idesc_f16(128, NOUT) : make_idesc_tf32(128, NOUT);
       int it = 0, j = 0;
+#ifdef OP3_TC_TRACE
+      unsigned long long t_full = 0, t_acc = 0, n_mma = 0;
+      const unsigned long long t_begin = clock64();
+#endif
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
         const int grp = item % groups_img;
         const int ntile = min(G, tiles_img - grp * G);
         const int buf = j & 1;
+#ifdef OP3_TC_TRACE
+        const unsigned long long ta0 = clock64();
+#endif
         if (j >= 2) mbar_wait(&acc_empty[buf], ((j >> 1) - 1) & 1);
+#ifdef OP3_TC_TRACE
+        t_acc += clock64() - ta0;
+#endif
         tc_fence_after();
         const uint32_t dbase = tmem_base + (uint32_t)(buf * 256);
         for (int cg = 0; cg < ngroups; ++cg, ++it) {
           const int s = it % NSTAGE;
+#ifdef OP3_TC_TRACE
+          const unsigned long long tf0 = clock64();
+#endif
           mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
+#ifdef OP3_TC_TRACE
+          t_full += clock64() - tf0;
+          n_mma += (unsigned long long)ntile * 25 * (SPLIT3 ? 2 : 1);
+#endif
           tc_fence_after();
           const uint32_t st = smem_u32(smem_raw + (size_t)s * stage_bytes);
           const uint64_t ad = make_smem_desc(st, PH, 8);
@@ -193,7 +216,11 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
             const uint32_t dcol = dbase + (uint32_t)(t * NB);
 #pragma unroll
             for (int tap = 0; tap < 25; ++tap) {
+#ifdef OP3_TC_ALIGNED_PROBE   /* timing experiment only (wrong results): every tap starts on a 128-byte line */
+              const uint32_t aoff = (uint32_t)(128 * t + (tap / 5) * P + (tap % 5)) & ~7u;
+#else
               const uint32_t aoff = (uint32_t)(128 * t + (tap / 5) * P + (tap % 5));   // 16-byte units
+#endif
               const uint32_t boff = (uint32_t)(tap * 2 * NB);
               if (F16) {
                 mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
@@ -208,6 +235,12 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
         }
         tc_commit(&acc_full[buf]);                       // accumulators of this item complete
       }
+#ifdef OP3_TC_TRACE
+      if (blockIdx.x < 256) {
+        atomicAdd(&g_tc_trace[blockIdx.x][0], t_full); atomicAdd(&g_tc_trace[blockIdx.x][1], t_acc);
+        atomicAdd(&g_tc_trace[blockIdx.x][2], clock64() - t_begin); atomicAdd(&g_tc_trace[blockIdx.x][3], n_mma);
+      }
+#endif
     }
   } else {
     // ===================== epilogue (warp % 4 = TMEM lane quadrant, warp / 4 = tile parity) =====================
@@ -334,6 +367,14 @@ int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* w
 }
 
 }  // namespace
+
+#ifdef OP3_TC_TRACE
+extern "C" int op3_debug_tc_trace(unsigned long long* out /*[256][4] host*/, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 256 * 4);
+  if (reset) { static unsigned long long z[256][4]; cudaMemcpyToSymbol(g_tc_trace, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int tc_nout(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 

@@ -140,10 +140,41 @@ __global__ void cem_resample_kernel(long long n, int TA, const float* __restrict
   out[i] = v;
 }
 
+// uint8 frames -> planar fp32 in [0,1] (op3_trainer.py:148-153 `/ 255.0`; load_dataset's NHWC -> NCHW moveaxis,
+// train_op3.py:27-28,46-47).  One thread per 4 output floats of one colour plane; 4-byte loads in the planar layout.
+__global__ void __launch_bounds__(256) frames_u8_kernel(long long n4, int DD, int channels_last,
+                                                        const unsigned char* __restrict__ in, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // index of a float4 of the planar output
+  if (i >= n4) return;
+  float4 v;
+  if (!channels_last) {
+    const uchar4 u = reinterpret_cast<const uchar4*>(in)[i];
+    v = make_float4(u.x / 255.f, u.y / 255.f, u.z / 255.f, u.w / 255.f);
+  } else {
+    const long long e = i * 4, plane = e / DD;             // plane = frame*3 + c
+    const int pix = (int)(e % DD), c = (int)(plane % 3);
+    const unsigned char* src = in + ((plane / 3) * DD + pix) * 3 + c;
+    v = make_float4(src[0] / 255.f, src[3] / 255.f, src[6] / 255.f, src[9] / 255.f);
+  }
+  out[i] = v;
+}
+
 }  // namespace
 }  // namespace op3
 
 using namespace op3;
+
+extern "C" int op3_prepare_frames(long long n_frames, int D, int channels_last, const unsigned char* in, float* out,
+                                  void* stream) {
+  OP3_REQUIRE(n_frames > 0 && D > 0 && D % 2 == 0 && in && out, "op3_prepare_frames: bad argument (D must be even)");
+  OP3_REQUIRE(((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 15) == 0, "op3_prepare_frames: in must be 4-byte, out 16-byte aligned");
+  const long long n4 = n_frames * 3 * D * D / 4;
+  frames_u8_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n4, D * D, channels_last, in,
+                                                                                    reinterpret_cast<float4*>(out));
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
 
 extern "C" int op3_cem_refit(int Na, int TA, int F, const float* actions, const long long* order, float min_std,
                              float* mean, float* stdv, void* stream) {

@@ -122,6 +122,21 @@ class FusedClipAdam:
             self.scratch = torch.zeros(2048, device=self.exp_avg.device)
 
 
+def frames_to_float(frames_u8):
+    """uint8 CUDA frames (..., 3, D, D) or channels-last (..., D, D, 3) -> float32 (..., 3, D, D) in [0, 1]."""
+    if frames_u8.device.type != "cuda":
+        raise RuntimeError("op3_b200: frames_to_float needs a CUDA tensor (no CPU fallback)")
+    x = frames_u8.contiguous()
+    channels_last = x.shape[-1] == 3 and x.shape[-3] != 3
+    D = x.shape[-2]
+    lead = tuple(x.shape[:-3])
+    n = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead + (3, D, D), device=x.device, dtype=torch.float32)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    check(_lib.load().op3_prepare_frames(n, D, 1 if channels_last else 0, ptr(x), ptr(out), st), "op3_prepare_frames")
+    return out
+
+
 class OP3Trainer:
     def __init__(self, train_dataset, test_dataset, model, scheduler_class, batch_size, lr=1e-3):
         self.batch_size = batch_size
@@ -152,9 +167,17 @@ class OP3Trainer:
         torch.save(sd, open(osp.join(directory, "{}_params.pkl".format(prefix)), "wb"))
 
     def prepare_tensors(self, tensors):
+        """op3_trainer.py:148-153.  Float frames take the reference's `/ 255.0`; uint8 frames (host pinned or device
+        resident, (B,T,3,D,D) or channels-last (B,T,D,D,3)) are moved as bytes and converted by op3_prepare_frames."""
         dev = ptu.device if ptu.device is not None else next(self._core().parameters()).device
-        imgs = tensors[0].to(dev) / 255.0
-        return (imgs, tensors[1].to(dev)) if len(tensors) == 2 else (imgs, None)
+        frames = tensors[0]
+        if frames.dtype == torch.uint8:
+            imgs = frames_to_float(frames.to(dev, non_blocking=True))
+        else:
+            imgs = frames.to(dev) / 255.0
+        if len(tensors) == 2 and tensors[1] is not None:
+            return imgs, tensors[1].to(dev, non_blocking=True)
+        return imgs, None
 
     def train_step(self, true_images, actions, schedule, loss_schedule):
         """One optimisation step (op3_trainer.py:166-197).  Returns the four logged scalars as device tensors."""

@@ -289,3 +289,30 @@ def test_cem_refit_and_resample_match_numpy():
         assert torch.equal(mean, mean2) and torch.equal(std, std2)
     with pytest.raises(ValueError):
         cem_refit(torch.zeros(8, 1, 4, device="cuda"), torch.arange(8, device="cuda"), 9)
+
+
+def test_prepare_frames_and_device_dataset():
+    """Data feed: uint8 -> float/255 in both layouts, bit-exact against torch's division,
+    and the device-resident dataset handing batches to OP3Trainer.prepare_tensors."""
+    from op3_b200.torch.op3_modules.op3_trainer import frames_to_float, OP3Trainer, TrainingScheduler
+    from op3_b200.torch.data_management.dataset import DeviceBlocksDataset
+    g = torch.Generator().manual_seed(0)
+    T, N, D = 3, 10, 64
+    feats = torch.randint(0, 256, (T, N, D, D, 3), generator=g, dtype=torch.uint8)      # the HDF5 layout
+    ref = feats.permute(1, 0, 4, 2, 3).float() / 255.0                                  # train_op3.py:27-28 + /255
+    planar = feats.permute(1, 0, 4, 2, 3).contiguous().cuda()
+    assert torch.equal(frames_to_float(planar).cpu(), ref)
+    cl = feats.permute(1, 0, 2, 3, 4).contiguous().cuda()
+    assert torch.equal(frames_to_float(cl).cpu(), ref)
+    acts = torch.rand(T, N, 4, generator=g)
+    ds = DeviceBlocksDataset.from_arrays(feats.numpy(), acts.numpy(), batchsize=4, shuffle=False)
+    m, _ = build_model(4, 4, seed=0)
+    tr = OP3Trainer(ds, ds, m, TrainingScheduler(4, "curriculum", T, T), 4, lr=3e-4)
+    batches = list(ds.dataloader)
+    assert len(batches) == 2
+    imgs, a = tr.prepare_tensors(batches[1])
+    assert imgs.shape == (4, T, 3, D, D) and torch.equal(imgs.cpu(), ref[4:8]) and torch.equal(a.cpu(), acts.permute(1, 0, 2)[4:8])
+    item, ai = ds[7]
+    assert torch.allclose(item.cpu(), ref[7] * 255.0) and torch.equal(ai.cpu(), acts[:, 7])
+    with pytest.raises(RuntimeError):
+        frames_to_float(planar.cpu())

@@ -35,6 +35,22 @@ def _worker(rank, world, port, out):
     assert order[0].item() == 7
     gathered2d = par.all_gather_rows(torch.full((e - s, 3), float(rank)), n)
     assert gathered2d.shape == (n, 3) and gathered2d[:6].eq(0).all() and gathered2d[6:].eq(1).all()
+    # device-resident data feed: the sampler gives every rank a disjoint shard of the same global batch (host logic
+    # only: uint8 tensors on the CPU here; the conversion kernel is CUDA-only and covered by the GPU tests)
+    from op3_b200.torch.data_management.dataset import DeviceBlocksDataset
+    frames = torch.arange(12, dtype=torch.uint8).view(12, 1, 1, 1, 1).expand(12, 2, 3, 4, 4).contiguous()
+    acts = torch.arange(12, dtype=torch.float32).view(12, 1, 1).expand(12, 2, 4).contiguous()
+    ds = DeviceBlocksDataset(frames, acts, batchsize=3, shuffle=True, seed=5)
+    assert ds.global_batch == 6 and len(ds.dataloader) == 2 and ds.action_dim == 4
+    seen = []
+    for fr, ac in ds.dataloader:
+        assert fr.shape == (3, 2, 3, 4, 4) and fr.dtype == torch.uint8 and ac.shape == (3, 2, 4)
+        assert torch.equal(fr[:, 0, 0, 0, 0].float(), ac[:, 0, 0])
+        seen += fr[:, 0, 0, 0, 0].tolist()
+    allseen = [None, None]
+    dist.all_gather_object(allseen, seen)
+    assert sorted(allseen[0] + allseen[1]) == list(range(12)), allseen
+    assert not set(allseen[0]) & set(allseen[1])
     out[rank] = 1
     dist.destroy_process_group()
 
