@@ -306,22 +306,32 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
   if (warp == WG_LOADERS / 32) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int S, int n_w, int n_b, float* __restrict__ dwt,
-                                       float* __restrict__ dbias) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int tot = n_w + n_b;
-  if (i >= tot) return;
-  // fixed summation order (deterministic); four independent chains keep enough loads in flight
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= S; k += 4) {
-    s0 += partial[(size_t)k * tot + i]; s1 += partial[(size_t)(k + 1) * tot + i];
-    s2 += partial[(size_t)(k + 2) * tot + i]; s3 += partial[(size_t)(k + 3) * tot + i];
+// Sum of the per-CTA partial slabs.  A block owns 64 outputs; its four 64-thread groups each walk a quarter of the slabs
+// (coalesced 256-byte rows, two chains in flight) and the first group adds the four partials in a fixed order, so the
+// result is deterministic and four times as many loads are in flight as with one thread per output.
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int S, int n_w, int n_b,
+                                                              float* __restrict__ dwt, float* __restrict__ dbias) {
+  __shared__ float s_part[4][64];
+  const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
+  const int i = blockIdx.x * 64 + j;
+  const int tot = n_w + n_b;
+  const int per = (S + 3) / 4, k0 = q * per, k1 = min(S, k0 + per);
+  float s0 = 0.f, s1 = 0.f;
+  if (i < tot) {
+    int k = k0;
+    for (; k + 2 <= k1; k += 2) {
+      s0 += partial[(size_t)k * tot + i];
+      s1 += partial[(size_t)(k + 1) * tot + i];
+    }
+    if (k < k1) s0 += partial[(size_t)k * tot + i];
   }
-  for (; k < S; ++k) s0 += partial[(size_t)k * tot + i];
-  const float s = (s0 + s1) + (s2 + s3);
-  if (i < n_w) dwt[i] += s;
-  else if (dbias) dbias[i - n_w] += s;
+  s_part[q][j] = s0 + s1;
+  __syncthreads();
+  if (q == 0 && i < tot) {
+    const float s = (s_part[0][j] + s_part[1][j]) + (s_part[2][j] + s_part[3][j]);
+    if (i < n_w) dwt[i] += s;
+    else if (dbias) dbias[i - n_w] += s;
+  }
 }
 
 
@@ -641,6 +651,9 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
 // block (steps with no MMAs).  Ring slots are numbered by a running per-CTA counter, so a slot is rewritten 7 steps after
 // it was filled, two steps after its last reader (the same empty barrier that guards the two A stages).
 // =====================================================================================================================
+#ifdef OP3_TC_TRACE
+__device__ unsigned long long g_ring_trace[256][4];   // issuer: cycles waiting for operands, total, MMAs, steps
+#endif
 constexpr int RB_RING = 56;                  // G chunks in the ring (+ 1 guard slot = copy of slot 0 for wrapped K pairs)
 constexpr int RB_PRE = 5;                    // refill steps per item: 5 blocks = 40 chunks >= 4*P/8 = 36 (D = 64)
 constexpr int RB_LOADERS = 2 * 4 * 32;       // two groups (even / odd steps) of 2 X warps + 2 G warps
@@ -857,6 +870,10 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
     int koff[5];                                           // (-achunks * ky) mod RING
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) koff[ky] = (5 * RB_RING - achunks * ky) % RB_RING;
+#ifdef OP3_TC_TRACE
+    unsigned long long t_full = 0, n_mma = 0;
+    const unsigned long long t_begin = clock64();
+#endif
     for (; item < n_items; ++t) {
       const int s = t & 1;
       const bool real = vb >= item_b0(item);
@@ -877,7 +894,14 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
           if (slot >= RB_RING) slot -= RB_RING;
         }
       }
+#ifdef OP3_TC_TRACE
+      const unsigned long long tf0 = clock64();
+#endif
       mbar_wait(&full_bar[s], (t >> 1) & 1);
+#ifdef OP3_TC_TRACE
+      t_full += clock64() - tf0;
+      if (real) n_mma += 40;
+#endif
       tc_fence_after();
       if (real) {
         // consecutive MMAs go to DIFFERENT accumulators (kernel rows): back-to-back MMAs on one accumulator serialise
@@ -899,11 +923,19 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
       advance(item, vb);
     }
     tc_commit(&acc_bar);
+#ifdef OP3_TC_TRACE
+    atomicAdd(&g_ring_trace[blockIdx.x][0], t_full); atomicAdd(&g_ring_trace[blockIdx.x][1], clock64() - t_begin);
+    atomicAdd(&g_ring_trace[blockIdx.x][2], n_mma); atomicAdd(&g_ring_trace[blockIdx.x][3], (unsigned long long)t);
+#endif
   }
   // ===================== epilogue =====================
   __syncthreads();
-  float* red = reinterpret_cast<float*>(smem_raw);         // [2 shifts][32 ci][480]: the X_lo rows
-  float* s_bias = red + 2 * 32 * 480;                      // [4 G warps][8 chunks][4]
+  // TMEM lanes: quadrant 0 / 2 = X shift 0 / 1 hi rows, quadrant 1 / 3 = the matching lo rows; columns 96*ky + 32*c + pc.
+  // (1) the lo quadrants go to shared memory (row pitch 481 floats: conflict-free), (2) the hi quadrants add them, scale
+  // and leave the sums there, (3) all warps write the slab as coalesced 128-byte rows of 32 output channels.
+  constexpr int RPITCH = 481;
+  float* red = reinterpret_cast<float*>(smem_raw);         // [2 shifts][32 rows][RPITCH]
+  float* s_bias = red + 2 * 32 * RPITCH;                   // [4 G warps][8 chunks][4]
   float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
   const float inv = 1.f / (sx_scale * sg_scale);           // powers of two: exact
   if (warp < MMA_WARP) {
@@ -921,39 +953,38 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
       dst[0] = bias_acc.x; dst[1] = bias_acc.y; dst[2] = bias_acc.z; dst[3] = bias_acc.w;
     }
   }
-  if (warp == 1 || warp == 3) {          // lanes 32..63 / 96..127: X_lo rows
-    for (int c0 = 0; c0 < 480; c0 += 16) {
+  const int quad = warp & 3, chalf = warp >> 2;            // two warps per TMEM lane quadrant split the 480 columns
+  if (warp < MMA_WARP && (quad & 1)) {
+    float* dst = red + ((size_t)(quad >> 1) * 32 + lane) * RPITCH;
+    for (int c0 = 240 * chalf; c0 < 240 * chalf + 240; c0 += 16) {
       float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) red[((size_t)(warp >> 1) * 32 + lane) * 480 + c0 + i] = v[i];
+      for (int i = 0; i < 16; ++i) dst[c0 + i] = v[i];
     }
   }
   __syncthreads();
-  if (warp == 0 || warp == 2) {          // lanes 0..31 / 64..95: X_hi rows; columns 96*ky + 32*c + co, tap kx = 2c + sub
-    const int sub = warp >> 1;
-    for (int ky = 0; ky < 5; ++ky)
-      for (int c = 0; c < 3; ++c) {
-        const int kx = 2 * c + sub;
-        if (kx > 4) continue;
+  if (warp < MMA_WARP && !(quad & 1)) {
+    float* dst = red + ((size_t)(quad >> 1) * 32 + lane) * RPITCH;
+    for (int c0 = 240 * chalf; c0 < 240 * chalf + 240; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < NCO; c0 += 16) {
-          float v[16];
-          const int col = 96 * ky + 32 * c + c0;
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
-          tmem_ld_wait();
-          const int ci = 4 * (lane & 7) + (lane >> 3);     // row 8*r + cc holds channel 4*cc + r
-          if (ci < cin_pad) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int pc = c0 + i, co = 4 * (pc & 7) + (pc >> 3);
-              if (co < g_chunks * 4)
-                slab[((size_t)(ky * 5 + kx) * cin_pad + ci) * cout_total + co0 + co] =
-                    (v[i] + red[((size_t)sub * 32 + lane) * 480 + col + i]) * inv;
-            }
-          }
-        }
+      for (int i = 0; i < 16; ++i) dst[c0 + i] = (v[i] + dst[c0 + i]) * inv;
+    }
+  }
+  __syncthreads();
+  {
+    const int co = lane, pc = 8 * (co & 3) + (co >> 2);    // column 8*r + cc holds output channel 4*cc + r
+    if (co < g_chunks * 4)
+      for (int r = warp; r < 25 * cin_pad; r += RB_THREADS / 32) {
+        const int tap = r / cin_pad, ci = r - tap * cin_pad;
+        const int ky = tap / 5, kx = tap - 5 * ky;
+        const int row = 8 * (ci & 3) + (ci >> 2);          // row 8*r + cc holds input channel 4*cc + r
+        slab[((size_t)tap * cin_pad + ci) * cout_total + co0 + co] =
+            red[((size_t)(kx & 1) * 32 + row) * RPITCH + 96 * ky + 32 * (kx >> 1) + pc];
       }
   }
   if (tid < g_chunks * 4)
@@ -1047,6 +1078,14 @@ int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const 
 
 }  // namespace
 
+#ifdef OP3_TC_TRACE
+extern "C" int op3_debug_ring_trace(unsigned long long* out /*[256][4] host*/, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_ring_trace, sizeof(unsigned long long) * 256 * 4);
+  if (reset) { static unsigned long long z[256][4]; cudaMemcpyToSymbol(g_ring_trace, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 size_t conv5x5_wgrad_tc_scratch_floats(int cin_pad, int cout) {
   return (size_t)wg_sets() * ((size_t)25 * cin_pad * cout + cout);
 }
@@ -1067,7 +1106,10 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
   const bool f16 = precision == OP3_PREC_F16X3 && (cout >= 32 || cout == 4) && D % 8 == 0;
   const bool use_ring = f16 && 4 * ((D + 8) / 8) <= 8 * RB_PRE;
   const size_t zero_slabs = use_ring ? 148 : (size_t)wg_sets();
-  OP3_CHECK(cudaMemsetAsync(scratch, 0, (zero_slabs * slab + 8) * sizeof(float), st));   // padding entries stay zero
+  // The per-row kernels leave padding entries of their slabs untouched (they must read as zero); the ring kernel writes
+  // every entry of every slab it owns, so only the 8 operand-maxima words behind the slabs are cleared for it.
+  if (use_ring) OP3_CHECK(cudaMemsetAsync(scratch + zero_slabs * slab, 0, 8 * sizeof(float), st));
+  else OP3_CHECK(cudaMemsetAsync(scratch, 0, (zero_slabs * slab + 8) * sizeof(float), st));
   if (f16) {
     // per-tensor operand maxima live in the 8 words after the partial slabs (scratch: conv5x5_wgrad_scratch_floats)
     // operand maxima: per-image arrays recorded by the producers (n = N entries), else one word reduced here (n = 1)
@@ -1110,7 +1152,7 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
     }
   }
   const int n_w = 25 * cin_pad * cout;
-  wgrad_tc_reduce_kernel<<<ceil_div(n_w + cout, 256), 256, 0, st>>>(scratch, n_slabs, n_w, cout, dwt, dbias);
+  wgrad_tc_reduce_kernel<<<ceil_div(n_w + cout, 64), 256, 0, st>>>(scratch, n_slabs, n_w, cout, dwt, dbias);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
