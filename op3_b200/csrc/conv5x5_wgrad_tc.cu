@@ -652,7 +652,7 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
 // it was filled, two steps after its last reader (the same empty barrier that guards the two A stages).
 // =====================================================================================================================
 #ifdef OP3_TC_TRACE
-__device__ unsigned long long g_ring_trace[256][4];   // issuer: cycles waiting for operands, total, MMAs, steps
+__device__ unsigned long long g_ring_trace[256][8];   // issuer: cycles waiting for operands, loop total, MMAs, steps, kernel total, prologue
 #endif
 constexpr int RB_RING = 56;                  // G chunks in the ring (+ 1 guard slot = copy of slot 0 for wrapped K pairs)
 constexpr int RB_PRE = 5;                    // refill steps per item: 5 blocks = 40 chunks >= 4*P/8 = 36 (D = 64)
@@ -685,6 +685,9 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
   const float sx_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(xmax, xmax_n)));     // one scale per TENSOR: the sum runs
   const float sg_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(gmax, gmax_n)));     // over all images
 
+#ifdef OP3_TC_TRACE
+  const unsigned long long t_kernel0 = clock64();
+#endif
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* ring = smem_raw;
   uint8_t* a_stage = smem_raw + RB_RING_BYTES;
@@ -926,6 +929,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
 #ifdef OP3_TC_TRACE
     atomicAdd(&g_ring_trace[blockIdx.x][0], t_full); atomicAdd(&g_ring_trace[blockIdx.x][1], clock64() - t_begin);
     atomicAdd(&g_ring_trace[blockIdx.x][2], n_mma); atomicAdd(&g_ring_trace[blockIdx.x][3], (unsigned long long)t);
+    atomicAdd(&g_ring_trace[blockIdx.x][5], t_begin - t_kernel0);
 #endif
   }
   // ===================== epilogue =====================
@@ -991,6 +995,9 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
     slab[(size_t)25 * cin_pad * cout_total + co0 + tid] = (s_bias[tid] + s_bias[32 + tid]) + (s_bias[64 + tid] + s_bias[96 + tid]);
   tc_fence_before();
   __syncthreads();
+#ifdef OP3_TC_TRACE
+  if (tid == 0) atomicAdd(&g_ring_trace[blockIdx.x][4], clock64() - t_kernel0);
+#endif
   if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
@@ -1080,8 +1087,8 @@ int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const 
 
 #ifdef OP3_TC_TRACE
 extern "C" int op3_debug_ring_trace(unsigned long long* out /*[256][4] host*/, int reset) {
-  if (out) cudaMemcpyFromSymbol(out, g_ring_trace, sizeof(unsigned long long) * 256 * 4);
-  if (reset) { static unsigned long long z[256][4]; cudaMemcpyToSymbol(g_ring_trace, z, sizeof(z)); }
+  if (out) cudaMemcpyFromSymbol(out, g_ring_trace, sizeof(unsigned long long) * 256 * 8);
+  if (reset) { static unsigned long long z[256][8]; cudaMemcpyToSymbol(g_ring_trace, z, sizeof(z)); }
   return 0;
 }
 #endif
