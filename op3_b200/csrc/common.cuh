@@ -83,6 +83,9 @@ enum { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2 };
 //   transB=0: B is stored [K,N] (ldb);    transB=1: B is stored [N,K] (ldb)  (nn.Linear weight)
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, int transA, const float* B, int ldb,
          int transB, float* C, int ldc, const float* bias, int act, int accumulate);
+// weight + bias gradient of y = x W^T + b in one launch: gW[out,in] += dY^T X, gB[out] += sum_m dY[m,:]
+int gemm_wgrad(cudaStream_t st, int out, int in, int M, const float* dY, int lddy, const float* X, int ldx, float* gW,
+               int ldgw, float* gB);
 // dPre[m,n] = dY[m,n] * act'(Y[m,n]) in place on dY (Y is the activation OUTPUT)
 int act_backward(cudaStream_t st, int M, int N, float* dY, int ldd, const float* Y, int ldy, int act);
 // out[n] (+)= sum_m X[m,n]

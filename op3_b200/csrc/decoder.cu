@@ -243,8 +243,7 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
   OP3_TRY(gemm(st, N, R, NCLS * 32, dT, NCLS * 32, 0, prep + L.wsum, R, 0, dz, R, nullptr, ACT_NONE, accumulate_dz ? 1 : 0));
   if (pg) {
     // d Wsum[cls*32+co][c] += sum_n dT[n][.] z[n][c] ; d biasT += column sums of dT ; d cmap += sum_n g
-    OP3_TRY(gemm(st, NCLS * 32, R, N, dT, NCLS * 32, 1, z, R, 0, pg + L.wsum, R, nullptr, ACT_NONE, 1));
-    OP3_TRY(colsum(st, N, NCLS * 32, dT, NCLS * 32, pg + L.biasT, 1));
+    OP3_TRY(gemm_wgrad(st, NCLS * 32, R, N, dT, NCLS * 32, z, R, pg + L.wsum, R, pg + L.biasT));
     dec_l1_dcmap_kernel<<<ceil_div(8 * D * D, 64), 256, 0, st>>>(g, N, D, reinterpret_cast<float4*>(pg + L.cmap));
     OP3_COUNT_LAUNCH();
     OP3_LAUNCH_CHECK();

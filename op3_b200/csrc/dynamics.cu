@@ -19,12 +19,10 @@ int mlp_fwd(cudaStream_t st, int M, const float* x, int ldx, const Op3Mlp& w, Ml
 int mlp_bwd(cudaStream_t st, int M, const float* x, int ldx, const Op3Mlp& w, const Op3Mlp& gw, MlpDims s, const float* h,
             const float* y, int ldy, float* dy, int lddy, float* dh, float* dx, int lddx, int acc_dx) {
   OP3_TRY(act_backward(st, M, s.out, dy, lddy, y, ldy, s.out_act));
-  OP3_TRY(gemm(st, s.out, s.hid, M, dy, lddy, 1, h, s.hid, 0, gw.last.w, s.hid, nullptr, ACT_NONE, 1));
-  OP3_TRY(colsum(st, M, s.out, dy, lddy, gw.last.b, 1));
+  OP3_TRY(gemm_wgrad(st, s.out, s.hid, M, dy, lddy, h, s.hid, gw.last.w, s.hid, gw.last.b));
   OP3_TRY(gemm(st, M, s.hid, s.out, dy, lddy, 0, w.last.w, s.hid, 0, dh, s.hid, nullptr, ACT_NONE, 0));
   OP3_TRY(act_backward(st, M, s.hid, dh, s.hid, h, s.hid, ACT_ELU));
-  OP3_TRY(gemm(st, s.hid, s.in, M, dh, s.hid, 1, x, ldx, 0, gw.fc0.w, s.in, nullptr, ACT_NONE, 1));
-  OP3_TRY(colsum(st, M, s.hid, dh, s.hid, gw.fc0.b, 1));
+  OP3_TRY(gemm_wgrad(st, s.hid, s.in, M, dh, s.hid, x, ldx, gw.fc0.w, s.in, gw.fc0.b));
   if (dx) OP3_TRY(gemm(st, M, s.in, s.hid, dh, s.hid, 0, w.fc0.w, s.in, 0, dx, lddx, nullptr, ACT_NONE, acc_dx));
   return OP3_OK;
 }

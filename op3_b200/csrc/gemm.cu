@@ -16,7 +16,8 @@ constexpr int BM = 32, BN = 32, BK = 16, KG = 4;
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                    const float* __restrict__ B, int ldb, float* __restrict__ C,
-                                                   int ldc, const float* __restrict__ bias, int act, int accumulate) {
+                                                   int ldc, const float* __restrict__ bias, int act, int accumulate,
+                                                   float* __restrict__ colsum_out) {
   static_assert(BM == BN, "square tiles");
   __shared__ float sm[2 * KG * BK * (BM + 4)];
   float (*As)[BK][BM + 4] = reinterpret_cast<float (*)[BK][BM + 4]>(sm);
@@ -33,6 +34,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float ra[8], rb[8];
+  // TA == 1 only (weight gradients dW = dY^T X): the first column of tiles also accumulates sum_k A[k][m] = the bias gradient
+  const bool do_cs = TA == 1 && colsum_out != nullptr && blockIdx.x == 0 && tx == 0;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
 
   auto fetch = [&](int k0) {
 #pragma unroll
@@ -79,12 +83,21 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (do_cs) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cs[i] += a[i];
+      }
     }
     __syncthreads();
   }
   // partial tiles of groups 1..3 -> shared memory (aliasing the operand buffers), summed by group 0 in a fixed order
   float (*part)[BM][BN + 1] = reinterpret_cast<float (*)[BM][BN + 1]>(sm);
-  static_assert(sizeof(sm) >= 3 * BM * (BN + 1) * sizeof(float), "reduction buffer does not fit");
+  static_assert(sizeof(sm) >= (3 * BM * (BN + 1) + KG * BM) * sizeof(float), "reduction buffer does not fit");
+  float (*cs_part)[BM] = reinterpret_cast<float (*)[BM]>(sm + 3 * BM * (BN + 1));
+  if (do_cs) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cs_part[kg][ty * 4 + i] = cs[i];
+  }
   if (kg > 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -92,6 +105,13 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
       for (int j = 0; j < 4; ++j) part[kg - 1][ty * 4 + i][tx * 4 + j] = acc[i][j];
   }
   __syncthreads();
+  if (kg == 0 && do_cs) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int mm = ty * 4 + i;
+      if (m0 + mm < M) colsum_out[m0 + mm] += (cs_part[0][mm] + cs_part[1][mm]) + (cs_part[2][mm] + cs_part[3][mm]);
+    }
+  }
   if (kg == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -153,10 +173,22 @@ int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, int tran
   if (M <= 0 || N <= 0) return OP3_OK;
   ProfScope prof(st, KID_GEMM, 2.0 * M * N * K);
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-  if (transA == 0 && transB == 0) gemm_kernel<0, 0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
-  else if (transA == 0 && transB == 1) gemm_kernel<0, 1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
-  else if (transA == 1 && transB == 0) gemm_kernel<1, 0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
-  else gemm_kernel<1, 1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
+  if (transA == 0 && transB == 0) gemm_kernel<0, 0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, nullptr);
+  else if (transA == 0 && transB == 1) gemm_kernel<0, 1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, nullptr);
+  else if (transA == 1 && transB == 0) gemm_kernel<1, 0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, nullptr);
+  else gemm_kernel<1, 1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, nullptr);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+// gW[out][in] += dY^T X and gB[out] += column sums of dY in ONE launch (dY: [M][out] rows, X: [M][in] rows)
+int gemm_wgrad(cudaStream_t st, int out, int in, int M, const float* dY, int lddy, const float* X, int ldx, float* gW,
+               int ldgw, float* gB) {
+  if (out <= 0 || in <= 0) return OP3_OK;
+  ProfScope prof(st, KID_GEMM, 2.0 * out * in * M);
+  dim3 grid(ceil_div(in, BN), ceil_div(out, BM));
+  gemm_kernel<1, 0><<<grid, 256, 0, st>>>(out, in, M, dY, lddy, X, ldx, gW, ldgw, nullptr, ACT_NONE, 1, gB);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;

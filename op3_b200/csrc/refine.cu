@@ -439,13 +439,11 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   if (d_h) OP3_TRY(axpy(st, (long long)N * LSTM, d_h, dh2));
   if (d_l1n) {
     OP3_TRY(gemm(st, N, LSTM, Rs, d_l1n, Rs, 0, p->ref_last_fc.w, LSTM, 0, dh2, LSTM, nullptr, ACT_NONE, 1));
-    OP3_TRY(gemm(st, Rs, LSTM, N, d_l1n, Rs, 1, io->h_out, LSTM, 0, g->ref_last_fc.w, LSTM, nullptr, ACT_NONE, 1));
-    OP3_TRY(colsum(st, N, Rs, d_l1n, Rs, g->ref_last_fc.b, 1));
+    OP3_TRY(gemm_wgrad(st, Rs, LSTM, N, d_l1n, Rs, io->h_out, LSTM, g->ref_last_fc.w, LSTM, g->ref_last_fc.b));
   }
   if (d_l2n) {
     OP3_TRY(gemm(st, N, LSTM, Rs, d_l2n, Rs, 0, p->ref_last_fc2.w, LSTM, 0, dh2, LSTM, nullptr, ACT_NONE, 1));
-    OP3_TRY(gemm(st, Rs, LSTM, N, d_l2n, Rs, 1, io->h_out, LSTM, 0, g->ref_last_fc2.w, LSTM, nullptr, ACT_NONE, 1));
-    OP3_TRY(colsum(st, N, Rs, d_l2n, Rs, g->ref_last_fc2.b, 1));
+    OP3_TRY(gemm_wgrad(st, Rs, LSTM, N, d_l2n, Rs, io->h_out, LSTM, g->ref_last_fc2.w, LSTM, g->ref_last_fc2.b));
   }
   // LSTM cell
   lstm_bwd_kernel<<<ceil_div(N * LSTM, 256), 256, 0, st>>>(N, A.gates, io->c, dh2, d_c, dgates, dc);
@@ -453,10 +451,8 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   OP3_LAUNCH_CHECK();
   OP3_TRY(gemm(st, N, XW, 4 * LSTM, dgates, 4 * LSTM, 0, p->lstm_w_ih, XW, 0, dX, XW, nullptr, ACT_NONE, 0));
   OP3_TRY(gemm(st, N, LSTM, 4 * LSTM, dgates, 4 * LSTM, 0, p->lstm_w_hh, LSTM, 0, dh, LSTM, nullptr, ACT_NONE, 1));
-  OP3_TRY(gemm(st, 4 * LSTM, XW, N, dgates, 4 * LSTM, 1, A.X, XW, 0, g->lstm_w_ih, XW, nullptr, ACT_NONE, 1));
-  OP3_TRY(gemm(st, 4 * LSTM, LSTM, N, dgates, 4 * LSTM, 1, io->h, LSTM, 0, g->lstm_w_hh, LSTM, nullptr, ACT_NONE, 1));
-  OP3_TRY(colsum(st, N, 4 * LSTM, dgates, 4 * LSTM, g->lstm_b_ih, 1));
-  OP3_TRY(colsum(st, N, 4 * LSTM, dgates, 4 * LSTM, g->lstm_b_hh, 1));
+  OP3_TRY(gemm_wgrad(st, 4 * LSTM, XW, N, dgates, 4 * LSTM, A.X, XW, g->lstm_w_ih, XW, g->lstm_b_ih));
+  OP3_TRY(gemm_wgrad(st, 4 * LSTM, LSTM, N, dgates, 4 * LSTM, io->h, LSTM, g->lstm_w_hh, LSTM, g->lstm_b_hh));
   // extras: LN1d parameter gradients and the direct paths into the previous state's lambdas / samples
   for (int j = 0; j < 2; ++j) {
     colsum_prod_kernel<<<ceil_div(Rs, 32), 256, 0, st>>>(N, Rs, dX + HID + j * Rs, XW, A.xn + j * Rs, 2 * Rs, g->ln1d_scale[j]);
@@ -474,8 +470,7 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   // FC (+ELU) on the pooled features
   OP3_TRY(act_backward(st, N, HID, dX, XW, A.X, XW, ACT_ELU));
   OP3_TRY(gemm(st, N, Rs, HID, dX, XW, 0, p->ref_fc.w, Rs, 0, dpool, Rs, nullptr, ACT_NONE, 0));
-  OP3_TRY(gemm(st, HID, Rs, N, dX, XW, 1, A.pooled, Rs, 0, g->ref_fc.w, Rs, nullptr, ACT_NONE, 1));
-  OP3_TRY(colsum(st, N, HID, dX, XW, g->ref_fc.b, 1));
+  OP3_TRY(gemm_wgrad(st, HID, Rs, N, dX, XW, A.pooled, Rs, g->ref_fc.w, Rs, g->ref_fc.b));
   // conv stack
   // fp16 mode: maxima of r1, r2 come from the forward pass (acts), those of g3, g2, g1 are recorded in slots 1..3 here
   const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
