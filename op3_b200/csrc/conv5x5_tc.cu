@@ -314,7 +314,286 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
   if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
+// =====================================================================================================================
+// "Quint-tap" fp16 variant (cin <= 32, 32 output channels per launch): the tensor core accepts one M=128 MMA per ~50 cycles
+// for ANY N <= 64 (measured in situ: 107 cycles for the N=64 + N=32 pair of one tap), so the kernel above pays per tap, not
+// per byte.  Here the five kx taps of a kernel row share ONE activation fetch: B = [w(kx=0); ...; w(kx=4)] is stacked along
+// N (N = 160) and the tap shift moves to the epilogue,
+//     D_kx[r] = sum_{ky,ci} w(ky,kx)[co][ci] * x[ci][r + ky*P]   (A operand: the tile shifted by ky*P only)
+//     out[p]  = sum_kx D_kx[p + kx]                               (lane shift inside the epilogue warp)
+// so a kernel row costs 3 MMAs (x_hi*w_hi, x_hi*w_lo, x_lo*w_hi, all into the same 160 TMEM columns) instead of 10.
+// Consequences: * a tile is 128 accumulator rows but only 124 outputs (rows 124..127 exist to be shifted into 120..123),
+//   tiles advance by 124 padded-linear pixels; * 160 columns per tile: a 3-slot accumulator ring filled TILE BY TILE, so
+//   both 16-channel K groups of a tile must be resident: the activations live in a RING in padded-linear pixel space
+//   ([hi/lo][4 k-chunks of 8 channels][6 chunk slots x 124 rows + 128 guard rows] x 16 B; every pixel is loaded, scaled and
+//   split once per image segment instead of 1.5x per halo group) and the weights are RESIDENT (100 KB, re-laid out from the
+//   ordinary fp16 slab by the prologue: [K group][ky][hi/lo][k-chunk][kx*32 + co]); * each CTA owns a contiguous range of
+//   the global tile sequence (balanced to one tile) and restarts the ring at image boundaries (3 extra chunks).
+// =====================================================================================================================
+constexpr int TQ_TS = 124;                          // outputs per tile
+constexpr int TQ_NSLOT = 6;                         // chunk slots in the ring: 4 in use by the current tile + 2 ahead
+constexpr int TQ_RING = TQ_NSLOT * TQ_TS;           // 744 rows
+constexpr int TQ_ROWS = TQ_RING + 128;              // + guard copy of rows [0, 128) for operands that wrap
+constexpr int TQ_PLANE = TQ_ROWS * 16;              // bytes
+constexpr int TQ_A_BYTES = 8 * TQ_PLANE;            // planes [hi/lo][k-chunk 0..3]
+constexpr int TQ_NQ = 160;                          // 5 taps x 32 output channels
+constexpr int TQ_W_SLAB = 2 * TQ_NQ * 16;           // one (K group, ky, hi/lo) slab: [k-chunk 2][160 rows][16 B]
+constexpr int TQ_W_BYTES = 2 * 5 * 2 * TQ_W_SLAB;
+constexpr int TQ_XCH = 4 * 2 * 10 * 16;             // floats per exchange buffer: [quad][half][(kx, lane < kx)][16]
+constexpr int TQ_SMEM = TQ_A_BYTES + TQ_W_BYTES + 2 * TQ_XCH * 4;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
+                   float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
+                   const float4* __restrict__ ref, const uint32_t* __restrict__ maxbits, const float* __restrict__ wscale) {
+  const int P = D + 4;
+  const int tiles_img = (D * P + TQ_TS - 1) / TQ_TS;
+  const long long total = (long long)N * tiles_img;
+  const int g0 = (int)(total * blockIdx.x / gridDim.x), g1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  const int ngroups = (in.total_chunks + 3) / 4;           // K groups of 16 channels (1 or 2)
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* a_s = smem_raw;
+  uint4* w_s = reinterpret_cast<uint4*>(smem_raw + TQ_A_BYTES);
+  float* xch = reinterpret_cast<float*>(smem_raw + TQ_A_BYTES + TQ_W_BYTES);
+  __shared__ uint64_t full_bar[TQ_NSLOT], empty_bar[TQ_NSLOT], acc_full[3], acc_empty[3];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[32];
+
+  if (tid < 32) s_bias[tid] = (bias != nullptr && tid < cout_real) ? bias[tid] : 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < TQ_NSLOT; ++s) { mbar_init(&full_bar[s], LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS * 32); }
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
+  {   // resident weights: ordinary slab [K group][tap][k-chunk][64 rows: hi 0..31, lo 32..63] -> [K group][ky][hi/lo][k-chunk][kx*32 + co]
+    const uint4* wsrc = reinterpret_cast<const uint4*>(wt);
+    for (int e = tid; e < ngroups * 25 * 2 * 64; e += TC_THREADS) {
+      const int row64 = e & 63, kc = (e >> 6) & 1, tap = (e >> 7) % 25, cg = e / (128 * 25);
+      const int hl = row64 >> 5, co = row64 & 31, ky = tap / 5, kx = tap - 5 * ky;
+      w_s[((((cg * 5 + ky) * 2 + hl) * 2 + kc) * TQ_NQ) + kx * 32 + co] = __ldg(wsrc + e);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp >= LOAD_WARP0) {
+    // ===================== loaders: one chunk of 124 pixels x (2 * ngroups) k-chunks per step =====================
+    const int lt = tid - LOAD_WARP0 * 32;
+    const int ntask = TQ_TS * 2 * ngroups;                 // task = (pixel, k-chunk of 8 channels)
+    int c = 0;                                             // running chunk counter of this CTA
+    for (int g = g0; g < g1;) {
+      const int n = g / tiles_img, ta = g - n * tiles_img;
+      const int T = min(tiles_img - ta, g1 - g);
+      const float sc = __uint_as_float(f16_scale_bits(maxbits[n]));
+      for (int jc = 0; jc < T + 3; ++jc, ++c) {
+        const int slot = c % TQ_NSLOT;
+        float4 v[3][2];
+        int rowi[3], kcs[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int e = lt + u * LOAD_THREADS;
+          v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          rowi[u] = -1; kcs[u] = 0;
+          if (e < ntask) {
+            const int kc = e / TQ_TS, i = e - kc * TQ_TS;
+            rowi[u] = i; kcs[u] = kc;
+            const int q = TQ_TS * (ta + jc) + i;
+            const int r = q / P, iy = r - 2, ix = q - r * P - 2;
+            if ((unsigned)iy < (unsigned)D && (unsigned)ix < (unsigned)D) {
+              const size_t off = (size_t)iy * D + ix;
+              if (2 * kc < in.total_chunks) v[u][0] = __ldg(tc_src_chunk_ptr(in, 2 * kc, n, D) + off);
+              if (2 * kc + 1 < in.total_chunks) v[u][1] = __ldg(tc_src_chunk_ptr(in, 2 * kc + 1, n, D) + off);
+            }
+          }
+        }
+        if (c >= TQ_NSLOT) mbar_wait(&empty_bar[slot], ((c / TQ_NSLOT) - 1) & 1);
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (rowi[u] >= 0) {
+            uint4 hi, lo;
+            f16_split2(v[u][0].x * sc, v[u][0].y * sc, hi.x, lo.x);
+            f16_split2(v[u][0].z * sc, v[u][0].w * sc, hi.y, lo.y);
+            f16_split2(v[u][1].x * sc, v[u][1].y * sc, hi.z, lo.z);
+            f16_split2(v[u][1].z * sc, v[u][1].w * sc, hi.w, lo.w);
+            const int row = slot * TQ_TS + rowi[u];
+            uint4* ph = reinterpret_cast<uint4*>(a_s + (size_t)kcs[u] * TQ_PLANE);
+            uint4* pl = reinterpret_cast<uint4*>(a_s + (size_t)(4 + kcs[u]) * TQ_PLANE);
+            ph[row] = hi; pl[row] = lo;
+            if (row < 128) { ph[row + TQ_RING] = hi; pl[row + TQ_RING] = lo; }
+          }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[slot]);
+      }
+      g += T;
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, TQ_NQ);
+      const uint64_t ad = make_smem_desc(smem_u32(a_s), TQ_ROWS, 8);
+      const uint64_t bd = make_smem_desc(smem_u32(w_s), TQ_NQ, 8);
+      const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
+      const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
+      int c_run = 0, j = 0;
+#ifdef OP3_TC_TRACE
+      unsigned long long t_full = 0, t_acc = 0, n_mma = 0;
+      const unsigned long long t_begin = clock64();
+#endif
+      for (int g = g0; g < g1;) {
+        const int n = g / tiles_img, ta = g - n * tiles_img;
+        const int T = min(tiles_img - ta, g1 - g);
+        const int c0 = c_run;
+        int ready = c0 - 1;                                // last chunk known to be in shared memory
+        for (int tau = 0; tau < T; ++tau, ++j) {
+          const int slot = j % 3;
+#ifdef OP3_TC_TRACE
+          unsigned long long tw = clock64();
+#endif
+          if (j >= 3) mbar_wait(&acc_empty[slot], ((j / 3) - 1) & 1);
+#ifdef OP3_TC_TRACE
+          t_acc += clock64() - tw; tw = clock64();
+#endif
+          while (ready < c0 + tau + 3) {
+            ++ready;
+            mbar_wait(&full_bar[ready % TQ_NSLOT], (ready / TQ_NSLOT) & 1);
+          }
+#ifdef OP3_TC_TRACE
+          t_full += clock64() - tw; n_mma += 15 * ngroups;
+#endif
+          tc_fence_after();
+          const uint32_t dcol = tmem_base + (uint32_t)(slot * TQ_NQ);
+          const int rowbase = ((c0 + tau) % TQ_NSLOT) * TQ_TS;
+          for (int cg = 0; cg < ngroups; ++cg) {
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+              int row = rowbase + ky * P;
+              if (row >= TQ_RING) row -= TQ_RING;
+              const uint32_t a_hi_op = a_lo32 + (uint32_t)((2 * cg) * TQ_ROWS + row);          // 16-byte units
+              const uint32_t a_lo_op = a_lo32 + (uint32_t)((4 + 2 * cg) * TQ_ROWS + row);
+              const uint32_t b_hi_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 0) * 2 * TQ_NQ);
+              const uint32_t b_lo_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 1) * 2 * TQ_NQ);
+              mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, (cg > 0 || ky > 0) ? 1u : 0u);
+              mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
+              mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+            }
+          }
+          tc_commit(&empty_bar[(c0 + tau) % TQ_NSLOT]);    // chunk c0+tau is dead once these MMAs have read it
+          if (tau == T - 1)
+            for (int x = 0; x < 3; ++x) tc_commit(&empty_bar[(c0 + T + x) % TQ_NSLOT]);   // the tail halo chunks of the item
+          tc_commit(&acc_full[slot]);
+        }
+        c_run = c0 + T + 3;
+        g += T;
+      }
+#ifdef OP3_TC_TRACE
+      if (blockIdx.x < 256) {
+        atomicAdd(&g_tc_trace[blockIdx.x][0], t_full); atomicAdd(&g_tc_trace[blockIdx.x][1], t_acc);
+        atomicAdd(&g_tc_trace[blockIdx.x][2], clock64() - t_begin); atomicAdd(&g_tc_trace[blockIdx.x][3], n_mma);
+      }
+#endif
+    }
+  } else {
+    // ===================== epilogue: warp % 4 = TMEM lane quadrant, warp / 4 = half of the 32 output channels =====================
+    const int quad = warp & 3, half = warp >> 2;
+    const size_t plane = (size_t)D * D;
+    int j = 0;
+    for (int g = g0; g < g1;) {
+      const int n = g / tiles_img, ta = g - n * tiles_img;
+      const int T = min(tiles_img - ta, g1 - g);
+      const float inv_scale = 1.f / (__uint_as_float(f16_scale_bits(maxbits[n])) * __ldg(wscale));   // powers of two: exact
+      float omax = 0.f;
+      for (int tau = 0; tau < T; ++tau, ++j) {
+        const int slot = j % 3;
+        const int r = quad * 32 + lane;
+        const int p = TQ_TS * (ta + tau) + r;
+        const int y = p / P, x = p - y * P;
+        const bool valid = r < TQ_TS && y < D && x < D;
+        const size_t obase = (((size_t)n * out_planes + out_chunk0) * D + (valid ? y : 0)) * D + (valid ? x : 0);
+        float4 ra[4];
+        if (epi == EPI_MUL_ELUGRAD) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c4 = 4 * half + i;
+            ra[i] = (valid && c4 < out_chunks) ? __ldg(&ref[obase + c4 * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+        mbar_wait(&acc_full[slot], (j / 3) & 1);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TQ_NQ + 16 * half);
+        float* xb = xch + (j & 1) * TQ_XCH;
+        // rows shifted across a quadrant boundary travel through shared memory: lane l < kx of D_kx is read by lane
+        // 32 - kx + l of the previous quadrant
+        float v[16];
+#pragma unroll
+        for (int kx = 1; kx < 5; ++kx) {
+          tmem_ld16(trow + 32 * kx, v);
+          tmem_ld_wait();
+          if (lane < kx) {
+            float* dst = xb + (((quad * 2 + half) * 10) + (kx * (kx - 1)) / 2 + lane) * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = v[i];
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
+        float acc[16];
+        tmem_ld16(trow, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int kx = 1; kx < 5; ++kx) {
+          tmem_ld16(trow + 32 * kx, v);
+          tmem_ld_wait();
+          const bool wrap = lane >= 32 - kx;
+          const float* srcx = xb + ((((quad + 1) & 3) * 2 + half) * 10 + (kx * (kx - 1)) / 2 + (lane + kx - 32)) * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float sft = __shfl_down_sync(0xffffffffu, v[i], kx);
+            if (wrap) sft = quad < 3 ? srcx[i] : 0.f;
+            acc[i] += sft;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[slot]);                     // this thread is done reading the accumulator slot
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c4 = 4 * half + i;
+            if (c4 >= out_chunks) continue;
+            float4 o = make_float4(acc[4 * i] * inv_scale + s_bias[16 * half + 4 * i],
+                                   acc[4 * i + 1] * inv_scale + s_bias[16 * half + 4 * i + 1],
+                                   acc[4 * i + 2] * inv_scale + s_bias[16 * half + 4 * i + 2],
+                                   acc[4 * i + 3] * inv_scale + s_bias[16 * half + 4 * i + 3]);
+            if (epi == EPI_ELU) {
+              o.x = elu_f(o.x); o.y = elu_f(o.y); o.z = elu_f(o.z); o.w = elu_f(o.w);
+            } else if (epi == EPI_MUL_ELUGRAD) {
+              o.x *= elu_grad_from_out(ra[i].x); o.y *= elu_grad_from_out(ra[i].y);
+              o.z *= elu_grad_from_out(ra[i].z); o.w *= elu_grad_from_out(ra[i].w);
+            }
+            out[obase + c4 * plane] = o;
+            omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          }
+        }
+      }
+      if (in.out_maxbits != nullptr) {                      // magnitudes of the written tensor, for its consumer's operand scale
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+        if (lane == 0 && __float_as_uint(omax) > __ldcg(&in.out_maxbits[n])) atomicMax(&in.out_maxbits[n], __float_as_uint(omax));
+      }
+      g += T;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
+}
+
 int g_num_sms = 0;
+bool g_tc_quint = true;   // op3_debug_set_quint(0) falls back to the per-tap kernel (A/B timing, tests)
 
 // per-image largest magnitude of a conv input (fp32 bit pattern; non-negative floats order like unsigned ints)
 __global__ void __launch_bounds__(256) tc_absmax_kernel(ConvInput in, int D, uint32_t* __restrict__ maxbits) {
@@ -366,6 +645,31 @@ int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* w
   return OP3_OK;
 }
 
+int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* wt, const float* bias, int cout_real,
+               float4* out, int out_planes, int out_chunk0, int out_chunks, int epi, const float4* ref,
+               const uint32_t* maxbits, const float* wscale) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    OP3_CHECK(cudaGetDevice(&dev));
+    OP3_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int P = D + 4;
+  const long long total = (long long)N * ((D * P + TQ_TS - 1) / TQ_TS);
+  const int grid = total < g_num_sms ? (int)total : g_num_sms;
+  conv5x5_tcq_kernel<<<grid, TC_THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
+                                                        out_chunks, epi, ref, maxbits, wscale);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+// the quint-tap kernel needs 128 + 4*P rows inside four 124-row chunks and at most two 16-channel K groups
+inline bool tcq_fits(int D, int total_chunks) { return 128 + 4 * (D + 4) <= 4 * TQ_TS && total_chunks <= 8; }
+
 }  // namespace
 
 #ifdef OP3_TC_TRACE
@@ -375,6 +679,8 @@ extern "C" int op3_debug_tc_trace(unsigned long long* out /*[256][4] host*/, int
   return 0;
 }
 #endif
+
+extern "C" int op3_debug_set_quint(int on) { g_tc_quint = on != 0; return 0; }
 
 int tc_nout(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 
@@ -416,7 +722,15 @@ int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvI
     const int h_nout = nout == 64 ? 32 : nout;
     const size_t slab = conv5x5_tc_f16_slab_floats(in.total_chunks * 4, h_nout);
     if (nout == 16) return launch_tc<16, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
-    if (nout == 32) return launch_tc<32, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
+    const bool quint = tcq_fits(D, in.total_chunks) && g_tc_quint;
+    if (nout == 32)
+      return quint ? launch_tcq(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4)
+                   : launch_tc<32, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
+    if (quint) {
+      OP3_TRY(launch_tcq(st, N, D, in, wt, bias, 32, out, planes, 0, 8, epi, elu_ref, maxbits, wt + slab - 4));
+      return launch_tcq(st, N, D, in, wt + slab, bias ? bias + 32 : nullptr, cout - 32, out, planes, 8, planes - 8, epi, elu_ref,
+                        maxbits, wt + 2 * slab - 4);
+    }
     OP3_TRY((launch_tc<32, 2>(st, N, D, in, wt, bias, 32, out, planes, 0, 8, epi, elu_ref, maxbits, wt + slab - 4)));
     return launch_tc<32, 2>(st, N, D, in, wt + slab, bias ? bias + 32 : nullptr, cout - 32, out, planes, 8, planes - 8, epi, elu_ref,
                             maxbits, wt + 2 * slab - 4);
