@@ -330,6 +330,11 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
 //   ordinary fp16 slab by the prologue: [K group][ky][hi/lo][k-chunk][kx*32 + co]); * each CTA owns a contiguous range of
 //   the global tile sequence (balanced to one tile) and restarts the ring at image boundaries (3 extra chunks).
 // =====================================================================================================================
+// ELU of the quint-tap epilogue: exp(x) - 1 with the full-accuracy expf (absolute error <= 1 ulp of 1.0 = 6e-8, far below
+// the fp16-split products feeding it) instead of expm1f, whose ~20 instructions per channel made the epilogue -- 32
+// channels x 124 pixels per tile -- the kernel's bottleneck once the tensor core needed only 2400 cycles per tile.
+__device__ __forceinline__ float elu_tc(float x) { return x > 0.f ? x : expf(x) - 1.f; }
+
 constexpr int TQ_TS = 124;                          // outputs per tile
 constexpr int TQ_NSLOT = 6;                         // chunk slots in the ring: 4 in use by the current tile + 2 ahead
 constexpr int TQ_RING = TQ_NSLOT * TQ_TS;           // 744 rows
@@ -364,7 +369,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   if (tid < 32) s_bias[tid] = (bias != nullptr && tid < cout_real) ? bias[tid] : 0.f;
   if (tid == 0) {
     for (int s = 0; s < TQ_NSLOT; ++s) { mbar_init(&full_bar[s], LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS * 32); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS * 16); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
@@ -384,51 +389,71 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
 
   if (warp >= LOAD_WARP0) {
     // ===================== loaders: one chunk of 124 pixels x (2 * ngroups) k-chunks per step =====================
+    // A thread owns up to three fixed (pixel-in-chunk, k-chunk) tasks; the loads of chunk c+1 are in flight while chunk c
+    // is converted and stored (one exposed global latency per item, not per chunk); pixel coordinates advance incrementally.
     const int lt = tid - LOAD_WARP0 * 32;
     const int ntask = TQ_TS * 2 * ngroups;                 // task = (pixel, k-chunk of 8 channels)
+    int ti[3], tk[3];
+    bool tact[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int e = lt + u * LOAD_THREADS;
+      tact[u] = e < ntask;
+      tk[u] = tact[u] ? e / TQ_TS : 0;
+      ti[u] = e - (e / TQ_TS) * TQ_TS;
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     int c = 0;                                             // running chunk counter of this CTA
     for (int g = g0; g < g1;) {
       const int n = g / tiles_img, ta = g - n * tiles_img;
       const int T = min(tiles_img - ta, g1 - g);
       const float sc = __uint_as_float(f16_scale_bits(maxbits[n]));
-      for (int jc = 0; jc < T + 3; ++jc, ++c) {
-        const int slot = c % TQ_NSLOT;
-        float4 v[3][2];
-        int rowi[3], kcs[3];
+      const float4* s0[3];
+      const float4* s1[3];
+      int iy[3], ix[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        s0[u] = (tact[u] && 2 * tk[u] < in.total_chunks) ? tc_src_chunk_ptr(in, 2 * tk[u], n, D) : nullptr;
+        s1[u] = (tact[u] && 2 * tk[u] + 1 < in.total_chunks) ? tc_src_chunk_ptr(in, 2 * tk[u] + 1, n, D) : nullptr;
+        const int q = TQ_TS * ta + ti[u];
+        const int r = q / P;
+        iy[u] = r - 2; ix[u] = q - r * P - 2;
+      }
+      float4 v[3][2], vn[3][2];
+      auto load_chunk = [&](float4 (*dst)[2]) {            // loads the chunk at the current coordinates, then advances them
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          const int e = lt + u * LOAD_THREADS;
-          v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          rowi[u] = -1; kcs[u] = 0;
-          if (e < ntask) {
-            const int kc = e / TQ_TS, i = e - kc * TQ_TS;
-            rowi[u] = i; kcs[u] = kc;
-            const int q = TQ_TS * (ta + jc) + i;
-            const int r = q / P, iy = r - 2, ix = q - r * P - 2;
-            if ((unsigned)iy < (unsigned)D && (unsigned)ix < (unsigned)D) {
-              const size_t off = (size_t)iy * D + ix;
-              if (2 * kc < in.total_chunks) v[u][0] = __ldg(tc_src_chunk_ptr(in, 2 * kc, n, D) + off);
-              if (2 * kc + 1 < in.total_chunks) v[u][1] = __ldg(tc_src_chunk_ptr(in, 2 * kc + 1, n, D) + off);
-            }
-          }
+          const bool ok = (unsigned)iy[u] < (unsigned)D && (unsigned)ix[u] < (unsigned)D;
+          const size_t off = (size_t)iy[u] * D + ix[u];
+          dst[u][0] = (ok && s0[u]) ? __ldg(s0[u] + off) : zero4;
+          dst[u][1] = (ok && s1[u]) ? __ldg(s1[u] + off) : zero4;
+          ix[u] += TQ_TS;
+          while (ix[u] >= P - 2) { ix[u] -= P; ++iy[u]; }
         }
+      };
+      load_chunk(v);
+      for (int jc = 0; jc < T + 3; ++jc, ++c) {
+        const int slot = c % TQ_NSLOT;
+        if (jc + 1 < T + 3) load_chunk(vn);
         if (c >= TQ_NSLOT) mbar_wait(&empty_bar[slot], ((c / TQ_NSLOT) - 1) & 1);
 #pragma unroll
         for (int u = 0; u < 3; ++u)
-          if (rowi[u] >= 0) {
+          if (tact[u]) {
             uint4 hi, lo;
             f16_split2(v[u][0].x * sc, v[u][0].y * sc, hi.x, lo.x);
             f16_split2(v[u][0].z * sc, v[u][0].w * sc, hi.y, lo.y);
             f16_split2(v[u][1].x * sc, v[u][1].y * sc, hi.z, lo.z);
             f16_split2(v[u][1].z * sc, v[u][1].w * sc, hi.w, lo.w);
-            const int row = slot * TQ_TS + rowi[u];
-            uint4* ph = reinterpret_cast<uint4*>(a_s + (size_t)kcs[u] * TQ_PLANE);
-            uint4* pl = reinterpret_cast<uint4*>(a_s + (size_t)(4 + kcs[u]) * TQ_PLANE);
+            const int row = slot * TQ_TS + ti[u];
+            uint4* ph = reinterpret_cast<uint4*>(a_s + (size_t)tk[u] * TQ_PLANE);
+            uint4* pl = reinterpret_cast<uint4*>(a_s + (size_t)(4 + tk[u]) * TQ_PLANE);
             ph[row] = hi; pl[row] = lo;
             if (row < 128) { ph[row + TQ_RING] = hi; pl[row + TQ_RING] = lo; }
           }
         fence_proxy_async();
         mbar_arrive(&full_bar[slot]);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) { v[u][0] = vn[u][0]; v[u][1] = vn[u][1]; }
       }
       g += T;
     }
@@ -469,18 +494,30 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
           tc_fence_after();
           const uint32_t dcol = tmem_base + (uint32_t)(slot * TQ_NQ);
           const int rowbase = ((c0 + tau) % TQ_NSLOT) * TQ_TS;
-          for (int cg = 0; cg < ngroups; ++cg) {
+          // operand start rows of the five kernel rows (ring wrap), then a fully unrolled issue sequence whose descriptor
+          // words are the tile's five row offsets plus compile-time constants: the issuing thread must stay ahead of an
+          // 80-cycle MMA while sharing its scheduler with three busy warps
+          uint32_t arow[5];
 #pragma unroll
-            for (int ky = 0; ky < 5; ++ky) {
-              int row = rowbase + ky * P;
-              if (row >= TQ_RING) row -= TQ_RING;
-              const uint32_t a_hi_op = a_lo32 + (uint32_t)((2 * cg) * TQ_ROWS + row);          // 16-byte units
-              const uint32_t a_lo_op = a_lo32 + (uint32_t)((4 + 2 * cg) * TQ_ROWS + row);
-              const uint32_t b_hi_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 0) * 2 * TQ_NQ);
-              const uint32_t b_lo_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 1) * 2 * TQ_NQ);
-              mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, (cg > 0 || ky > 0) ? 1u : 0u);
-              mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
-              mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+          for (int ky = 0; ky < 5; ++ky) {
+            int row = rowbase + ky * P;
+            if (row >= TQ_RING) row -= TQ_RING;
+            arow[ky] = a_lo32 + (uint32_t)row;
+          }
+#pragma unroll
+          for (int cg = 0; cg < 2; ++cg) {
+            if (cg < ngroups) {
+#pragma unroll
+              for (int ky = 0; ky < 5; ++ky) {
+                const uint32_t a_hi_op = arow[ky] + (uint32_t)((2 * cg) * TQ_ROWS);             // 16-byte units
+                const uint32_t a_lo_op = arow[ky] + (uint32_t)((4 + 2 * cg) * TQ_ROWS);
+                const uint32_t b_hi_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 0) * 2 * TQ_NQ);
+                const uint32_t b_lo_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 1) * 2 * TQ_NQ);
+                if (cg == 0 && ky == 0) mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, 0u);
+                else mma_f16_acc(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc);
+                mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
+                mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+              }
             }
           }
           tc_commit(&empty_bar[(c0 + tau) % TQ_NSLOT]);    // chunk c0+tau is dead once these MMAs have read it
@@ -499,9 +536,12 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
 #endif
     }
   } else {
-    // ===================== epilogue: warp % 4 = TMEM lane quadrant, warp / 4 = half of the 32 output channels =====================
-    const int quad = warp & 3, half = warp >> 2;
+    // ===================== epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate tiles, so a
+    // tile's epilogue may last two tile times; each warp handles the 32 output channels in two passes of 16 =====================
+    const int quad = warp & 3, grp = warp >> 2;
     const size_t plane = (size_t)D * D;
+    float* xb = xch + grp * TQ_XCH;
+    const float m1 = lane < 31 ? 1.f : 0.f, m2 = lane < 30 ? 1.f : 0.f, m3 = lane < 29 ? 1.f : 0.f, m4 = lane < 28 ? 1.f : 0.f;
     int j = 0;
     for (int g = g0; g < g1;) {
       const int n = g / tiles_img, ta = g - n * tiles_img;
@@ -509,75 +549,103 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
       const float inv_scale = 1.f / (__uint_as_float(f16_scale_bits(maxbits[n])) * __ldg(wscale));   // powers of two: exact
       float omax = 0.f;
       for (int tau = 0; tau < T; ++tau, ++j) {
+        if ((j & 1) != grp) continue;
         const int slot = j % 3;
         const int r = quad * 32 + lane;
         const int p = TQ_TS * (ta + tau) + r;
         const int y = p / P, x = p - y * P;
         const bool valid = r < TQ_TS && y < D && x < D;
         const size_t obase = (((size_t)n * out_planes + out_chunk0) * D + (valid ? y : 0)) * D + (valid ? x : 0);
-        float4 ra[4];
+        float4 ra[8];
         if (epi == EPI_MUL_ELUGRAD) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c4 = 4 * half + i;
-            ra[i] = (valid && c4 < out_chunks) ? __ldg(&ref[obase + c4 * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
-          }
+          for (int i = 0; i < 8; ++i) ra[i] = (valid && i < out_chunks) ? __ldg(&ref[obase + i * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
         mbar_wait(&acc_full[slot], (j / 3) & 1);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TQ_NQ + 16 * half);
-        float* xb = xch + (j & 1) * TQ_XCH;
-        // rows shifted across a quadrant boundary travel through shared memory: lane l < kx of D_kx is read by lane
-        // 32 - kx + l of the previous quadrant
-        float v[16];
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TQ_NQ);
+        // Every accumulator value is read from TMEM once, two 16-column groups per wait (TMEM load latency is long while
+        // the tensor core is busy; one wait per load made the epilogue the bottleneck).  out[p] = sum_kx D_kx[p + kx]: the
+        // shift is a warp shuffle; the rows that cross a quadrant boundary (lane l < kx of D_kx, read by lane 32 - kx + l of
+        // the previous quadrant) travel through shared memory and are added after the group barrier.
+        float acc[2][16];
 #pragma unroll
-        for (int kx = 1; kx < 5; ++kx) {
-          tmem_ld16(trow + 32 * kx, v);
+        for (int half = 0; half < 2; ++half) {
+          float v1[16], v2[16];
+          tmem_ld16(trow + 16 * half, acc[half]);
+          tmem_ld16(trow + 32 + 16 * half, v1);
+          tmem_ld16(trow + 64 + 16 * half, v2);
           tmem_ld_wait();
-          if (lane < kx) {
-            float* dst = xb + (((quad * 2 + half) * 10) + (kx * (kx - 1)) / 2 + lane) * 16;
+          float* dst = xb + ((quad * 2 + half) * 10) * 16;
+          if (lane < 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[i] = v[i];
+            for (int i = 0; i < 16; ++i) dst[(0 + lane) * 16 + i] = v1[i];
           }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
-        float acc[16];
-        tmem_ld16(trow, acc);
-        tmem_ld_wait();
+          if (lane < 2) {
 #pragma unroll
-        for (int kx = 1; kx < 5; ++kx) {
-          tmem_ld16(trow + 32 * kx, v);
+            for (int i = 0; i < 16; ++i) dst[(1 + lane) * 16 + i] = v2[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {         // out-of-range shuffles return the caller's own (finite) value: masked by 0
+            acc[half][i] = fmaf(__shfl_down_sync(0xffffffffu, v1[i], 1), m1, acc[half][i]);
+            acc[half][i] = fmaf(__shfl_down_sync(0xffffffffu, v2[i], 2), m2, acc[half][i]);
+          }
+          tmem_ld16(trow + 96 + 16 * half, v1);
+          tmem_ld16(trow + 128 + 16 * half, v2);
           tmem_ld_wait();
-          const bool wrap = lane >= 32 - kx;
-          const float* srcx = xb + ((((quad + 1) & 3) * 2 + half) * 10 + (kx * (kx - 1)) / 2 + (lane + kx - 32)) * 16;
+          if (lane < 3) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[(3 + lane) * 16 + i] = v1[i];
+          }
+          if (lane < 4) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[(6 + lane) * 16 + i] = v2[i];
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float sft = __shfl_down_sync(0xffffffffu, v[i], kx);
-            if (wrap) sft = quad < 3 ? srcx[i] : 0.f;
-            acc[i] += sft;
+            acc[half][i] = fmaf(__shfl_down_sync(0xffffffffu, v1[i], 3), m3, acc[half][i]);
+            acc[half][i] = fmaf(__shfl_down_sync(0xffffffffu, v2[i], 4), m4, acc[half][i]);
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[slot]);                     // this thread is done reading the accumulator slot
-        if (valid) {
+        mbar_arrive(&acc_empty[slot]);                       // every TMEM read of this tile is done
+        asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory");      // the four warps of this group
+        if (quad < 3 && lane >= 28) {                        // rows whose shifted sources live in the next quadrant
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c4 = 4 * half + i;
-            if (c4 >= out_chunks) continue;
-            float4 o = make_float4(acc[4 * i] * inv_scale + s_bias[16 * half + 4 * i],
-                                   acc[4 * i + 1] * inv_scale + s_bias[16 * half + 4 * i + 1],
-                                   acc[4 * i + 2] * inv_scale + s_bias[16 * half + 4 * i + 2],
-                                   acc[4 * i + 3] * inv_scale + s_bias[16 * half + 4 * i + 3]);
-            if (epi == EPI_ELU) {
-              o.x = elu_f(o.x); o.y = elu_f(o.y); o.z = elu_f(o.z); o.w = elu_f(o.w);
-            } else if (epi == EPI_MUL_ELUGRAD) {
-              o.x *= elu_grad_from_out(ra[i].x); o.y *= elu_grad_from_out(ra[i].y);
-              o.z *= elu_grad_from_out(ra[i].z); o.w *= elu_grad_from_out(ra[i].w);
-            }
-            out[obase + c4 * plane] = o;
-            omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          for (int half = 0; half < 2; ++half) {
+            const float* src = xb + (((quad + 1) * 2 + half) * 10) * 16;
+#pragma unroll
+            for (int kx = 1; kx < 5; ++kx)
+              if (lane >= 32 - kx) {
+                const float* sr = src + ((kx * (kx - 1)) / 2 + (lane + kx - 32)) * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[half][i] += sr[i];
+              }
           }
         }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c4 = 4 * half + i;
+              if (c4 >= out_chunks) continue;
+              float4 o = make_float4(acc[half][4 * i] * inv_scale + s_bias[16 * half + 4 * i],
+                                     acc[half][4 * i + 1] * inv_scale + s_bias[16 * half + 4 * i + 1],
+                                     acc[half][4 * i + 2] * inv_scale + s_bias[16 * half + 4 * i + 2],
+                                     acc[half][4 * i + 3] * inv_scale + s_bias[16 * half + 4 * i + 3]);
+              if (epi == EPI_ELU) {
+                o.x = elu_tc(o.x); o.y = elu_tc(o.y); o.z = elu_tc(o.z); o.w = elu_tc(o.w);
+              } else if (epi == EPI_MUL_ELUGRAD) {
+                o.x *= elu_grad_from_out(ra[c4].x); o.y *= elu_grad_from_out(ra[c4].y);
+                o.z *= elu_grad_from_out(ra[c4].z); o.w *= elu_grad_from_out(ra[c4].w);
+              }
+              out[obase + c4 * plane] = o;
+              omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory");      // exchange rows read before the next tile rewrites them
       }
       if (in.out_maxbits != nullptr) {                      // magnitudes of the written tensor, for its consumer's operand scale
 #pragma unroll
