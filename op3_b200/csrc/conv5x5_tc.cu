@@ -330,10 +330,10 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
 //   ordinary fp16 slab by the prologue: [K group][ky][hi/lo][k-chunk][kx*32 + co]); * each CTA owns a contiguous range of
 //   the global tile sequence (balanced to one tile) and restarts the ring at image boundaries (3 extra chunks).
 // =====================================================================================================================
-// ELU of the quint-tap epilogue: exp(x) - 1 with the full-accuracy expf (absolute error <= 1 ulp of 1.0 = 6e-8, far below
-// the fp16-split products feeding it) instead of expm1f, whose ~20 instructions per channel made the epilogue -- 32
-// channels x 124 pixels per tile -- the kernel's bottleneck once the tensor core needed only 2400 cycles per tile.
-__device__ __forceinline__ float elu_tc(float x) { return x > 0.f ? x : expf(x) - 1.f; }
+// ELU of the quint-tap epilogue: ex2.approx(x * log2 e) - 1 (absolute error <= ~2e-7 for x <= 0, below the 2e-6 floor of the
+// fp16-split products feeding it) instead of expm1f, whose ~20 instructions per channel made the epilogue -- 32 channels x
+// 124 pixels per tile -- the kernel's bottleneck once the tensor core needed only 2400 cycles per tile.
+__device__ __forceinline__ float elu_tc(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
 constexpr int TQ_TS = 124;                          // outputs per tile
 constexpr int TQ_NSLOT = 6;                         // chunk slots in the ring: 4 in use by the current tile + 2 ahead
@@ -541,6 +541,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     const int quad = warp & 3, grp = warp >> 2;
     const size_t plane = (size_t)D * D;
     float* xb = xch + grp * TQ_XCH;
+    const bool want_max = in.out_maxbits != nullptr;
     const float m1 = lane < 31 ? 1.f : 0.f, m2 = lane < 30 ? 1.f : 0.f, m3 = lane < 29 ? 1.f : 0.f, m4 = lane < 28 ? 1.f : 0.f;
     int j = 0;
     for (int g = g0; g < g1;) {
@@ -576,14 +577,14 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
           tmem_ld16(trow + 32 + 16 * half, v1);
           tmem_ld16(trow + 64 + 16 * half, v2);
           tmem_ld_wait();
-          float* dst = xb + ((quad * 2 + half) * 10) * 16;
+          float4* dst4 = reinterpret_cast<float4*>(xb + ((quad * 2 + half) * 10) * 16);
           if (lane < 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(0 + lane) * 16 + i] = v1[i];
+            for (int i = 0; i < 4; ++i) dst4[(0 + lane) * 4 + i] = make_float4(v1[4 * i], v1[4 * i + 1], v1[4 * i + 2], v1[4 * i + 3]);
           }
           if (lane < 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(1 + lane) * 16 + i] = v2[i];
+            for (int i = 0; i < 4; ++i) dst4[(1 + lane) * 4 + i] = make_float4(v2[4 * i], v2[4 * i + 1], v2[4 * i + 2], v2[4 * i + 3]);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {         // out-of-range shuffles return the caller's own (finite) value: masked by 0
@@ -595,11 +596,11 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
           tmem_ld_wait();
           if (lane < 3) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(3 + lane) * 16 + i] = v1[i];
+            for (int i = 0; i < 4; ++i) dst4[(3 + lane) * 4 + i] = make_float4(v1[4 * i], v1[4 * i + 1], v1[4 * i + 2], v1[4 * i + 3]);
           }
           if (lane < 4) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(6 + lane) * 16 + i] = v2[i];
+            for (int i = 0; i < 4; ++i) dst4[(6 + lane) * 4 + i] = make_float4(v2[4 * i], v2[4 * i + 1], v2[4 * i + 2], v2[4 * i + 3]);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -613,13 +614,16 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         if (quad < 3 && lane >= 28) {                        // rows whose shifted sources live in the next quadrant
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            const float* src = xb + (((quad + 1) * 2 + half) * 10) * 16;
+            const float4* src = reinterpret_cast<const float4*>(xb + (((quad + 1) * 2 + half) * 10) * 16);
 #pragma unroll
             for (int kx = 1; kx < 5; ++kx)
               if (lane >= 32 - kx) {
-                const float* sr = src + ((kx * (kx - 1)) / 2 + (lane + kx - 32)) * 16;
+                const float4* sr = src + ((kx * (kx - 1)) / 2 + (lane + kx - 32)) * 4;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[half][i] += sr[i];
+                for (int i = 0; i < 4; ++i) {
+                  const float4 t = sr[i];
+                  acc[half][4 * i] += t.x; acc[half][4 * i + 1] += t.y; acc[half][4 * i + 2] += t.z; acc[half][4 * i + 3] += t.w;
+                }
               }
           }
         }
@@ -641,7 +645,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
                 o.z *= elu_grad_from_out(ra[c4].z); o.w *= elu_grad_from_out(ra[c4].w);
               }
               out[obase + c4 * plane] = o;
-              omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+              if (want_max) omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
             }
           }
         }
