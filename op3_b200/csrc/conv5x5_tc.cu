@@ -665,7 +665,6 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
 }
 
 int g_num_sms = 0;
-bool g_tc_quint = true;   // op3_debug_set_quint(0) falls back to the per-tap kernel (A/B timing, tests)
 
 // per-image largest magnitude of a conv input (fp32 bit pattern; non-negative floats order like unsigned ints)
 __global__ void __launch_bounds__(256) tc_absmax_kernel(ConvInput in, int D, uint32_t* __restrict__ maxbits) {
@@ -739,10 +738,10 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
   OP3_LAUNCH_CHECK();
   return OP3_OK;
 }
-// the quint-tap kernel needs 128 + 4*P rows inside four 124-row chunks and at most two 16-channel K groups
-inline bool tcq_fits(int D, int total_chunks) { return 128 + 4 * (D + 4) <= 4 * TQ_TS && total_chunks <= 8; }
-
 }  // namespace
+
+// the quint-tap kernel needs 128 + 4*P rows inside four 124-row chunks and at most two 16-channel K groups
+bool tc_quint_fits(int D, int total_chunks) { return 128 + 4 * (D + 4) <= 4 * TQ_TS && total_chunks <= 8; }
 
 #ifdef OP3_TC_TRACE
 extern "C" int op3_debug_tc_trace(unsigned long long* out /*[256][4] host*/, int reset) {
@@ -751,8 +750,6 @@ extern "C" int op3_debug_tc_trace(unsigned long long* out /*[256][4] host*/, int
   return 0;
 }
 #endif
-
-extern "C" int op3_debug_set_quint(int on) { g_tc_quint = on != 0; return 0; }
 
 int tc_nout(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 
@@ -791,10 +788,15 @@ int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvI
       OP3_LAUNCH_CHECK();
       maxbits = mb;
     }
-    const int h_nout = nout == 64 ? 32 : nout;
+    const int h_nout = (nout == 64 || (nout == 16 && tc_quint_fits(D, in.total_chunks))) ? 32 : nout;
     const size_t slab = conv5x5_tc_f16_slab_floats(in.total_chunks * 4, h_nout);
-    if (nout == 16) return launch_tc<16, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
-    const bool quint = tcq_fits(D, in.total_chunks) && g_tc_quint;
+    const bool quint = tc_quint_fits(D, in.total_chunks);
+    // narrow layers (cout <= 16) run on the quint-tap kernel with zero rows up to 32 output channels (op3_prepare builds
+    // their slab that way when the kernel fits): its cost does not depend on cout, and it beats both the 16-column
+    // per-tap kernel and the FFMA kernel
+    if (nout == 16 && !quint)
+      return launch_tc<16, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
+    if (nout == 16) return launch_tcq(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
     if (nout == 32)
       return quint ? launch_tcq(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4)
                    : launch_tc<32, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
@@ -826,7 +828,8 @@ int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvI
 int conv5x5_auto(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt_ffma, const float* wt_tc,
                  const float* bias, float4* out, int epi, const float4* elu_ref, float* tc_scratch) {
   const int prec = op3_get_precision();
-  if (prec == OP3_PREC_FP32 || cout == 4) return conv5x5_forward(st, N, D, in, cout, wt_ffma, bias, out, epi, elu_ref);
+  const bool narrow_on_tc = prec == OP3_PREC_F16X3 && tc_quint_fits(D, in.total_chunks);   // 0.12 ms vs 0.22 ms on the FMA pipe
+  if (prec == OP3_PREC_FP32 || (cout == 4 && !narrow_on_tc)) return conv5x5_forward(st, N, D, in, cout, wt_ffma, bias, out, epi, elu_ref);
   return conv5x5_tc_forward(st, prec, N, D, in, cout, wt_tc, bias, out, epi, elu_ref, tc_scratch);
 }
 

@@ -190,7 +190,9 @@ extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const
     OP3_TRY(conv5x5_auto(st, N, D, in, 32, prep + L.dec_wf[i], prep + L.dec_tf[i], prep + L.dec_bf[i], A.a[i + 1], EPI_ELU,
                          nullptr, tcs));
   }
-  OP3_TRY(conv5x5_auto(st, N, D, single_src(A.a[3], 8), 4, prep + L.dec_wf[3], prep + L.dec_tf[3], prep + L.dec_bf[3],
+  ConvInput in5 = single_src(A.a[3], 8);
+  if (f16) in5.maxbits = tc_slot(tcs, N, 4);               // recorded by layer 4's epilogue
+  OP3_TRY(conv5x5_auto(st, N, D, in5, 4, prep + L.dec_wf[3], prep + L.dec_tf[3], prep + L.dec_bf[3],
                        reinterpret_cast<float4*>(out), EPI_NONE, nullptr, tcs));
   return OP3_OK;
 }

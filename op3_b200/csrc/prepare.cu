@@ -252,7 +252,9 @@ extern "C" int op3_prepare(const Op3Dims* d, const Op3Params* p, float* prep, vo
                      float* slab) {
       if (prec == OP3_PREC_F16X3) {
         const int nout_full = tc_nout(gemm_cout);
-        const int halves = nout_full == 64 ? 2 : 1, nout = halves == 2 ? 32 : nout_full;
+        // narrow layers get 32-row slabs (zero rows beyond cout) when the quint-tap kernel will run them (conv5x5_tc_forward)
+        const bool widen = nout_full == 16 && tc_quint_fits(d->D, gemm_cin_pad / 4);
+        const int halves = nout_full == 64 ? 2 : 1, nout = (halves == 2 || widen) ? 32 : nout_full;
         const int groups16 = (gemm_cin_pad / 4 + 3) / 4;
         const size_t per = conv5x5_tc_f16_slab_floats(gemm_cin_pad, nout);
         const int tot = groups16 * 25 * 2 * (2 * nout) * 8;

@@ -147,6 +147,7 @@ __device__ __forceinline__ const float4* tc_src_chunk_ptr(const ConvInput& in, i
 
 // conv5x5_tc.cu
 int tc_nout(int cout);
+bool tc_quint_fits(int D, int total_chunks);    // the quint-tap fp16 kernel applies (see conv5x5_tc.cu)
 size_t conv5x5_tc_weight_floats(int cin_pad, int cout);
 size_t conv5x5_tc_f16_slab_floats(int cin_pad, int nout);   // one fp16 slab (+ its scale word), in floats
 size_t tc_scratch_floats(int N);                             // 8 slots of per-image operand maxima (fp16 mode)
