@@ -335,6 +335,8 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
 // 124 pixels per tile -- the kernel's bottleneck once the tensor core needed only 2400 cycles per tile.
 __device__ __forceinline__ float elu_tc(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
+constexpr int TQ_IDLE_WARP = MMA_WARP + 4;           // the loader-range warp on the issuer's scheduler
+constexpr int TQ_LOAD_THREADS = LOAD_THREADS - 32;
 constexpr int TQ_TS = 124;                          // outputs per tile
 constexpr int TQ_NSLOT = 6;                         // chunk slots in the ring: 4 in use by the current tile + 2 ahead
 constexpr int TQ_RING = TQ_NSLOT * TQ_TS;           // 744 rows
@@ -368,7 +370,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
 
   if (tid < 32) s_bias[tid] = (bias != nullptr && tid < cout_real) ? bias[tid] : 0.f;
   if (tid == 0) {
-    for (int s = 0; s < TQ_NSLOT; ++s) { mbar_init(&full_bar[s], LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TQ_NSLOT; ++s) { mbar_init(&full_bar[s], TQ_LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS * 16); }
     fence_mbar_init();
   }
@@ -387,17 +389,19 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp >= LOAD_WARP0) {
+  if (warp == TQ_IDLE_WARP) {
+    // shares the issuer's scheduler (warp % 4): left idle so that the issuing thread is not starved of issue slots
+  } else if (warp >= LOAD_WARP0) {
     // ===================== loaders: one chunk of 124 pixels x (2 * ngroups) k-chunks per step =====================
     // A thread owns up to three fixed (pixel-in-chunk, k-chunk) tasks; the loads of chunk c+1 are in flight while chunk c
     // is converted and stored (one exposed global latency per item, not per chunk); pixel coordinates advance incrementally.
-    const int lt = tid - LOAD_WARP0 * 32;
+    const int lt = tid - LOAD_WARP0 * 32 - (warp > TQ_IDLE_WARP ? 32 : 0);
     const int ntask = TQ_TS * 2 * ngroups;                 // task = (pixel, k-chunk of 8 channels)
     int ti[3], tk[3];
     bool tact[3];
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
-      const int e = lt + u * LOAD_THREADS;
+      const int e = lt + u * TQ_LOAD_THREADS;
       tact[u] = e < ntask;
       tk[u] = tact[u] ? e / TQ_TS : 0;
       ti[u] = e - (e / TQ_TS) * TQ_TS;
