@@ -358,13 +358,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int KMAX>
+// EXACT: K == KMAX, so every `k < K` slot predicate folds away at compile time (~10 % of the instructions at K = 4)
+template <int KMAX, bool EXACT>
 __global__ void __cluster_dims__(MIXF_CL, 1, 1) __launch_bounds__(MIXF_THREADS)
 mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long mse_bstride,
                  const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ g2,
                  const float* __restrict__ g3, const float* __restrict__ b0, const float* __restrict__ b1,
-                 const float* __restrict__ b2, const float* __restrict__ b3, int B, int K, int D, int emit, int Rs,
+                 const float* __restrict__ b2, const float* __restrict__ b3, int B, int K_in, int D, int emit, int Rs,
                  float beta, unsigned* __restrict__ sync) {
+  const int K = EXACT ? KMAX : K_in;
   extern __shared__ __align__(128) unsigned char mixf_raw[];
   MixfSmem& sm = *reinterpret_cast<MixfSmem*>(mixf_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -826,20 +828,22 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
       ((uintptr_t)io->image & 15) == 0 && (io->image_bstride & 3) == 0 && ((uintptr_t)io->dec_out & 15) == 0) {
     dim3 gf(MIXF_CL, B);
     const float* nul = nullptr;
-#define OP3_MIX_FUSED(KM)                                                                                              \
+#define OP3_MIX_FUSED(KM, EX)                                                                                          \
   do {                                                                                                                 \
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
-      OP3_CHECK(cudaFuncSetAttribute(mix_fused_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      OP3_CHECK(cudaFuncSetAttribute(mix_fused_kernel<KM, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
-    mix_fused_kernel<KM><<<gf, MIXF_THREADS, fused_smem, st>>>(                                                        \
+    mix_fused_kernel<KM, EX><<<gf, MIXF_THREADS, fused_smem, st>>>(                                                    \
         *io, io->mse_image, io->mse_image_bstride, emit ? p->ln2d_gamma[0] : nul, emit ? p->ln2d_gamma[1] : nul,       \
         emit ? p->ln2d_gamma[2] : nul, emit ? p->ln2d_gamma[3] : nul, emit ? p->ln2d_beta[0] : nul,                    \
         emit ? p->ln2d_beta[1] : nul, emit ? p->ln2d_beta[2] : nul, emit ? p->ln2d_beta[3] : nul, B, K, D,             \
         emit ? 1 : 0, d->Rs, d->beta, io->sync);                                                                       \
   } while (0)
-    if (K <= 4) OP3_MIX_FUSED(4); else if (K <= 8) OP3_MIX_FUSED(8); else OP3_MIX_FUSED(16);
+    if (K == 4) OP3_MIX_FUSED(4, true); else if (K < 4) OP3_MIX_FUSED(4, false);
+    else if (K == 8) OP3_MIX_FUSED(8, true); else if (K < 8) OP3_MIX_FUSED(8, false);
+    else OP3_MIX_FUSED(16, false);
 #undef OP3_MIX_FUSED
     OP3_COUNT_LAUNCH();
     OP3_LAUNCH_CHECK();
