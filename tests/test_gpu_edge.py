@@ -18,6 +18,8 @@ SHAPES = [  # B, K, D, action_dim, schedule, loss weights
     (2, 16, 16, 0, [0, 1], [1, 1]),
     (2, 2, 8, 4, [1, 0, 0], [1, 0, 1]),
     (1, 3, 40, 0, [0, 2, 1], [1, 1, 1]),
+    (1, 2, 88, 0, [0, 1], [1, 1]),        # the largest image side the quint-tap fp16 conv kernel takes (128 + 4*(D+2) <= 496)
+    (1, 2, 96, 4, [0, 1, 0], [1, 0, 1]),  # the first one that falls back to the per-tap tensor-core kernel
 ]
 
 
