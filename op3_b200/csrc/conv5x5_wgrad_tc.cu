@@ -670,14 +670,19 @@ constexpr int RB_RING_BYTES = (RB_RING + 1) * RB_SLOT_BYTES;
 constexpr int RB_SMEM = RB_RING_BYTES + 2 * RB_A_BYTES;
 
 __global__ void __launch_bounds__(RB_THREADS, 1)
-conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const float4* __restrict__ dpre, int g_planes,
+conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__ dpre, int g_planes,
                           int g_chunk0, int g_chunks, int cout_total, int co0, const uint32_t* __restrict__ xmax, int xmax_n,
                           const uint32_t* __restrict__ gmax, int gmax_n, float* __restrict__ partial) {
   constexpr int NCO = 32;
   const int P = D + 8;                                     // multiple of 8
   const int QN = (D + 4) * P;                              // padded-linear input pixels per image
   const int NBLK = (QN + HG_BP - 1) / HG_BP;
-  const int n_items = N * SEG;
+  // Each CTA owns a contiguous range [g0, g1) of the global block sequence (image-major), balanced to one block; an
+  // "item" is one image's share of that range.  Only the first item of a CTA can start inside an image.
+  const long long total_blocks = (long long)N * NBLK;
+  const int g0 = (int)(total_blocks * blockIdx.x / gridDim.x), g1 = (int)(total_blocks * (blockIdx.x + 1) / gridDim.x);
+  const int item0 = g0 / NBLK;
+  const int n_items = g1 > g0 ? (g1 + NBLK - 1) / NBLK : 0;   // one past the last image this CTA touches
   const int cin_chunks = in.total_chunks;
   const int cin_pad = cin_chunks * 4;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -708,11 +713,11 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
   float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // step sequence of this CTA: for item = blockIdx.x, += gridDim.x: vb = b0 - RB_PRE .. b1 - 1  (vb < b0: ring refill only)
-  auto item_b0 = [&](int item) { return (item % SEG) * L; };
-  auto item_b1 = [&](int item) { int e = (item % SEG) * L + L; return e < NBLK ? e : NBLK; };
+  auto item_b0 = [&](int item) { int b = g0 - item * NBLK; return b > 0 ? b : 0; };
+  auto item_b1 = [&](int item) { int e = g1 - item * NBLK; return e < NBLK ? e : NBLK; };
   auto advance = [&](int& item, int& vb) {                 // next step; item >= n_items afterwards means "no more steps"
     if (++vb >= item_b1(item)) {
-      item += gridDim.x;
+      item += 1;
       vb = item_b0(item) - RB_PRE;
     }
   };
@@ -724,7 +729,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
     const int j = t64 >> 3, cc = t64 & 7;                  // a quarter warp shares the pixel chunk (see the row order above)
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)P - 1) / (uint32_t)P);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int item = blockIdx.x, vb = item_b0(item) - RB_PRE, t = 0;
+    int item = item0, vb = item_b0(item0) - RB_PRE, t = 0;
     if (grp == 1) { advance(item, vb); t = 1; }
     int nitem = item, nvb = vb;                            // the group's next step (t + 2)
     auto step2 = [&](int& it_, int& vb_) { advance(it_, vb_); if (it_ < n_items) advance(it_, vb_); };
@@ -734,7 +739,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
 #pragma unroll
         for (int e = 0; e < 9; ++e) xv[e] = zero4;
         if (!act || vb_ < item_b0(item_)) return;
-        const int n = item_ / SEG, q = vb_ * HG_BP + 8 * j;
+        const int n = item_, q = vb_ * HG_BP + 8 * j;
         const float4* src = tc_src_chunk_ptr(in, cc, n, D);
         const int r = (int)__umulhi((uint32_t)q, magic);
         const int iy = r - 2, ix = q - r * P - 2;          // q..q+7 share a row (q and P are multiples of 8)
@@ -790,7 +795,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
 #pragma unroll
         for (int e = 0; e < 12; ++e) gv[e] = zero4;
         if (!act) return;
-        const int n = item_ / SEG;
+        const int n = item_;
         const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + cc) * D * D;
         const int p0 = vb_ * HG_BP + 8 * j;
         if (p0 >= 0) {
@@ -868,7 +873,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, int SEG, int L, const floa
     const uint32_t ring_u32 = smem_u32(ring);
     const uint64_t bd0 = make_smem_desc(ring_u32, RB_B_ROWS, 8);
     const uint32_t b_lo0 = (uint32_t)bd0, b_hi32 = (uint32_t)(bd0 >> 32);
-    int item = blockIdx.x, vb = item_b0(item) - RB_PRE, t = 0;
+    int item = item0, vb = item_b0(item0) - RB_PRE, t = 0;
     bool first = true;
     int koff[5];                                           // (-achunks * ky) mod RING
 #pragma unroll
@@ -1060,22 +1065,9 @@ int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const 
     if (g_wg_sms > 148) g_wg_sms = 148;                     // scratch is sized for 148 slabs
   }
   const int P = D + 8, NBLK = ((D + 4) * P + HG_BP - 1) / HG_BP;
-  // segments per image: the split with the best last-round occupancy (refill steps are cheap: no MMAs)
-  int best_seg = 1;
-  double best = 0.0;
-  for (int seg = 1; seg <= 8; ++seg) {
-    const int L = (NBLK + seg - 1) / seg;
-    if ((L - 1) * seg >= NBLK) continue;                   // would leave an empty segment
-    const long long items = (long long)N * seg;
-    const int grid = items < g_wg_sms ? (int)items : g_wg_sms;
-    const double rounds = (double)((items + grid - 1) / grid);
-    const double eff = (double)items / (rounds * grid) * ((double)L / (L + 0.3 * RB_PRE));
-    if (eff > best) { best = eff; best_seg = seg; }
-  }
-  const int SEG = best_seg, L = (NBLK + SEG - 1) / SEG;
-  const long long items = (long long)N * SEG;
-  const int grid = items < g_wg_sms ? (int)items : g_wg_sms;
-  conv5x5_wgrad_ring_kernel<<<grid, RB_THREADS, RB_SMEM, st>>>(in, N, D, SEG, L, dpre, g_planes, g_chunk0, g_chunks, cout_total,
+  const long long total_blocks = (long long)N * NBLK;
+  const int grid = total_blocks < g_wg_sms ? (int)total_blocks : g_wg_sms;
+  conv5x5_wgrad_ring_kernel<<<grid, RB_THREADS, RB_SMEM, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total,
                                                               co0, xmax, xmax_n, gmax, gmax_n, scratch);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
