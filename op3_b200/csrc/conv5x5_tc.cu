@@ -359,7 +359,9 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   const long long total = (long long)N * tiles_img;
   const int g0 = (int)(total * blockIdx.x / gridDim.x), g1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
   const int ngroups = (in.total_chunks + 3) / 4;           // K groups of 16 channels (1 or 2)
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  // the warp index is broadcast with a shuffle so that the compiler KNOWS the role branches are warp-uniform (it then keeps
+  // the issuer's descriptor arithmetic in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* a_s = smem_raw;
@@ -440,7 +442,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
       for (int jc = 0; jc < T + 3; ++jc, ++c) {
         const int slot = c % TQ_NSLOT;
         if (jc + 1 < T + 3) load_chunk(vn);
-        if (c >= TQ_NSLOT) mbar_wait(&empty_bar[slot], ((c / TQ_NSLOT) - 1) & 1);
+        if (c >= TQ_NSLOT) mbar_wait_warp(&empty_bar[slot], ((c / TQ_NSLOT) - 1) & 1);
 #pragma unroll
         for (int u = 0; u < 3; ++u)
           if (tact[u]) {
@@ -463,8 +465,14 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
       g += T;
     }
   } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // The WHOLE warp runs this loop in uniform control flow and only the tcgen05 instructions are predicated on one lane:
+    // descriptor words computed by all lanes from loop counters and kernel parameters stay in UNIFORM registers.  Issued
+    // from inside an `if (lane == 0)` region instead, every MMA is wrapped in an ELECT / R2UR.BROADCAST waterfall of ~12
+    // instructions (~25 cycles per MMA: the whole gap between the isolated and the in-situ MMA rate).
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc_f16(128, TQ_NQ);
       const uint64_t ad = make_smem_desc(smem_u32(a_s), TQ_ROWS, 8);
       const uint64_t bd = make_smem_desc(smem_u32(w_s), TQ_NQ, 8);
@@ -497,12 +505,9 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
           t_full += clock64() - tw; n_mma += 15 * ngroups;
 #endif
           tc_fence_after();
-          const uint32_t dcol = tmem_base + (uint32_t)(slot * TQ_NQ);
+          const uint32_t dcol = tmem_u + (uint32_t)(slot * TQ_NQ);
           const int rowbase = ((c0 + tau) % TQ_NSLOT) * TQ_TS;
-          // operand start rows of the five kernel rows (ring wrap), then a fully unrolled issue sequence whose descriptor
-          // words are the tile's five row offsets plus compile-time constants: the issuing thread must stay ahead of an
-          // 80-cycle MMA while sharing its scheduler with three busy warps
-          uint32_t arow[5];
+          uint32_t arow[5];                                // operand start rows of the five kernel rows (ring wrap)
 #pragma unroll
           for (int ky = 0; ky < 5; ++ky) {
             int row = rowbase + ky * P;
@@ -518,23 +523,28 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
                 const uint32_t a_lo_op = arow[ky] + (uint32_t)((4 + 2 * cg) * TQ_ROWS);
                 const uint32_t b_hi_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 0) * 2 * TQ_NQ);
                 const uint32_t b_lo_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 1) * 2 * TQ_NQ);
-                if (cg == 0 && ky == 0) mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, 0u);
-                else mma_f16_acc(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc);
-                mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
-                mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+                if (leader) {
+                  if (cg == 0 && ky == 0) mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, 0u);
+                  else mma_f16_acc(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc);
+                  mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
+                  mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+                }
               }
             }
           }
-          tc_commit(&empty_bar[(c0 + tau) % TQ_NSLOT]);    // chunk c0+tau is dead once these MMAs have read it
-          if (tau == T - 1)
-            for (int x = 0; x < 3; ++x) tc_commit(&empty_bar[(c0 + T + x) % TQ_NSLOT]);   // the tail halo chunks of the item
-          tc_commit(&acc_full[slot]);
+          if (leader) {
+            tc_commit(&empty_bar[(c0 + tau) % TQ_NSLOT]);  // chunk c0+tau is dead once these MMAs have read it
+            if (tau == T - 1)
+              for (int x = 0; x < 3; ++x) tc_commit(&empty_bar[(c0 + T + x) % TQ_NSLOT]);   // the tail halo chunks of the item
+            tc_commit(&acc_full[slot]);
+          }
+          __syncwarp();
         }
         c_run = c0 + T + 3;
         g += T;
       }
 #ifdef OP3_TC_TRACE
-      if (blockIdx.x < 256) {
+      if (leader && blockIdx.x < 256) {
         atomicAdd(&g_tc_trace[blockIdx.x][0], t_full); atomicAdd(&g_tc_trace[blockIdx.x][1], t_acc);
         atomicAdd(&g_tc_trace[blockIdx.x][2], clock64() - t_begin); atomicAdd(&g_tc_trace[blockIdx.x][3], n_mma);
       }
@@ -567,7 +577,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
 #pragma unroll
           for (int i = 0; i < 8; ++i) ra[i] = (valid && i < out_chunks) ? __ldg(&ref[obase + i * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
-        mbar_wait(&acc_full[slot], (j / 3) & 1);
+        mbar_wait_warp(&acc_full[slot], (j / 3) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TQ_NQ);
         // Every accumulator value is read from TMEM once, two 16-column groups per wait (TMEM load latency is long while

@@ -685,7 +685,8 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
   const int n_items = g1 > g0 ? (g1 + NBLK - 1) / NBLK : 0;   // one past the last image this CTA touches
   const int cin_chunks = in.total_chunks;
   const int cin_pad = cin_chunks * 4;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  // warp index broadcast by shuffle: the role branches are then provably warp-uniform (see the issuer below)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
   const int achunks = P >> 3;                              // G chunk offset per kernel row
   const float sx_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(xmax, xmax_n)));     // one scale per TENSOR: the sum runs
   const float sg_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(gmax, gmax_n)));     // over all images
@@ -760,7 +761,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
         nitem = item; nvb = vb;
         step2(nitem, nvb);
         if (nitem < n_items) load_x(nitem, nvb, xn);
-        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (k >= 1) mbar_wait_warp(&empty_bar[grp], (k - 1) & 1);
         if (act && vb >= item_b0(item)) {
           uint4* row = reinterpret_cast<uint4*>(a_stage + (size_t)grp * RB_A_BYTES) + (size_t)j * RB_A_ROWS + cc;
 #define OP3_HG_X_CHANNEL(C, R)                                                                                   \
@@ -823,7 +824,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
         nitem = item; nvb = vb;
         step2(nitem, nvb);
         if (nitem < n_items) load_g(nitem, nvb, gn);
-        if (k >= 1) mbar_wait(&empty_bar[grp], (k - 1) & 1);
+        if (k >= 1) mbar_wait_warp(&empty_bar[grp], (k - 1) & 1);
         if (act) {
           const int slot = (8 * t + j) % RB_RING;          // running slot counter: 8 new chunks per step
           uint4* row = reinterpret_cast<uint4*>(ring + (size_t)slot * RB_SLOT_BYTES) + cc;
@@ -867,13 +868,26 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
         item = nitem; vb = nvb;
       }
     }
-  } else if (lane == 0) {
+  } else {
     // ===================== MMA issuer =====================
+    // The WHOLE warp runs this loop in uniform control flow; only the tcgen05 instructions are predicated on the lane chosen
+    // by elect.sync.  ptxas then keeps every descriptor word (loop counters + constants) in UNIFORM registers: UTCHMMA
+    // preceded by one UIADD3.  Issued from inside an `if (lane == 0)` region, each MMA was wrapped in an ELECT /
+    // R2UR.BROADCAST waterfall of ~12 instructions -- ~25 cycles per MMA, the whole gap between the isolated (49-56
+    // cycles) and the in-situ (75) rate of these N=96 MMAs, independent of loaders, operand source or bookkeeping.
+#ifdef OP3_RING_LANE0
+    const bool leader = lane == 0;
+#else
+    const bool leader = elect_one();
+#endif
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc = make_idesc_f16(128, 96);
-    const uint32_t ring_u32 = smem_u32(ring);
-    const uint64_t bd0 = make_smem_desc(ring_u32, RB_B_ROWS, 8);
+    const uint64_t bd0 = make_smem_desc(smem_u32(ring), RB_B_ROWS, 8);
     const uint32_t b_lo0 = (uint32_t)bd0, b_hi32 = (uint32_t)(bd0 >> 32);
-    int item = item0, vb = item_b0(item0) - RB_PRE, t = 0;
+    const uint64_t ad0 = make_smem_desc(smem_u32(a_stage), RB_A_ROWS, 8);
+    const uint32_t a_lo0 = (uint32_t)ad0, a_hi32 = (uint32_t)(ad0 >> 32);
+    int item = item0, t = 0, c0 = 0;                       // c0 = (8 t) mod RING: slot of this block's first G chunk
+    int cur_b0 = item_b0(item0), cur_b1 = item_b1(item0), vb = cur_b0 - RB_PRE;
     bool first = true;
     int koff[5];                                           // (-achunks * ky) mod RING
 #pragma unroll
@@ -884,20 +898,16 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
 #endif
     for (; item < n_items; ++t) {
       const int s = t & 1;
-      const bool real = vb >= item_b0(item);
-      // everything that does not depend on the operands is computed BEFORE the wait, so that the MMAs follow the barrier
-      // immediately: slots of the 5 x 4 K-pair operands (wrapped) and the A descriptor
-      const uint64_t ad = make_smem_desc(smem_u32(a_stage + (size_t)s * RB_A_BYTES), RB_A_ROWS, 8);
-      const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
-      const int c0 = 8 * (t % (RB_RING / 8));              // slot of this block's first G chunk = (8 t) mod 56
-      uint32_t boff[5][HG_CH / 2];
+      const bool real = vb >= cur_b0;
+      const uint32_t a_lo32 = a_lo0 + (uint32_t)(s * (RB_A_BYTES / 16));
+      uint32_t boff[5][HG_CH / 2];                         // wrapped ring slots of the 5 x 4 K-pair operands, 16-byte units
 #pragma unroll
       for (int ky = 0; ky < 5; ++ky) {
         int slot = c0 + koff[ky];
         if (slot >= RB_RING) slot -= RB_RING;
 #pragma unroll
         for (int ks = 0; ks < HG_CH / 2; ++ks) {
-          boff[ky][ks] = b_lo0 + (uint32_t)(slot * RB_B_ROWS);                  // 16-byte units
+          boff[ky][ks] = b_lo0 + (uint32_t)(slot * RB_B_ROWS);
           slot += 2;
           if (slot >= RB_RING) slot -= RB_RING;
         }
@@ -912,29 +922,59 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
 #endif
       tc_fence_after();
       if (real) {
+        // The X block goes to TENSOR MEMORY first (4 K-steps x 8 columns behind the 480 accumulator columns): its ten MMAs
+        // per K-step then fetch only the 3 KB of G from shared memory instead of 4 + 3 KB.  tcgen05.cp and tcgen05.mma
+        // execute in issue order, so the next block's copy cannot overtake this block's MMAs.
+#ifdef OP3_RING_TMEM_A
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < HG_CH / 2; ++ks)
+            tc_cp_a128(tmem_u + (uint32_t)(480 + 8 * ks), a_lo32 + (uint32_t)(2 * ks * RB_A_ROWS), a_hi32);
+        }
+#endif
         // consecutive MMAs go to DIFFERENT accumulators (kernel rows): back-to-back MMAs on one accumulator serialise
 #pragma unroll
         for (int ks = 0; ks < HG_CH / 2; ++ks) {
+#ifdef OP3_RING_TMEM_A
+          const uint32_t a_tm = tmem_u + (uint32_t)(480 + 8 * ks);
+#else
           const uint32_t aoff = a_lo32 + (uint32_t)(2 * ks * RB_A_ROWS);
+#endif
 #pragma unroll
           for (int hl = 0; hl < 2; ++hl)
 #pragma unroll
             for (int ky = 0; ky < 5; ++ky) {
-              const uint32_t dcol = tmem_base + (uint32_t)(96 * ky);
-              if (ks == 0 && hl == 0) mma_f16(dcol, aoff, a_hi32, boff[ky][ks], b_hi32, idesc, first ? 0u : 1u);
-              else mma_f16_acc(dcol, aoff, a_hi32, boff[ky][ks] + (hl ? 96u : 0u), b_hi32, idesc);
+              const uint32_t dcol = tmem_u + (uint32_t)(96 * ky);
+              if (leader) {
+#ifdef OP3_RING_TMEM_A
+                if (ks == 0 && hl == 0) mma_f16_ts(dcol, a_tm, boff[ky][ks], b_hi32, idesc, first ? 0u : 1u);
+                else mma_f16_ts_acc(dcol, a_tm, boff[ky][ks] + (hl ? 96u : 0u), b_hi32, idesc);
+#else
+                if (ks == 0 && hl == 0) mma_f16(dcol, aoff, a_hi32, boff[ky][ks], b_hi32, idesc, first ? 0u : 1u);
+                else mma_f16_acc(dcol, aoff, a_hi32, boff[ky][ks] + (hl ? 96u : 0u), b_hi32, idesc);
+#endif
+              }
             }
         }
         first = false;
       }
-      tc_commit(&empty_bar[s]);
-      advance(item, vb);
+      if (leader) tc_commit(&empty_bar[s]);
+      __syncwarp();
+      if (++vb >= cur_b1) {                                // next image of this CTA's range
+        item += 1;
+        cur_b0 = item_b0(item); cur_b1 = item_b1(item);
+        vb = cur_b0 - RB_PRE;
+      }
+      c0 += 8;
+      if (c0 >= RB_RING) c0 -= RB_RING;
     }
-    tc_commit(&acc_bar);
+    if (leader) tc_commit(&acc_bar);
 #ifdef OP3_TC_TRACE
-    atomicAdd(&g_ring_trace[blockIdx.x][0], t_full); atomicAdd(&g_ring_trace[blockIdx.x][1], clock64() - t_begin);
-    atomicAdd(&g_ring_trace[blockIdx.x][2], n_mma); atomicAdd(&g_ring_trace[blockIdx.x][3], (unsigned long long)t);
-    atomicAdd(&g_ring_trace[blockIdx.x][5], t_begin - t_kernel0);
+    if (leader) {
+      atomicAdd(&g_ring_trace[blockIdx.x][0], t_full); atomicAdd(&g_ring_trace[blockIdx.x][1], clock64() - t_begin);
+      atomicAdd(&g_ring_trace[blockIdx.x][2], n_mma); atomicAdd(&g_ring_trace[blockIdx.x][3], (unsigned long long)t);
+      atomicAdd(&g_ring_trace[blockIdx.x][5], t_begin - t_kernel0);
+    }
 #endif
   }
   // ===================== epilogue =====================
@@ -948,7 +988,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
   float* slab = partial + (size_t)blockIdx.x * ((size_t)25 * cin_pad * cout_total + cout_total);
   const float inv = 1.f / (sx_scale * sg_scale);           // powers of two: exact
   if (warp < MMA_WARP) {
-    mbar_wait(&acc_bar, 0);
+    mbar_wait_warp(&acc_bar, 0);
     tc_fence_after();
   }
   if (warp < MMA_WARP && (warp & 3) >= 2) {                // G warps: 8 lanes (pixel chunks) share a channel chunk

@@ -62,6 +62,26 @@ __device__ __forceinline__ void mma_f16_acc(uint32_t d_tmem, uint32_t alo, uint3
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t}\n"
       :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
 }
+// A operand in TENSOR MEMORY (tests/probes/probe_tmem_a.cu: bit-identical to the smem-A form): `tcgen05.cp.128x256b` copies a
+// 128-row x 32-byte K-major smem tile (one K=16 fp16 step, the same descriptor an MMA would take) into 8 TMEM columns, in
+// issue order with the MMAs; MMAs that name it fetch only B from shared memory.
+__device__ __forceinline__ void tc_cp_a128(uint32_t a_tmem, uint32_t alo, uint32_t ahi) {
+  asm volatile("{\n\t.reg .b64 da;\n\tmov.b64 da, {%1, %2};\n\ttcgen05.cp.cta_group::1.128x256b [%0], da;\n\t}\n"
+               :: "r"(a_tmem), "r"(alo), "r"(ahi) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_acc(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, 1;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
 // Power-of-two scale that brings a tensor whose largest magnitude has the fp32 bit pattern `maxbits` into [2^13, 2^14)
 // (fp16 overflows at 2^16; products are accumulated in fp32).  Zero / denormal maxima get scale 1.
 __host__ __device__ __forceinline__ uint32_t f16_scale_bits(uint32_t maxbits) {
@@ -106,6 +126,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1ull << 28)) __trap();
   }
+}
+
+// elect.sync: true in exactly one lane of the (fully converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+// Warp-convergent wait: ONE lane polls the barrier, the others park at the warp barrier.  With every lane polling, the
+// eight-plus waiting warps of a warp-specialised kernel keep the shared-memory pipe busy with try_wait probes next to the
+// tensor core's operand fetches.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 template <int COLS>
