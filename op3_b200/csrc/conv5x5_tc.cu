@@ -62,7 +62,7 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
   const int groups_img = (tiles_img + G - 1) / G;
   const int n_items = N * groups_img;
   const int ngroups = F16 ? (in.total_chunks + 3) / 4 : (in.total_chunks + 1) / 2;   // K groups of 16 / 8 channels
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;   // provably warp-uniform roles
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int a_bytes = 2 * PH * 16;
@@ -172,8 +172,11 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
       }
     }
   } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: whole warp in uniform control flow, tcgen05 instructions on the elect.sync leader
+    // (descriptor words stay in uniform registers: no ELECT / R2UR waterfall per MMA) =====================
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc1 = F16 ? make_idesc_f16(128, NB) : make_idesc_tf32(128, NB);
       const uint32_t idesc2 = F16 ? make_idesc_f16(128, NOUT) : make_idesc_tf32(128, NOUT);
       int it = 0, j = 0;
@@ -193,7 +196,7 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
         t_acc += clock64() - ta0;
 #endif
         tc_fence_after();
-        const uint32_t dbase = tmem_base + (uint32_t)(buf * 256);
+        const uint32_t dbase = tmem_u + (uint32_t)(buf * 256);
         for (int cg = 0; cg < ngroups; ++cg, ++it) {
           const int s = it % NSTAGE;
 #ifdef OP3_TC_TRACE
@@ -222,21 +225,24 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
               const uint32_t aoff = (uint32_t)(128 * t + (tap / 5) * P + (tap % 5));   // 16-byte units
 #endif
               const uint32_t boff = (uint32_t)(tap * 2 * NB);
-              if (F16) {
-                mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
-                mma_f16(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
-              } else {
-                mma_tf32(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
-                if (SPLIT3) mma_tf32(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
+              if (leader) {
+                if (F16) {
+                  mma_f16(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
+                  mma_f16(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
+                } else {
+                  mma_tf32(dcol, a_lo32 + aoff, a_hi32, b_lo32 + boff, b_hi32, idesc1, (cg > 0 || tap > 0) ? 1u : 0u);
+                  if (SPLIT3) mma_tf32(dcol, al_lo32 + aoff, al_hi32, b_lo32 + boff, b_hi32, idesc2, 1u);
+                }
               }
             }
           }
-          tc_commit(&empty_bar[s]);                      // smem stage free once these MMAs have read it
+          if (leader) tc_commit(&empty_bar[s]);          // smem stage free once these MMAs have read it
+          __syncwarp();
         }
-        tc_commit(&acc_full[buf]);                       // accumulators of this item complete
+        if (leader) tc_commit(&acc_full[buf]);           // accumulators of this item complete
       }
 #ifdef OP3_TC_TRACE
-      if (blockIdx.x < 256) {
+      if (leader && blockIdx.x < 256) {
         atomicAdd(&g_tc_trace[blockIdx.x][0], t_full); atomicAdd(&g_tc_trace[blockIdx.x][1], t_acc);
         atomicAdd(&g_tc_trace[blockIdx.x][2], clock64() - t_begin); atomicAdd(&g_tc_trace[blockIdx.x][3], n_mma);
       }
