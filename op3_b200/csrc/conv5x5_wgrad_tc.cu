@@ -59,7 +59,7 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
   const int n_items = N * NBLK;
   const int cin_chunks = in.total_chunks;
   const int cin_pad = cin_chunks * 4;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;   // provably warp-uniform roles
   const int a0 = (ky * P) >> 2;                            // chunk offset of taps kx = 0..3; kx = 4 uses a0 + 1
   const bool have = n_items > (int)blockIdx.x;
 
@@ -208,7 +208,10 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
         gm[0] = gmn[0]; gm[1] = gmn[1];
       }
     }
-  } else if (lane == 0) {
+  } else {
+    // whole warp in uniform control flow, tcgen05 instructions on the elect.sync leader (uniform-register descriptors)
+    const bool leader = elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     // ===================== MMA issuer: per 8 pixels, [X_0;X_1] x [G_0|G_2](a0) (N = 2 NB) and [X_0;X_1] x G_0(a0+1) ==========
     // An MMA's cost is its shared-memory operand traffic ((4 KB of A + 32 B x N of B) / 128 B per clock for N <= 128), so
     // the two G copies share one read of A.
@@ -229,14 +232,15 @@ conv5x5_wgrad_tc_kernel(ConvInput in, int N, int D, const float4* __restrict__ d
 #pragma unroll
       for (int ks = 0; ks < WG_BP / 8; ++ks) {
         const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-        mma_tf32(tmem_base, a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32, b2_lo32 + (uint32_t)(2 * ks * B_ROWS), b2_hi32,
+        if (leader) mma_tf32(tmem_u, a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32, b2_lo32 + (uint32_t)(2 * ks * B_ROWS), b2_hi32,
                  idesc2, acc);
-        mma_tf32(tmem_base + (uint32_t)(2 * NB), a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32,
+        if (leader) mma_tf32(tmem_u + (uint32_t)(2 * NB), a_lo32 + (uint32_t)(2 * ks * WG_A_ROWS), a_hi32,
                  b1_lo32 + (uint32_t)(2 * ks * B_ROWS), b1_hi32, idesc1, acc);
       }
-      tc_commit(&empty_bar[s]);
+      if (leader) tc_commit(&empty_bar[s]);
+      __syncwarp();
     }
-    tc_commit(&acc_bar);
+    if (leader) tc_commit(&acc_bar);
   }
   // ===================== epilogue: quadrant sums -> per-CTA partial slab =====================
   __syncthreads();                      // loaders are done with smem; reuse it as the combine buffer
@@ -398,7 +402,7 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
   const int n_items = N * NBLK;
   const int cin_chunks = in.total_chunks;
   const int cin_pad = cin_chunks * 4;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;   // provably warp-uniform roles
   const int a0 = (ky * P) >> 3;                            // chunk offset of this kernel row
   const bool have = n_items > (int)blockIdx.x;
   const float sx_scale = __uint_as_float(f16_scale_bits(wg_tensor_max(xmax, xmax_n)));     // one scale per TENSOR: the sum runs
@@ -554,7 +558,10 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
         for (int e = 0; e < 12; ++e) gv[e] = gn[e];
       }
     }
-  } else if (lane == 0) {
+  } else {
+    // whole warp in uniform control flow, tcgen05 instructions on the elect.sync leader (uniform-register descriptors)
+    const bool leader = elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     // ===================== MMA issuer: [X_0; X_1] x [G_0 | G_2 | G_4], K = 16 pixels =====================
     const uint32_t idesc = make_idesc_f16(128, 192);
     int it = 0;
@@ -569,11 +576,12 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
       const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
 #pragma unroll
       for (int ks = 0; ks < HG_CH / 2; ++ks)
-        mma_f16(tmem_base, a_lo32 + (uint32_t)(2 * ks * HG_A_ROWS), a_hi32, b_lo32 + (uint32_t)(2 * ks * HG_B_ROWS), b_hi32, idesc,
+        if (leader) mma_f16(tmem_u, a_lo32 + (uint32_t)(2 * ks * HG_A_ROWS), a_hi32, b_lo32 + (uint32_t)(2 * ks * HG_B_ROWS), b_hi32, idesc,
                 (it > 0 || ks > 0) ? 1u : 0u);
-      tc_commit(&empty_bar[s]);
+      if (leader) tc_commit(&empty_bar[s]);
+      __syncwarp();
     }
-    tc_commit(&acc_bar);
+    if (leader) tc_commit(&acc_bar);
   }
   // ===================== epilogue =====================
   __syncthreads();
