@@ -662,6 +662,9 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
 #ifdef OP3_TC_TRACE
 __device__ unsigned long long g_ring_trace[256][8];   // issuer: cycles waiting for operands, loop total, MMAs, steps, kernel total, prologue
 #endif
+#ifndef OP3_RING_SMEM_A
+#define OP3_RING_TMEM_A 1     /* X block staged in TMEM with tcgen05.cp (define OP3_RING_SMEM_A for the smem-A form) */
+#endif
 constexpr int RB_RING = 56;                  // G chunks in the ring (+ 1 guard slot = copy of slot 0 for wrapped K pairs)
 constexpr int RB_PRE = 5;                    // refill steps per item: 5 blocks = 40 chunks >= 4*P/8 = 36 (D = 64)
 constexpr int RB_LOADERS = 2 * 4 * 32;       // two groups (even / odd steps) of 2 X warps + 2 G warps
@@ -769,27 +772,46 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
         nitem = item; nvb = vb;
         step2(nitem, nvb);
         if (nitem < n_items) load_x(nitem, nvb, xn);
-        if (k >= 1) mbar_wait_warp(&empty_bar[grp], (k - 1) & 1);
-        if (act && vb >= item_b0(item)) {
-          uint4* row = reinterpret_cast<uint4*>(a_stage + (size_t)grp * RB_A_BYTES) + (size_t)j * RB_A_ROWS + cc;
-#define OP3_HG_X_CHANNEL(C, R)                                                                                   \
+        // Scale + hi/lo split IN PLACE before the stage is free: the packed (hi, lo) words of a pixel pair overwrite the
+        // two fp32 values they came from, so nothing is added to the register budget (168 of 170) and between "stage empty"
+        // and "stage full" only the shifted copies and the 16 stores remain.
+        const bool fill = act && vb >= item_b0(item);
+        uint32_t x8l[4];                                   // lo half of the ninth pixel (its hi half replaces xv[8])
+        if (fill) {
+#define OP3_HG_X_CONVERT(C, R)                                                                                   \
           {                                                                                                      \
-            uint32_t h01, l01, h23, l23, h45, l45, h67, l67, h8, l8;                                             \
-            hg_pair(xv[0].C, xv[1].C, sx_scale, h01, l01);                                                       \
-            hg_pair(xv[2].C, xv[3].C, sx_scale, h23, l23);                                                       \
-            hg_pair(xv[4].C, xv[5].C, sx_scale, h45, l45);                                                       \
-            hg_pair(xv[6].C, xv[7].C, sx_scale, h67, l67);                                                       \
-            hg_pair(xv[8].C, 0.f, sx_scale, h8, l8);                                                             \
+            uint32_t hh, ll;                                                                                     \
+            hg_pair(xv[0].C, xv[1].C, sx_scale, hh, ll); xv[0].C = __uint_as_float(hh); xv[1].C = __uint_as_float(ll); \
+            hg_pair(xv[2].C, xv[3].C, sx_scale, hh, ll); xv[2].C = __uint_as_float(hh); xv[3].C = __uint_as_float(ll); \
+            hg_pair(xv[4].C, xv[5].C, sx_scale, hh, ll); xv[4].C = __uint_as_float(hh); xv[5].C = __uint_as_float(ll); \
+            hg_pair(xv[6].C, xv[7].C, sx_scale, hh, ll); xv[6].C = __uint_as_float(hh); xv[7].C = __uint_as_float(ll); \
+            hg_pair(xv[8].C, 0.f, sx_scale, hh, ll); xv[8].C = __uint_as_float(hh); x8l[R] = ll;                    \
+          }
+          OP3_HG_X_CONVERT(x, 0)
+          OP3_HG_X_CONVERT(y, 1)
+          OP3_HG_X_CONVERT(z, 2)
+          OP3_HG_X_CONVERT(w, 3)
+#undef OP3_HG_X_CONVERT
+        }
+        if (k >= 1) mbar_wait_warp(&empty_bar[grp], (k - 1) & 1);
+        if (fill) {
+          uint4* row = reinterpret_cast<uint4*>(a_stage + (size_t)grp * RB_A_BYTES) + (size_t)j * RB_A_ROWS + cc;
+#define OP3_HG_X_STORE(C, R)                                                                                     \
+          {                                                                                                      \
+            const uint32_t h01 = __float_as_uint(xv[0].C), l01 = __float_as_uint(xv[1].C), h23 = __float_as_uint(xv[2].C),   \
+                           l23 = __float_as_uint(xv[3].C), h45 = __float_as_uint(xv[4].C), l45 = __float_as_uint(xv[5].C),   \
+                           h67 = __float_as_uint(xv[6].C), l67 = __float_as_uint(xv[7].C), h8 = __float_as_uint(xv[8].C),    \
+                           l8 = x8l[R];                                                                          \
             row[8 * R] = make_uint4(h01, h23, h45, h67);                                                         \
             row[32 + 8 * R] = make_uint4(l01, l23, l45, l67);                                                    \
             row[64 + 8 * R] = make_uint4(hg_shift1(h01, h23), hg_shift1(h23, h45), hg_shift1(h45, h67), hg_shift1(h67, h8)); \
             row[96 + 8 * R] = make_uint4(hg_shift1(l01, l23), hg_shift1(l23, l45), hg_shift1(l45, l67), hg_shift1(l67, l8)); \
           }
-          OP3_HG_X_CHANNEL(x, 0)
-          OP3_HG_X_CHANNEL(y, 1)
-          OP3_HG_X_CHANNEL(z, 2)
-          OP3_HG_X_CHANNEL(w, 3)
-#undef OP3_HG_X_CHANNEL
+          OP3_HG_X_STORE(x, 0)
+          OP3_HG_X_STORE(y, 1)
+          OP3_HG_X_STORE(z, 2)
+          OP3_HG_X_STORE(w, 3)
+#undef OP3_HG_X_STORE
         }
         fence_proxy_async();
         mbar_arrive(&full_bar[grp]);
@@ -832,21 +854,49 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
         nitem = item; nvb = vb;
         step2(nitem, nvb);
         if (nitem < n_items) load_g(nitem, nvb, gn);
+        // bias sums, then scale + hi/lo split IN PLACE before the ring slots are free: the packed (hi, lo) words of a pixel
+        // pair overwrite the two fp32 values they came from (no extra registers); between "slots empty" and "slots full"
+        // only the three shifted row sets are assembled and stored
+#ifdef OP3_TC_TRACE
+        const unsigned long long tc0 = clock64();
+#endif
+        if (act) {
+          if (vb >= item_b0(item)) {                       // refill chunks belong to the previous range's sum
+#pragma unroll
+            for (int e = 4; e < 12; ++e) {
+              bias_acc.x += gv[e].x; bias_acc.y += gv[e].y; bias_acc.z += gv[e].z; bias_acc.w += gv[e].w;
+            }
+          }
+#define OP3_HG_G_CONVERT(C)                                                                                      \
+          _Pragma("unroll") for (int e = 0; e < 12; e += 2) {                                                    \
+            uint32_t hh, ll;                                                                                     \
+            hg_pair(gv[e].C, gv[e + 1].C, sg_scale, hh, ll);                                                     \
+            gv[e].C = __uint_as_float(hh); gv[e + 1].C = __uint_as_float(ll);                                    \
+          }
+          OP3_HG_G_CONVERT(x)
+          OP3_HG_G_CONVERT(y)
+          OP3_HG_G_CONVERT(z)
+          OP3_HG_G_CONVERT(w)
+#undef OP3_HG_G_CONVERT
+        }
+#ifdef OP3_TC_TRACE
+        const unsigned long long tw0 = clock64();
+#endif
         if (k >= 1) mbar_wait_warp(&empty_bar[grp], (k - 1) & 1);
+#ifdef OP3_TC_TRACE
+        const unsigned long long tw1 = clock64();
+#endif
         if (act) {
           const int slot = (8 * t + j) % RB_RING;          // running slot counter: 8 new chunks per step
           uint4* row = reinterpret_cast<uint4*>(ring + (size_t)slot * RB_SLOT_BYTES) + cc;
           uint4* guard = reinterpret_cast<uint4*>(ring + (size_t)RB_RING * RB_SLOT_BYTES) + cc;
           const bool dup = slot == 0;                      // slot 0 is mirrored behind the ring for K pairs that wrap
-#define OP3_HG_G_CHANNEL(C, R)                                                                                   \
+#define OP3_HG_G_STORE(C, R)                                                                                     \
           {                                                                                                      \
-            uint32_t hm2, lm2, hm1, lm1, h0, l0, h1, l1, h2, l2, h3, l3;                                         \
-            hg_pair(gv[0].C, gv[1].C, sg_scale, hm2, lm2);                                                       \
-            hg_pair(gv[2].C, gv[3].C, sg_scale, hm1, lm1);                                                       \
-            hg_pair(gv[4].C, gv[5].C, sg_scale, h0, l0);                                                         \
-            hg_pair(gv[6].C, gv[7].C, sg_scale, h1, l1);                                                         \
-            hg_pair(gv[8].C, gv[9].C, sg_scale, h2, l2);                                                         \
-            hg_pair(gv[10].C, gv[11].C, sg_scale, h3, l3);                                                       \
+            const uint32_t hm2 = __float_as_uint(gv[0].C), lm2 = __float_as_uint(gv[1].C), hm1 = __float_as_uint(gv[2].C),   \
+                           lm1 = __float_as_uint(gv[3].C), h0 = __float_as_uint(gv[4].C), l0 = __float_as_uint(gv[5].C),     \
+                           h1 = __float_as_uint(gv[6].C), l1 = __float_as_uint(gv[7].C), h2 = __float_as_uint(gv[8].C),      \
+                           l2 = __float_as_uint(gv[9].C), h3 = __float_as_uint(gv[10].C), l3 = __float_as_uint(gv[11].C);    \
             const uint4 g0h = make_uint4(h0, h1, h2, h3), g0l = make_uint4(l0, l1, l2, l3);       /* p0   .. p0+7 */ \
             const uint4 g2h = make_uint4(hm1, h0, h1, h2), g2l = make_uint4(lm1, l0, l1, l2);     /* p0-2 .. p0+5 */ \
             const uint4 g4h = make_uint4(hm2, hm1, h0, h1), g4l = make_uint4(lm2, lm1, l0, l1);   /* p0-4 .. p0+3 */ \
@@ -857,20 +907,26 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
               guard[96 + 8 * R] = g0l; guard[128 + 8 * R] = g2l; guard[160 + 8 * R] = g4l;                       \
             }                                                                                                    \
           }
-          OP3_HG_G_CHANNEL(x, 0)
-          OP3_HG_G_CHANNEL(y, 1)
-          OP3_HG_G_CHANNEL(z, 2)
-          OP3_HG_G_CHANNEL(w, 3)
-#undef OP3_HG_G_CHANNEL
-          if (vb >= item_b0(item)) {                       // refill chunks belong to the previous segment's sum
-#pragma unroll
-            for (int e = 4; e < 12; ++e) {
-              bias_acc.x += gv[e].x; bias_acc.y += gv[e].y; bias_acc.z += gv[e].z; bias_acc.w += gv[e].w;
-            }
-          }
+          OP3_HG_G_STORE(x, 0)
+          OP3_HG_G_STORE(y, 1)
+          OP3_HG_G_STORE(z, 2)
+          OP3_HG_G_STORE(w, 3)
+#undef OP3_HG_G_STORE
         }
+#ifdef OP3_TC_TRACE
+        const unsigned long long tw2 = clock64();
+#endif
         fence_proxy_async();
+#ifdef OP3_TC_TRACE
+        const unsigned long long tw3 = clock64();
+#endif
         mbar_arrive(&full_bar[grp]);
+#ifdef OP3_TC_TRACE
+        if (tid == 64) {
+          atomicAdd(&g_ring_trace[blockIdx.x][6], tw1 - tw0); atomicAdd(&g_ring_trace[blockIdx.x][7], tw2 - tw1);
+          atomicAdd(&g_ring_trace[blockIdx.x][4], tw3 - tw2); atomicAdd(&g_ring_trace[blockIdx.x][5], tw0 - tc0);
+        }
+#endif
 #pragma unroll
         for (int e = 0; e < 12; ++e) gv[e] = gn[e];
         item = nitem; vb = nvb;
@@ -981,7 +1037,6 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
     if (leader) {
       atomicAdd(&g_ring_trace[blockIdx.x][0], t_full); atomicAdd(&g_ring_trace[blockIdx.x][1], clock64() - t_begin);
       atomicAdd(&g_ring_trace[blockIdx.x][2], n_mma); atomicAdd(&g_ring_trace[blockIdx.x][3], (unsigned long long)t);
-      atomicAdd(&g_ring_trace[blockIdx.x][5], t_begin - t_kernel0);
     }
 #endif
   }
@@ -1049,7 +1104,6 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
   tc_fence_before();
   __syncthreads();
 #ifdef OP3_TC_TRACE
-  if (tid == 0) atomicAdd(&g_ring_trace[blockIdx.x][4], clock64() - t_kernel0);
 #endif
   if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }

@@ -41,9 +41,9 @@ def main():
     lib.op3_debug_ring_trace(buf.ctypes.data, 0)
     full = buf[:148].astype(np.float64)
     t = full.mean(0)
-    print("ring kernel totals per step (cycles): mean %.0f max %.0f min %.0f; prologue mean %.0f; issuer loop mean %.0f max %.0f"
-          % (t[4], full[:, 4].max(), full[:, 4].min(), t[5], t[1], full[:, 1].max()))
-    print("ring issuer operand wait: mean %.0f max %.0f min %.0f" % (t[0], full[:, 0].max(), full[:, 0].min()))
+    hs = t[3] / 2
+    print("ring G loader (warp 2 of group 0, per step of its own): convert %.0f, wait for empty %.0f, stores %.0f, proxy fence %.0f cycles"
+          % (t[5] / hs, t[6] / hs, t[7] / hs, t[4] / hs))
     print("ring wgrad, one step, mean over CTAs: wait operands %.0f cyc of %.0f total (%.1f%%), MMAs %.0f, steps %.0f"
           % (t[0], t[1], 100 * t[0] / t[1], t[2], t[3]))
     print("  cycles per MMA excluding operand waits: %.1f; including: %.1f" % ((t[1] - t[0]) / t[2], t[1] / t[2]))
