@@ -343,6 +343,9 @@ __device__ __forceinline__ float elu_tc(float x) { return x > 0.f ? x : __expf(x
 
 constexpr int TQ_IDLE_WARP = MMA_WARP + 4;           // the loader-range warp on the issuer's scheduler
 constexpr int TQ_LOAD_THREADS = LOAD_THREADS - 32;
+#ifndef OP3_TCQ_SMEM_A
+#define OP3_TCQ_TMEM_A 1      /* x_hi staged in TMEM once per kernel row (define OP3_TCQ_SMEM_A for the all-smem form) */
+#endif
 constexpr int TQ_PAD = 2;                           // pad columns per row of the padded-linear pixel space
 constexpr int TQ_TS = 124;                          // outputs per tile
 constexpr int TQ_NSLOT = 6;                         // chunk slots in the ring: 4 in use by the current tile + 2 ahead
@@ -530,9 +533,18 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
                 const uint32_t b_hi_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 0) * 2 * TQ_NQ);
                 const uint32_t b_lo_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 1) * 2 * TQ_NQ);
                 if (leader) {
+#ifdef OP3_TCQ_TMEM_A
+                  // x_hi feeds two MMAs: staged once in the 8 TMEM columns behind the accumulators (tcgen05.cp, in issue order
+                  // with the MMAs), so they fetch only their 5 KB of weights from shared memory
+                  tc_cp_a128(tmem_u + 480u, a_hi_op, a_hi32);
+                  if (cg == 0 && ky == 0) mma_f16_ts(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc, 0u);
+                  else mma_f16_ts_acc(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc);
+                  mma_f16_ts_acc(dcol, tmem_u + 480u, b_lo_op, b_hi32, idesc);
+#else
                   if (cg == 0 && ky == 0) mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, 0u);
                   else mma_f16_acc(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc);
                   mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
+#endif
                   mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
                 }
               }
