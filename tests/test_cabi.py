@@ -79,3 +79,24 @@ def test_training_scheduler_matches_reference_fixture(golden_dir):
         assert np.array_equal(got, expect), (kind, epoch, is_train, max_T)
         assert s.should_save_model(int(epoch)) == save
         assert np.array_equal(s.get_loss_schedule(got), np.arange(1, len(got) + 1))
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) must print ONE JSON line with the keys the
+    driver reads, without touching a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "train_sequences_per_sec" and j["unit"] == "sequences/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["steps"] == 1
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"]
