@@ -655,12 +655,13 @@ conv5x5_wgrad_f16_kernel(ConvInput in, int N, int D, const float4* __restrict__ 
 // 4*P/8 + 8 G chunks live in a shared-memory ring (57 slots of [G_0hi G_2hi G_4hi | G_0lo G_2lo G_4lo] rows); per 64-pixel
 // block and kernel row the issuer runs 4 K-steps x 2 MMAs (B = the 96 hi rows, then the 96 lo rows, same accumulator
 // columns: D += A*G_hi + A*G_lo), N = 96, accumulators at TMEM columns 96*ky (480 of 512).
-// Work items are (image, segment of blocks); each item first refills the ring with the 5 blocks of G before its first
-// block (steps with no MMAs).  Ring slots are numbered by a running per-CTA counter, so a slot is rewritten 7 steps after
-// it was filled, two steps after its last reader (the same empty barrier that guards the two A stages).
+// Each CTA owns a contiguous range of the global (image-major) block sequence; where the range enters an image it first
+// refills the ring with the 5 blocks of G before its first block (steps with no MMAs).  Ring slots are numbered by a
+// running per-CTA counter, so a slot is rewritten 7 steps after it was filled, two steps after its last reader (the same
+// empty barrier that guards the two A stages).  The X block of a step is copied to TMEM (tcgen05.cp) and read from there.
 // =====================================================================================================================
 #ifdef OP3_TC_TRACE
-__device__ unsigned long long g_ring_trace[256][8];   // issuer: cycles waiting for operands, loop total, MMAs, steps, kernel total, prologue
+__device__ unsigned long long g_ring_trace[256][8];   // issuer: operand wait, loop total, MMAs, steps; one G-loader warp: fence, convert, wait, stores
 #endif
 #ifndef OP3_RING_SMEM_A
 #define OP3_RING_TMEM_A 1     /* X block staged in TMEM with tcgen05.cp (define OP3_RING_SMEM_A for the smem-A form) */
@@ -939,11 +940,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
     // preceded by one UIADD3.  Issued from inside an `if (lane == 0)` region, each MMA was wrapped in an ELECT /
     // R2UR.BROADCAST waterfall of ~12 instructions -- ~25 cycles per MMA, the whole gap between the isolated (49-56
     // cycles) and the in-situ (75) rate of these N=96 MMAs, independent of loaders, operand source or bookkeeping.
-#ifdef OP3_RING_LANE0
-    const bool leader = lane == 0;
-#else
     const bool leader = elect_one();
-#endif
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc = make_idesc_f16(128, 96);
     const uint64_t bd0 = make_smem_desc(smem_u32(ring), RB_B_ROWS, 8);
