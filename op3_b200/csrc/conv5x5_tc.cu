@@ -36,6 +36,7 @@ constexpr int TC_LD_U = 4;   // pixels per loader thread and pass in the fp16 mo
 // debug timeline of the MMA issuer thread: [sm][0] cycles waiting for operand stages, [1] waiting for a free
 // accumulator buffer, [2] total cycles in the item loop, [3] number of MMAs issued
 __device__ unsigned long long g_tc_trace[256][4];
+__device__ unsigned long long g_tcq_epi[8];          // quint epilogue warp 0: acc wait, loads+shuffles, barrier, tiles, fix-up, ELU+stores, barrier
 #endif
 
 template <int NOUT, int MODE>
@@ -595,7 +596,13 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
 #pragma unroll
           for (int i = 0; i < 8; ++i) ra[i] = (valid && i < out_chunks) ? __ldg(&ref[obase + i * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
+#ifdef OP3_TC_TRACE
+        const unsigned long long te0 = clock64();
+#endif
         mbar_wait_warp(&acc_full[slot], (j / 3) & 1);
+#ifdef OP3_TC_TRACE
+        const unsigned long long te1 = clock64();
+#endif
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TQ_NQ);
         // Every accumulator value is read from TMEM once, two 16-column groups per wait (TMEM load latency is long while
@@ -643,7 +650,13 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         }
         tc_fence_before();
         mbar_arrive(&acc_empty[slot]);                       // every TMEM read of this tile is done
+#ifdef OP3_TC_TRACE
+        const unsigned long long te2 = clock64();
+#endif
         asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory");      // the four warps of this group
+#ifdef OP3_TC_TRACE
+        const unsigned long long te3 = clock64();
+#endif
         if (quad < 3 && lane >= 28) {                        // rows whose shifted sources live in the next quadrant
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -660,6 +673,9 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
               }
           }
         }
+#ifdef OP3_TC_TRACE
+        const unsigned long long te4 = clock64();
+#endif
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           if (valid) {
@@ -682,7 +698,16 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
             }
           }
         }
+#ifdef OP3_TC_TRACE
+        const unsigned long long te5 = clock64();
+#endif
         asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory");      // exchange rows read before the next tile rewrites them
+#ifdef OP3_TC_TRACE
+        if (tid == 0) {     // per-tile timeline of one epilogue warp: see tools/tc_trace.py
+          atomicAdd(&g_tcq_epi[0], te1 - te0); atomicAdd(&g_tcq_epi[1], te2 - te1); atomicAdd(&g_tcq_epi[2], te3 - te2); atomicAdd(&g_tcq_epi[3], 1ull);
+          atomicAdd(&g_tcq_epi[4], te4 - te3); atomicAdd(&g_tcq_epi[5], te5 - te4); atomicAdd(&g_tcq_epi[6], clock64() - te5);
+        }
+#endif
       }
       if (in.out_maxbits != nullptr) {                      // magnitudes of the written tensor, for its consumer's operand scale
 #pragma unroll
@@ -777,6 +802,11 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
 bool tc_quint_fits(int D, int total_chunks) { return 128 + 4 * (D + TQ_PAD) <= 4 * TQ_TS && total_chunks <= 8; }
 
 #ifdef OP3_TC_TRACE
+extern "C" int op3_debug_tcq_epi(unsigned long long* out /*[8] host*/, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_tcq_epi, sizeof(unsigned long long) * 8);
+  if (reset) { static unsigned long long z[8]; cudaMemcpyToSymbol(g_tcq_epi, z, sizeof(z)); }
+  return 0;
+}
 extern "C" int op3_debug_tc_trace(unsigned long long* out /*[256][4] host*/, int reset) {
   if (out) cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 256 * 4);
   if (reset) { static unsigned long long z[256][4]; cudaMemcpyToSymbol(g_tc_trace, z, sizeof(z)); }

@@ -39,6 +39,9 @@ def main():
         check(lib.op3_decoder_fwd(C.byref(d), N, ptr(prep), ptr(z), ptr(acts), ptr(out), st), "decoder_fwd")
     torch.cuda.synchronize()
     f(None, 1)
+    g = lib.op3_debug_tcq_epi
+    g.argtypes = [C.c_void_p, C.c_int]
+    g(None, 1)
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -55,6 +58,13 @@ def main():
           % tuple(t.mean(0) / launches))
     tot, nm = t[:, 2].mean() / launches, t[:, 3].mean() / launches
     print("cycles per MMA pair while issuing: %.1f" % ((tot - t[:, 0].mean() / launches - t[:, 1].mean() / launches) / (nm / 2)))
+    e = np.zeros(8, dtype=np.uint64)
+    g(e.ctypes.data, 0)
+    if e[3]:
+        n = float(e[3])
+        print("quint epilogue (warp 0 of every CTA, cycles per tile): wait for accumulators %.0f | TMEM loads + shuffles (-> slot released) %.0f | "
+              "group barrier %.0f | boundary fix-up %.0f | scale + bias + ELU + stores %.0f | second barrier %.0f"
+              % (e[0] / n, e[1] / n, e[2] / n, e[4] / n, e[5] / n, e[6] / n))
     print("max over CTAs total %.0f, min %.0f" % (t[:, 2].max() / launches, t[:, 2].min() / launches))
 
 
