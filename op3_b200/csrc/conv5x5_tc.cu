@@ -358,7 +358,7 @@ constexpr int TQ_NQ = 160;                          // 5 taps x 32 output channe
 constexpr int TQ_W_SLAB = 2 * TQ_NQ * 16;           // one (K group, ky, hi/lo) slab: [k-chunk 2][160 rows][16 B]
 constexpr int TQ_W_BYTES = 2 * 5 * 2 * TQ_W_SLAB;
 constexpr int TQ_XCH = 4 * 2 * 10 * 16;             // floats per exchange buffer: [quad][half][(kx, lane < kx)][16]
-constexpr int TQ_SMEM = TQ_A_BYTES + TQ_W_BYTES + 2 * TQ_XCH * 4;
+constexpr int TQ_SMEM = TQ_A_BYTES + TQ_W_BYTES + 2 * TQ_XCH * 4 + EPI_WARPS * 128 * 4;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
@@ -377,6 +377,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   uint8_t* a_s = smem_raw;
   uint4* w_s = reinterpret_cast<uint4*>(smem_raw + TQ_A_BYTES);
   float* xch = reinterpret_cast<float*>(smem_raw + TQ_A_BYTES + TQ_W_BYTES);
+  float* fixb = xch + 2 * TQ_XCH;                            // per epilogue warp: [4 target lanes][32] boundary sums
   __shared__ uint64_t full_bar[TQ_NSLOT], empty_bar[TQ_NSLOT], acc_full[3], acc_empty[3];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[32];
@@ -657,21 +658,31 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
 #ifdef OP3_TC_TRACE
         const unsigned long long te3 = clock64();
 #endif
-        if (quad < 3 && lane >= 28) {                        // rows whose shifted sources live in the next quadrant
+        if (quad < 3) {
+          // Rows whose shifted sources live in the next quadrant (lanes 28..31).  All 32 lanes gather: lane = (half, column)
+          // sums, for each of the four target lanes, the kx terms it is missing (10 conflict-free LDS instead of 160 issue
+          // slots spent on four active lanes); the targets then pick up their 32 sums with eight LDS.128.
+          float* fx = fixb + warp * 128;                     // [4 targets][32 (half, column)]
+          const float* src = xb + (((quad + 1) * 2 + (lane >> 4)) * 10) * 16 + (lane & 15);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const float4* src = reinterpret_cast<const float4*>(xb + (((quad + 1) * 2 + half) * 10) * 16);
+          for (int tt = 0; tt < 4; ++tt) {                   // target lane 28 + tt misses kx = 4 - tt .. 4 (source lane tt + kx - 4)
+            float sl = 0.f;
 #pragma unroll
-            for (int kx = 1; kx < 5; ++kx)
-              if (lane >= 32 - kx) {
-                const float4* sr = src + ((kx * (kx - 1)) / 2 + (lane + kx - 32)) * 4;
+            for (int kx = 4 - tt; kx <= 4; ++kx) sl += src[((kx * (kx - 1)) / 2 + (tt + kx - 4)) * 16];
+            fx[tt * 32 + lane] = sl;
+          }
+          __syncwarp();
+          if (lane >= 28) {
+            const float4* f4 = reinterpret_cast<const float4*>(fx + (lane - 28) * 32);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 t = sr[i];
-                  acc[half][4 * i] += t.x; acc[half][4 * i + 1] += t.y; acc[half][4 * i + 2] += t.z; acc[half][4 * i + 3] += t.w;
-                }
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t = f4[half * 4 + i];
+                acc[half][4 * i] += t.x; acc[half][4 * i + 1] += t.y; acc[half][4 * i + 2] += t.z; acc[half][4 * i + 3] += t.w;
               }
           }
+          __syncwarp();
         }
 #ifdef OP3_TC_TRACE
         const unsigned long long te4 = clock64();
