@@ -380,7 +380,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   float* fixb = xch + 2 * TQ_XCH;                            // per epilogue warp: [4 target lanes][32] boundary sums
   __shared__ uint64_t full_bar[TQ_NSLOT], empty_bar[TQ_NSLOT], acc_full[3], acc_empty[3];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[32];
+  __shared__ __align__(16) float s_bias[32];
 
   if (tid < 32) s_bias[tid] = (bias != nullptr && tid < cout_real) ? bias[tid] : 0.f;
   if (tid == 0) {
@@ -694,10 +694,9 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
             for (int i = 0; i < 4; ++i) {
               const int c4 = 4 * half + i;
               if (c4 >= out_chunks) continue;
-              float4 o = make_float4(acc[half][4 * i] * inv_scale + s_bias[16 * half + 4 * i],
-                                     acc[half][4 * i + 1] * inv_scale + s_bias[16 * half + 4 * i + 1],
-                                     acc[half][4 * i + 2] * inv_scale + s_bias[16 * half + 4 * i + 2],
-                                     acc[half][4 * i + 3] * inv_scale + s_bias[16 * half + 4 * i + 3]);
+              const float4 bb = *reinterpret_cast<const float4*>(&s_bias[16 * half + 4 * i]);
+              float4 o = make_float4(fmaf(acc[half][4 * i], inv_scale, bb.x), fmaf(acc[half][4 * i + 1], inv_scale, bb.y),
+                                     fmaf(acc[half][4 * i + 2], inv_scale, bb.z), fmaf(acc[half][4 * i + 3], inv_scale, bb.w));
               if (epi == EPI_ELU) {
                 o.x = elu_tc(o.x); o.y = elu_tc(o.y); o.z = elu_tc(o.z); o.w = elu_tc(o.w);
               } else if (epi == EPI_MUL_ELUGRAD) {
