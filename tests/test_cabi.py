@@ -100,3 +100,39 @@ def test_bench_reference_arm_prints_contract_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"]
+
+
+def test_install_aliases_and_device_dataset_host_logic():
+    """`op3_b200.install()` makes the reference's module names resolve to this package, including the data
+    feed; the device-resident dataset's sampler covers every item once per epoch (single process, CPU tensors)."""
+    import importlib
+    import sys
+    import torch
+    import op3_b200
+    saved = {k: sys.modules.get(k) for k in op3_b200._ALIASES}
+    try:
+        op3_b200.install()
+        for ref_name, ours in op3_b200._ALIASES.items():
+            assert sys.modules[ref_name] is importlib.import_module(ours), ref_name
+        from op3.torch.data_management.dataset import BlocksDataset, DeviceBlocksDataset   # noqa: F401 (resolves through the alias)
+        from op3.torch.op3_modules.op3_trainer import TrainingScheduler
+        assert list(TrainingScheduler(4, "curriculum", 5, 5).get_schedule(0, is_train=False)) == [0, 0, 0, 0, 1, 0]
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    from op3_b200.torch.data_management.dataset import DeviceBlocksDataset
+    frames = torch.arange(10, dtype=torch.uint8).view(1, 10, 1, 1, 1).expand(3, 10, 4, 4, 3).contiguous()   # HDF5 layout (T,N,D,D,3)
+    ds = DeviceBlocksDataset(frames, None, batchsize=4, shuffle=True, seed=1, drop_last=False, time_major=True)
+    assert ds.n == 10 and ds.action_dim == 0 and len(ds.dataloader) == 3
+    seen = []
+    for (fr,) in ds.dataloader:
+        assert fr.shape[1:] == (3, 4, 4, 3) and fr.dtype == torch.uint8
+        seen += fr[:, 0, 0, 0, 0].tolist()
+    assert sorted(seen) == list(range(10))
+    first = [b[0][:, 0, 0, 0, 0].tolist() for b in ds.dataloader]
+    ds2 = DeviceBlocksDataset(frames, None, batchsize=4, shuffle=True, seed=1, drop_last=False, time_major=True)
+    ds2.epoch = 1
+    assert [b[0][:, 0, 0, 0, 0].tolist() for b in ds2.dataloader] == first     # the permutation is a function of (seed, epoch)
