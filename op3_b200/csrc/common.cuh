@@ -75,6 +75,26 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- per-device host-side caches: cudaFuncSetAttribute and the SM count belong to the CURRENT device, not the process
+constexpr int OP3_MAX_DEVICES = 64;
+struct PerDeviceOnce {          // `static PerDeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)`
+  bool done[OP3_MAX_DEVICES] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= OP3_MAX_DEVICES) return true;
+    const bool f = !done[dev];
+    done[dev] = true;
+    return f;
+  }
+};
+inline int device_sm_count() {  // SMs of the current device (cached per device)
+  static int sms[OP3_MAX_DEVICES] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= OP3_MAX_DEVICES) return 148;
+  if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
+  return sms[dev];
+}
+
 // ---- internal kernels shared between translation units ----------------------------------------
 // gemm.cu ------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2 };

@@ -142,11 +142,10 @@ int launch_fwd(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
                int epi, const float4* ref) {
   constexpr int NT = 128 * (COUT / COUT_T);
   size_t smem = 2 * (size_t)(FWD_IN_F4 + 25 * COUT) * sizeof(float4);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_fwd_kernel<COUT, COUT_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    attr_set = true;
   }
   int tiles = ceil_div(D, TW) * ceil_div(D, TR);
   dim3 grid(tiles, N);
@@ -431,11 +430,10 @@ int launch_wgrad(cudaStream_t st, int N, int D, const ConvInput& in, const float
   size_t smem = 2 * (size_t)(WG_IN_F4 + DP_F4) * sizeof(float4);
   size_t red = (size_t)NT * 6 * COG * sizeof(float);
   if (red > smem) smem = red;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_kernel<COUT, COG, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    attr_set = true;
   }
   int chunks = in.total_chunks;
   long long total_tiles = (long long)N * ceil_div(D, TW) * (D / WR);
@@ -460,10 +458,9 @@ int launch_wgrad2(cudaStream_t st, int N, int D, const ConvInput& in, const floa
   size_t smem = 2 * (size_t)(IN_F4 + DP_F4) * sizeof(float4);
   size_t red = (size_t)NT * 104 * sizeof(float);
   if (red > smem) smem = red;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad2_kernel<COUT, WR2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   int chunks = in.total_chunks;
   long long total_tiles = (long long)N * ceil_div(D, TW) * (D / WR2);

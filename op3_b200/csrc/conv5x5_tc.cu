@@ -732,7 +732,6 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
-int g_num_sms = 0;
 
 // per-image largest magnitude of a conv input (fp32 bit pattern; non-negative floats order like unsigned ints)
 __global__ void __launch_bounds__(256) tc_absmax_kernel(ConvInput in, int D, uint32_t* __restrict__ maxbits) {
@@ -763,16 +762,11 @@ int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* w
     if (smem <= 226 * 1024) break;
   }
   OP3_REQUIRE(G >= 1, "conv5x5_tc: D=%d does not fit in shared memory", D);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_tc_kernel<NOUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    OP3_CHECK(cudaGetDevice(&dev));
-    OP3_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_num_sms = device_sm_count();
   const int tiles_img = (D * P + 127) / 128;
   const int groups_img = (tiles_img + G - 1) / G;
   const int n_items = N * groups_img;
@@ -787,16 +781,11 @@ int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* w
 int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* wt, const float* bias, int cout_real,
                float4* out, int out_planes, int out_chunk0, int out_chunks, int epi, const float4* ref,
                const uint32_t* maxbits, const float* wscale) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
-    attr_set = true;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    OP3_CHECK(cudaGetDevice(&dev));
-    OP3_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_num_sms = device_sm_count();
   const int P = D + TQ_PAD;
   const long long total = (long long)N * ((D * P + TQ_TS - 1) / TQ_TS);
   const int grid = total < g_num_sms ? (int)total : g_num_sms;

@@ -1115,10 +1115,9 @@ int launch_wgrad_tc(cudaStream_t st, int N, int D, const ConvInput& in, const fl
   size_t red = (size_t)(3 * 2 * 32 * NCO + 64) * sizeof(float);
   if (red > smem) smem = red;
   OP3_REQUIRE(smem <= 226 * 1024, "conv5x5_wgrad_tc: %zu bytes of shared memory", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_tc_kernel<NCO, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
   }
   dim3 grid(wg_sets(), 5);
   conv5x5_wgrad_tc_kernel<NCO, SPLIT3><<<grid, WG_THREADS, smem, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total,
@@ -1133,10 +1132,9 @@ int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const f
                      int gmax_n, float* scratch) {
   size_t smem = HG_GROUPS * (size_t)HG_STAGE_BYTES;
   OP3_REQUIRE(smem <= 226 * 1024, "conv5x5_wgrad_f16: %zu bytes of shared memory", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
   }
   dim3 grid(wg_sets(), 5);
   conv5x5_wgrad_f16_kernel<<<grid, HG_THREADS, smem, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total, co0, xmax,
@@ -1146,23 +1144,15 @@ int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const f
   return OP3_OK;
 }
 
-int g_wg_sms = 0;
-
 // returns the number of per-CTA partial slabs written (the grid size)
 int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, int g_planes, int g_chunk0,
                       int g_chunks, int cout_total, int co0, const uint32_t* xmax, int xmax_n, const uint32_t* gmax,
                       int gmax_n, float* scratch, int* grid_out) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
   }
-  if (g_wg_sms == 0) {
-    int dev = 0;
-    OP3_CHECK(cudaGetDevice(&dev));
-    OP3_CHECK(cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev));
-    if (g_wg_sms > 148) g_wg_sms = 148;                     // scratch is sized for 148 slabs
-  }
+  const int g_wg_sms = device_sm_count() > 148 ? 148 : device_sm_count();   // scratch is sized for 148 slabs
   const int P = D + 8, NBLK = ((D + 4) * P + HG_BP - 1) / HG_BP;
   const long long total_blocks = (long long)N * NBLK;
   const int grid = total_blocks < g_wg_sms ? (int)total_blocks : g_wg_sms;

@@ -830,10 +830,9 @@ extern "C" int op3_mixture_fwd(const Op3Dims* d, const Op3Params* p, const Op3Mi
     const float* nul = nullptr;
 #define OP3_MIX_FUSED(KM, EX)                                                                                          \
   do {                                                                                                                 \
-    static bool attr_set = false;                                                                                      \
-    if (!attr_set) {                                                                                                   \
+    static PerDeviceOnce attr_once;                                                                                    \
+    if (attr_once.first()) {                                                                                           \
       OP3_CHECK(cudaFuncSetAttribute(mix_fused_kernel<KM, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      attr_set = true;                                                                                                 \
     }                                                                                                                  \
     mix_fused_kernel<KM, EX><<<gf, MIXF_THREADS, fused_smem, st>>>(                                                    \
         *io, io->mse_image, io->mse_image_bstride, emit ? p->ln2d_gamma[0] : nul, emit ? p->ln2d_gamma[1] : nul,       \

@@ -215,6 +215,20 @@ class Engine:
     # ------------------------------------------------------------------ forward
     def forward(self, images, actions, init_state, schedule, loss_schedule, noise_fn, need_grad):
         """Returns (outputs dict, tape or None).  images (B,T,3,D,D) float32 cuda or None; actions (B,T,A) or None."""
+        ref = images if images is not None else actions if actions is not None else (
+            init_state["post"]["samples"] if init_state is not None else None)
+        if ref is None:
+            raise ValueError("Need either images or actions")
+        if ref.device.type != "cuda":
+            raise RuntimeError("op3_b200: inputs are on %s; the OP3 kernels are CUDA-only (no CPU fallback)" % ref.device)
+        pdev = self.flat_params().device
+        if ref.device != pdev:
+            raise RuntimeError("op3_b200: inputs are on %s but the model parameters are on %s (one process per GPU; "
+                               "nn.DataParallel replication is not supported)" % (ref.device, pdev))
+        with torch.cuda.device(ref.device):       # launches, attribute caches and streams belong to the tensors' device
+            return self._forward(images, actions, init_state, schedule, loss_schedule, noise_fn, need_grad)
+
+    def _forward(self, images, actions, init_state, schedule, loss_schedule, noise_fn, need_grad):
         m, lib = self.model, self.lib
         if images is not None:
             B, dev = images.shape[0], images.device
@@ -277,9 +291,6 @@ class Engine:
             post, prior = init_state["post"], init_state["prior"]
             if post["samples"].shape[0] != B:
                 raise ValueError("initial_hidden_state batch %d != input batch %d" % (post["samples"].shape[0], B))
-            if schedule and schedule[0] in (0, 2) and not post["lambdas1"].requires_grad:
-                # contract of the reference (trap T9): autograd.grad in refine() needs lambdas that require grad
-                raise RuntimeError("One of the differentiated Tensors does not require grad")
             s0.l1 = post["lambdas1"].detach().reshape(N, Rs).contiguous().float()
             s0.l2 = post["lambdas2"].detach().reshape(N, Rs).contiguous().float()
             s0.z = torch.empty(N, R, **f32)
@@ -423,10 +434,16 @@ class Engine:
                 cur += 1
             state = step.dst
             refine_after = i + 1 < T1 and schedule[i + 1] in (0, 2)
-            need_img = lw[i] != 0.0 or refine_after or (i == T1 - 1 and images is not None)
-            img = images[:, cur] if (need_img and images is not None) else None
-            if (lw[i] != 0.0 or refine_after) and img is None:
-                raise ValueError("loss / refinement at step %d needs images" % i)
+            img = None
+            if lw[i] != 0.0 or refine_after:
+                if images is None:
+                    raise ValueError("loss / refinement at step %d needs images" % i)
+                img = images[:, cur]            # IndexError past the last frame, like the reference (op3_model.py:383)
+            elif i == T1 - 1 and images is not None:
+                # only the final mse (against images[:, -1], op3_model.py:411) is needed: a rollout may run past the
+                # last observed frame (mpc_stack.py:256-257: obs (B,1,...) with schedule [0,0,0,0,1]); the per-step
+                # likelihood statistics of this decode carry zero weight, so any observed frame serves as their target
+                img = images[:, min(cur, images.shape[1] - 1)]
             cached = decode(state, i, img, lw[i], refine_after, i == T1 - 1)
             if need_grad:
                 steps.append(step)
@@ -457,6 +474,10 @@ class Engine:
     def backward(self, tape, g_total, g_kle, g_clog):
         """Accumulate d(g_total*total + g_kle*kle + g_clog*clog)/d params into a fresh flat gradient buffer and
         return it (same layout as flat_params())."""
+        with torch.cuda.device(self.flat_params().device):
+            return self._backward(tape, g_total, g_kle, g_clog)
+
+    def _backward(self, tape, g_total, g_kle, g_clog):
         m, lib = self.model, self.lib
         d, B = tape.dims, tape.B
         K, D, Rd, Rs = m.K, m.image_size, m.det_size, m.sto_size

@@ -18,6 +18,19 @@ def _require_cuda(t, what):
         raise RuntimeError("op3_b200: %s is on %s; the OP3 kernels are CUDA-only (no CPU fallback)" % (what, t.device))
 
 
+def _on_tensor_device(fn):
+    """Run `fn(net, x, ...)` with x's device current: launches and attribute caches are per device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(net, x, *args, **kw):
+        _require_cuda(x, "input")
+        with torch.cuda.device(x.device):
+            return fn(net, x, *args, **kw)
+    return wrapper
+
+
+@_on_tensor_device
 def decoder_forward(net, latents, engine=None):
     """DecoderNetwork.forward (decoder_network.py:83-88): latents (N,R) -> (mask_logits (N,1,D,D), colors (N,3,D,D))."""
     lib = _lib.load()
@@ -57,6 +70,7 @@ def _mlp_ptrs(struct_mlp, mlp, keep):
         field.w, field.b = w.data_ptr(), b.data_ptr()
 
 
+@_on_tensor_device
 def physics_forward(net, sampled_state, actions, K=None, engine=None):
     """PhysicsNetwork.forward (physics_network.py:94-141) + attention probes (:156-187).
     Returns (deter or None, lambdas1, lambdas2, act_att (N,1) or None, pair_att (N,K-1,1) or None, deltas (N,1))."""
@@ -110,6 +124,7 @@ def physics_forward(net, sampled_state, actions, K=None, engine=None):
 _REF_CHANNEL = [3, 4, 5, 7, 6, 8, 9, 11, 12, 13, 14, -1, 0, 1, 2, 10, 15, 16, -1, -1]
 
 
+@_on_tensor_device
 def refinement_forward(net, a, h, c, extra):
     """RefinementNetwork.forward (refinement_network.py:189-219): a (N,15,D,D), h/c (N,128) or (1,N,128), extra (N,5*Rs)
     -> (lambdas1 (N,Rs), lambdas2 (N,Rs), h (1,N,128), c (1,N,128))."""

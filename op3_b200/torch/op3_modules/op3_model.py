@@ -108,6 +108,20 @@ class OP3Model(nn.Module):
             object.__setattr__(self, "_engine", Engine(self))
         return self._engine
 
+    def __getstate__(self):
+        # the engine holds a ctypes handle and device buffers keyed to THIS module: never pickled / deep-copied
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        return state
+
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel (train_op3.py:99-100 with variant['dataparallel']) shallow-copies __dict__, so every replica
+        # would share one Engine bound to device 0's parameters.  Multi-GPU here is one process per GPU (torchrun).
+        if torch.cuda.device_count() > 1:
+            raise RuntimeError("op3_b200: nn.DataParallel over several GPUs is not supported; launch one process per GPU "
+                               "with torchrun (OP3Trainer all-reduces the gradients) and set variant['dataparallel']=False")
+        return super()._replicate_for_data_parallel()
+
     def _noise(self, B, K, Rs, dev):
         if self.deterministic_sampling:          # samples = means (op3_model.py:148-149)
             return torch.zeros(B, K, Rs, device=dev)
@@ -182,8 +196,9 @@ class OP3Model(nn.Module):
         return self._tensors_to_state(self._state_to_tensors(out["state"], B))
 
     def refine(self, hidden_states, images, action=None, previous_decode_loss_info=None):
-        """op3_model.py:195-264 (inference form): one refinement step on `images` (B,3,D,D).  Like the reference it
-        needs posterior lambdas that require grad (a detached state must pass through a dynamics step first)."""
+        """op3_model.py:195-264 (inference form): one refinement step on `images` (B,3,D,D).  The gradient inputs of
+        the refinement network are closed forms computed by the kernels, so -- unlike the reference, whose
+        autograd.grad needs lambdas that require grad -- any state (detached or not) can be refined."""
         # `action` is only forwarded to the refinement net as add_fc_input (op3_model.py:233-244); the built
         # 'size_dependent_conv' architecture has added_fc_input_size=0 and ignores it (refinement_network.py:201-202)
         return self._step_from(hidden_states, images, None, 0)

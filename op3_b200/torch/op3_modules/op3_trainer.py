@@ -99,9 +99,15 @@ class FusedClipAdam:
                 g[o:o + p.numel()].copy_(p.grad.reshape(-1))
         return flat, g
 
-    def step(self, grad_scale=1.0):
+    def step(self, grad_scale=1.0, flat_grad=None):
+        """`flat_grad`: an already gathered (e.g. all-reduced) flat gradient buffer; default: gather from p.grad."""
         lib = _lib.load()
-        flat, g = self._flat_grad()
+        if flat_grad is None:
+            flat, g = self._flat_grad()
+        else:
+            flat, g = self.model.engine.flat_params(), flat_grad
+            if g.numel() != flat.numel() or g.device != flat.device:
+                raise ValueError("flat_grad must match the flat parameter buffer")
         if self.exp_avg is None or self.exp_avg.data_ptr() == 0 or self.exp_avg.numel() != flat.numel():
             self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
             self.scratch = torch.zeros(2048, device=flat.device)
@@ -187,13 +193,12 @@ class OP3Trainer:
             true_images, actions, initial_hidden_state=None, schedule=schedule, loss_schedule=loss_schedule)
         total_loss, total_clog_prob, total_kle_loss, mse = total_loss.mean(), total_clog_prob.mean(), total_kle_loss.mean(), mse.mean()
         total_loss.backward()
-        scale = 1.0
+        scale, g = 1.0, None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            _, g = self.optimizer._flat_grad()
+            _, g = self.optimizer._flat_grad()                # gathered ONCE: the reduced buffer is what step() consumes
             dist.all_reduce(g, op=dist.ReduceOp.SUM)          # one flat 3.5-3.8 MB buffer, NCCL over NVLink
-            self._core().engine.last_flat_grad = g
             scale = 1.0 / dist.get_world_size()
-        self.optimizer.step(grad_scale=scale)
+        self.optimizer.step(grad_scale=scale, flat_grad=g)
         return total_loss.detach(), total_clog_prob.detach(), total_kle_loss.detach(), mse.detach()
 
     def train_epoch(self, epoch):
