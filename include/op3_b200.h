@@ -266,6 +266,10 @@ int op3_cem_resample(int Na, int TA, const float* mean, const float* std, const 
  * (channels_last = 0) or [n_frames][D][D][3] (channels_last = 1) bytes; out: [n_frames][3][D][D] floats. */
 int op3_prepare_frames(long long n_frames, int D, int channels_last, const unsigned char* in, float* out, void* stream);
 
+/* One layer of Mlp.forward (op3/torch/networks.py:63-74): y[M][out] = act(x[M][in] W^T + b), W [out][in] (nn.Linear).
+ * act: 0 identity, 1 ELU, 2 sigmoid, 3 ReLU, 4 tanh. */
+int op3_linear_fwd(int M, int in, int out, const float* x, const float* w, const float* b, int act, float* y, void* stream);
+
 /* sub_images[a][k][c] = colors*mask (op3_model.py:612) from planar colours / masks */
 int op3_sub_images(long long n_slots, int D, const float* colors, const float* mask, float* out, void* stream);
 

@@ -46,5 +46,24 @@ def install():
     reference scripts import their modules."""
     import importlib
     import sys
+    import types
     for ref_name, ours in _ALIASES.items():
-        sys.modules[ref_name] = importlib.import_module(ours)
+        mod = importlib.import_module(ours)
+        sys.modules[ref_name] = mod
+        # `import op3.torch.op3_modules.op3_model as m` walks attributes from the top-level package, so the alias must
+        # also hang off its parent packages (the reference's own, when its checkout is importable; bare namespace
+        # stand-ins otherwise)
+        parent_name, leaf = ref_name.rsplit(".", 1)
+        parts = parent_name.split(".")
+        for i in range(1, len(parts) + 1):
+            name = ".".join(parts[:i])
+            if name not in sys.modules:
+                try:
+                    importlib.import_module(name)
+                except ImportError:
+                    pkg = types.ModuleType(name)
+                    pkg.__path__ = []
+                    sys.modules[name] = pkg
+            if i > 1:
+                setattr(sys.modules[".".join(parts[:i - 1])], parts[i - 1], sys.modules[name])
+        setattr(sys.modules[parent_name], leaf, mod)

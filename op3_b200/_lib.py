@@ -99,6 +99,7 @@ SIGNATURES = {
     "op3_get_loss": (C.c_int, [_P(Op3Dims), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "op3_sub_images": (C.c_int, [C.c_longlong, C.c_int, c_fp, c_fp, c_fp, c_fp]),
     "op3_prepare_frames": (C.c_int, [C.c_longlong, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
+    "op3_linear_fwd": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_int, c_fp, c_fp]),
     "op3_cem_refit": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp, C.c_float, c_fp, c_fp, c_fp]),
     "op3_cem_resample": (C.c_int, [C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
 }

@@ -97,7 +97,7 @@ inline int device_sm_count() {  // SMs of the current device (cached per device)
 
 // ---- internal kernels shared between translation units ----------------------------------------
 // gemm.cu ------------------------------------------------------------------------------------
-enum { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2 };
+enum { ACT_NONE = 0, ACT_ELU = 1, ACT_SIGMOID = 2, ACT_RELU = 3, ACT_TANH = 4 };
 // C[M,N] = act( opA(A)[M,K] * opB(B)[K,N] + bias[N] ) (+ C if accumulate)
 //   transA=0: A is row-major [M,K] (lda); transA=1: A is stored [K,M] (lda)
 //   transB=0: B is stored [K,N] (ldb);    transB=1: B is stored [N,K] (ldb)  (nn.Linear weight)

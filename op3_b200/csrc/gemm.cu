@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
         if (accumulate) v += C[(size_t)gm * ldc + gn];
         if (act == ACT_ELU) v = elu_f(v);
         else if (act == ACT_SIGMOID) v = sigmoid_f(v);
+        else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == ACT_TANH) v = tanhf(v);
         C[(size_t)gm * ldc + gn] = v;
       }
     }
@@ -226,3 +228,11 @@ int fill_zero(cudaStream_t st, void* p, size_t bytes) {
 }
 
 }  // namespace op3
+
+// y[M][out] = act(x[M][in] W^T + b): one nn.Linear + activation of networks.py:63-74 (Mlp.forward)
+extern "C" int op3_linear_fwd(int M, int in, int out, const float* x, const float* w, const float* b, int act, float* y,
+                              void* stream) {
+  OP3_REQUIRE(M >= 0 && in > 0 && out > 0 && x && w && y, "op3_linear_fwd: bad arguments");
+  OP3_REQUIRE(act >= op3::ACT_NONE && act <= op3::ACT_TANH, "op3_linear_fwd: activation %d not in 0..4", act);
+  return op3::gemm((cudaStream_t)stream, M, out, in, x, in, 0, w, in, 1, y, out, b, act, 0);
+}

@@ -202,6 +202,125 @@ def mpc_large_case(Na=4096):
     print("mpc_4096 ok", np.asarray(order)[:5], np.asarray(sc)[:3])
 
 
+def activation_case():
+    """OP3Model.get_all_activation_values / get_activation_values (op3_model.py:645-698) for 23 probe actions on the
+    B=1 state of mpc_case (pickplace latent-action MPC, mpc_pickplace.py:663-703)."""
+    K, Np = 4, 23
+    m, p = build_reference(pickplace_variant, K, 4, seed=7)
+    m.eval_mode = True
+    frames = synth_frames(1, 2, seed=31)
+    acts = synth_actions(1, 2, seed=32)[:, :, [0, 1, 3, 4]]
+    NOISE.load(orc.make_noise(1, K, 64, 5, seed=40))
+    info = m.batch_internal_inference(frames, acts, None, np.array([0, 0, 1, 0], dtype=np.float64))
+    probe = synth_actions(Np, 1, seed=35)[:, 0][:, [0, 1, 3, 4]]
+    sa, ia, dv, ld = m.get_all_activation_values(info["state"], probe)
+    sa1 = m.get_activation_values(info["state"], probe)
+    np.savez_compressed(os.path.join(HERE, "activations.npz"), K=K, Np=Np, state_action=sa.numpy(), interaction=ia.numpy(),
+                        deltas=dv.numpy(), lambda_deltas=ld.numpy(), state_action_only=sa1.detach().numpy())
+    print("activations ok", sa.shape, ia.shape)
+
+
+def chunked_noise(full, chunk):
+    """Reference draw order of batch_internal_inference (op3_model.py:569-642): per chunk of `chunk` samples one draw
+    for the initial state (if it is created) and one per schedule step.  `full` = list of (Na,K,Rs) tensors."""
+    Na = full[0].shape[0]
+    return [f[i:i + chunk] for i in range(0, Na, chunk) for f in full]
+
+
+def mpc_stack_case(Na=4096):
+    """BASELINE.json config 5, stack flavour (mpc_stack.py:249-258): Na candidate AFTER-images (B,T=1,3,D,D), no
+    actions, no initial state, schedule [0,0,0,0,1] (K=7, action_dim 0), ranked with Cost(subimage, mse, raw, min)
+    (mpc_stack.py:553-558) against the goal latents of a goal frame refined 5 times (mpc_stack.py:403-423)."""
+    K = 7
+    m, p = build_reference(stack_variant, K, 0, seed=7)
+    m.eval_mode = True
+    goal_frames = synth_frames(1, 1, seed=61)
+    NOISE.load(orc.make_noise(1, K, 64, 6, seed=62))
+    goal = m.batch_internal_inference(goal_frames, None, None, np.zeros(5))
+    obs = synth_frames(Na, 1, seed=63)
+    sched = np.array([0, 0, 0, 0, 1], dtype=np.float64)
+    full = orc.make_noise(Na, K, 64, len(sched) + 1, seed=64)
+    NOISE.load(chunked_noise(full, 10))
+    pred = m.batch_internal_inference(obs, None, None, sched)
+    import exps.stack_exps.mpc_stack as ref_stack
+    cost = ref_stack.Cost(None, core_type="subimage", compare_func="mse", post_process="raw", aggregate="min")
+    sc, order, gidx = cost.get_action_rankings(goal["state"]["post"]["samples"][0], goal["sub_images"][0], goal_frames[:, 0],
+                                               pred["state"]["post"]["samples"], pred["sub_images"], pred["final_recon"],
+                                               plot_actions=0)
+    res = {"Na": Na, "K": K, "sorted": np.asarray(sc, dtype=np.float32), "order": np.asarray(order, dtype=np.int32),
+           "gidx": np.asarray(gidx, dtype=np.int32)}
+    summarize("goal/sub_images", goal["sub_images"], res)
+    summarize("pred/final_recon", pred["final_recon"], res)
+    summarize("pred/sub_images", pred["sub_images"], res)
+    summarize("pred/samples", pred["state"]["post"]["samples"], res)
+    np.savez_compressed(os.path.join(HERE, "mpc_stack_%d.npz" % Na), **res)
+    print("mpc_stack ok", np.asarray(order)[:5], np.asarray(sc)[:3])
+
+
+def pretrained_case():
+    """REPORTED (not gated): the three shipped checkpoints on the shipped real frames
+    (data/goals), one training step each in fp32 AND fp64 of the reference.  Weights + inputs + outputs are committed
+    so that the GPU box (no /root/reference) can replay them (tests/test_gpu_pretrained.py)."""
+    import pickle
+    REF = "/root/reference"
+    cases = [
+        ("stack", "exps/stack_exps/saved_models/s64d64_v1_params.pkl", stack_variant, 7, 0, [0, 0, 0, 0, 1]),
+        ("pickplace", "exps/pickplace_exps/saved_models/curriculum_aws_params.pkl", pickplace_variant, 4, 4,
+         [0, 0, 0, 0, 1, 1, 1, 1, 0]),
+        ("cloth", "exps/realworld_exps/saved_models/cloth_reg_params.pkl", pickplace_variant, 4, 4, [0, 0, 0, 0, 1, 1, 0]),
+    ]
+    # real frames: stack before/after pairs, pickplace 5-frame trajectories with 6-dim actions
+    pairs = []
+    for name in ["bridge", "air-cube", "double-bridge", "air-triangle"]:
+        d = pickle.load(open(os.path.join(REF, "data/goals/stack_goals/manual_constructions", name, "0.p"), "rb"))
+        pairs.append(np.asarray(d["images"], dtype=np.uint8))                      # (2,64,64,3)
+    stack_frames = np.stack(pairs)                                                 # (4,2,64,64,3)
+    gd = pickle.load(open(os.path.join(REF, "data/goals/pickplace_goals/objects_seed_2/goal_data.pkl"), "rb"))
+    pp_frames = np.asarray(gd["frames"][:4], dtype=np.uint8)                       # (4,5,64,64,3)
+    pp_actions = np.asarray(gd["actions"][:4], dtype=np.float32)                   # (4,4,6)
+    for name, ckpt, variant, K, A, sched in cases:
+        sd = torch.load(os.path.join(REF, ckpt), map_location="cpu")
+        sd = {k[len("module."):] if k.startswith("module.") else k: v.float() for k, v in sd.items()}
+        if name == "stack":
+            fr_u8, acts = stack_frames, None
+        else:
+            fr_u8 = pp_frames
+            acts = torch.from_numpy(np.concatenate([pp_actions, pp_actions[:, -1:]], 1))   # (4,5,6): T actions
+        B, T = fr_u8.shape[:2]
+        frames = torch.from_numpy(fr_u8).permute(0, 1, 4, 2, 3).float() / 255.0
+        schedule = np.array(sched, dtype=np.float64)
+        lw = np.arange(1, len(sched) + 1)
+        noise = orc.make_noise(B, K, 64, len(sched) + 1, seed=70)
+        res = {"schedule": schedule, "K": K, "action_dim": A, "frames_u8": fr_u8}
+        if acts is not None:
+            res["actions"] = acts.numpy()
+        for k, v in sd.items():
+            res["w/" + k] = v.numpy()
+        for tag, dt in [("f32", torch.float32), ("f64", torch.float64)]:
+            torch.set_default_dtype(dt)          # ptu.zeros / torch.zeros inside the reference follow the default
+            a = dict(variant["op3_args"]); a["K"] = K
+            m = ref_model.create_model_v2(a, a["det_repsize"], a["sto_repsize"], A)
+            m.load_state_dict(sd, strict=True)
+            m = m.to(dt)
+            m.decode_net.broadcast_net.coords = m.decode_net.broadcast_net.coords.to(dt)
+            m.refinement_net.coords = m.refinement_net.coords.to(dt)
+            NOISE.load([n.to(dt) for n in noise])
+            out = m.forward(frames.to(dt), None if acts is None else acts.to(dt), None, schedule, lw)
+            out[3].backward()
+            res[tag + "/total_loss"] = out[3].item(); res[tag + "/kle_loss"] = out[4].item()
+            res[tag + "/clog_prob"] = out[5].item(); res[tag + "/mse"] = out[6].item()
+            res[tag + "/masks_last"] = out[1][:, -1].detach().float().numpy().astype(np.float16)
+            res[tag + "/final_recon"] = out[2].detach().float().numpy()
+            summarize(tag + "/masks_list", out[1], res)
+            for k, v in m.named_parameters():
+                summarize(tag + "/grad/" + k, v.grad if v.grad is not None else torch.zeros_like(v), res)
+            res[tag + "/grad_total_norm"] = float(torch.sqrt(sum((v.grad.double() ** 2).sum() for v in m.parameters()
+                                                                 if v.grad is not None)))
+            print("pretrained", name, tag, "loss", res[tag + "/total_loss"], "mse", res[tag + "/mse"])
+        torch.set_default_dtype(torch.float32)
+        np.savez_compressed(os.path.join(HERE, "pretrained_%s.npz" % name), **res)
+
+
 def schedule_case():
     """TrainingScheduler outputs (op3_trainer.py:36-111) for every schedule type under a fixed numpy seed."""
     from op3.torch.op3_modules.op3_trainer import TrainingScheduler as Ref
@@ -222,6 +341,12 @@ def schedule_case():
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:                       # e.g. `make_golden.py mpc_stack pretrained`: regenerate selected (slow) cases only
+        for name in only:
+            {"mpc_stack": mpc_stack_case, "pretrained": pretrained_case, "mpc_large": mpc_large_case,
+             "mpc_stack_small": lambda: mpc_stack_case(Na=40), "activations": activation_case}[name]()
+        sys.exit(0)
     schedule_case()
     train_case("stack_small", stack_variant, K=3, action_dim=0, B=2, T=2, schedule=[0, 0, 1], full_masks=True)
     train_case("pickplace_small", pickplace_variant, K=3, action_dim=4, B=2, T=3, schedule=[0, 0, 1, 1, 0],
@@ -232,3 +357,7 @@ if __name__ == "__main__":
     module_case()
     mpc_case()
     mpc_large_case()
+    activation_case()
+    pretrained_case()
+    mpc_stack_case(Na=40)
+    mpc_stack_case()               # ~30-60 min of CPU: 4096 candidates x (5 decodes + 4 refinements), K=7

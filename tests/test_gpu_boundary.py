@@ -1,0 +1,123 @@
+"""GPU: the reference-facing surface beyond forward/backward -- attention probes at model level
+(op3_model.py:645-698), Mlp.forward (networks.py:63-74), checkpoint round trips (op3_trainer.py:145-146,
+mpc_stack.py:465-473) and optimizer-state resume."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import op3_oracle as orc
+from helpers import load_golden
+from gpu_util import build_model, NoiseInjector, max_abs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_get_all_activation_values_match_reference_golden():
+    """Golden from the unmodified reference (make_golden.activation_case): 23 probe actions on a B=1 state."""
+    g = load_golden("activations")
+    K, Np = int(g["K"]), int(g["Np"])
+    m, p = build_model(4, K, seed=7)
+    m.eval_mode = True
+    frames = orc.synth_frames(1, 2, seed=31).cuda()
+    acts = orc.synth_actions(1, 2, seed=32)[:, :, [0, 1, 3, 4]].cuda()
+    with NoiseInjector(orc.make_noise(1, K, 64, 5, seed=40)):
+        info = m.batch_internal_inference(frames, acts, None, np.array([0., 0., 1., 0.]))
+    probe = orc.synth_actions(Np, 1, seed=35)[:, 0][:, [0, 1, 3, 4]].cuda()
+    sa, ia, dv, ld = m.get_all_activation_values(info["state"], probe)
+    assert sa.shape == (Np, K) and ia.shape == (Np, K, K - 1) and dv.shape == (Np, K) and ld.shape == (Np, K)
+    assert max_abs(sa, torch.from_numpy(g["state_action"])) <= 2e-5
+    assert max_abs(ia, torch.from_numpy(g["interaction"])) <= 2e-5
+    for ours, key in [(dv, "deltas"), (ld, "lambda_deltas")]:
+        ref = torch.from_numpy(g[key])
+        assert max_abs(ours, ref) <= 1e-4 * ref.abs().max().item() + 1e-5, key
+    sa1 = m.get_activation_values(info["state"], probe)
+    assert max_abs(sa1, torch.from_numpy(g["state_action_only"])) <= 2e-5
+
+
+@pytest.mark.parametrize("hidden,out_act", [(F.relu, None), (torch.nn.ELU(), torch.nn.Sigmoid()), (torch.tanh, None)])
+def test_mlp_forward_matches_torch(hidden, out_act):
+    from op3_b200.torch.networks import Mlp, identity
+    torch.manual_seed(3)
+    mlp = Mlp((96, 40), 7, 33, hidden_activation=hidden, output_activation=out_act or identity)
+    x = torch.randn(5, 11, 33)
+    h = x
+    for fc in mlp.fcs:
+        h = hidden(F.linear(h, fc.weight, fc.bias))
+    pre = F.linear(h, mlp.last_fc.weight, mlp.last_fc.bias)
+    want = out_act(pre) if out_act else pre
+    mlp = mlp.cuda()
+    got, got_pre = mlp(x.cuda(), return_preactivations=True)
+    assert got.shape == (5, 11, 7)
+    assert max_abs(got, want.detach()) <= 2e-6 and max_abs(got_pre, pre.detach()) <= 2e-6
+    assert max_abs(mlp(x.cuda()), want.detach()) <= 2e-6
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        mlp(x)
+
+
+def test_save_model_reload_and_optimizer_resume(tmp_path):
+    """save_model writes `<prefix>_params.pkl` with `module.` keys (the reference's DataParallel checkpoints,
+    op3_trainer.py:145-146); reloading it the way mpc_stack.py:465-473 does gives the same model; restoring the
+    optimizer state_dict continues the Adam trajectory bit for bit."""
+    from op3_b200.torch.op3_modules.op3_trainer import OP3Trainer, TrainingScheduler
+    B, K, T, sched = 2, 3, 2, np.array([0., 0., 1.])
+    lw = np.arange(1, 4)
+    frames = orc.synth_frames(B, T).cuda()
+
+    def make():
+        m, _ = build_model(0, K, seed=0)
+        return OP3Trainer(None, None, m, TrainingScheduler(2, "single_step_physics", None, T), B, lr=3e-4)
+
+    def step(tr, i):
+        with NoiseInjector(orc.make_noise(B, K, 64, 4, seed=100 + i)):
+            return [float(v) for v in tr.train_step(frames, None, sched, lw)]
+
+    a = make()
+    for i in range(2):
+        step(a, i)
+    a.save_model("ckpt", directory=str(tmp_path))
+    opt_state = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in a.optimizer.state_dict().items()}
+    want = [step(a, i) for i in (2, 3)]
+
+    # reload like the MPC scripts: strip `module.`, load_state_dict strict
+    sd = torch.load(os.path.join(str(tmp_path), "ckpt_params.pkl"), map_location="cpu")
+    assert all(k.startswith("module.") for k in sd)
+    b = make()
+    b.model.load_state_dict({k[len("module."):]: v for k, v in sd.items()}, strict=True)
+    b.optimizer.load_state_dict(opt_state)
+    got = [step(b, i) for i in (2, 3)]
+    assert got == want, "resumed trajectory differs: %r vs %r" % (got, want)
+    for (k, pa), (_, pb) in zip(a.model.named_parameters(), b.model.named_parameters()):
+        assert torch.equal(pa, pb), k
+
+
+def test_train_vae_loop_body_with_dataparallel_wrapper(tmp_path):
+    """The body of train_vae (exps/train_op3/train_op3.py:96-116) on synthetic data: float TensorDataset + BlocksDataset
+    (as load_dataset builds them), create_model_v2, nn.DataParallel on ONE visible device, OP3Trainer.train_epoch /
+    test_epoch / save_model."""
+    from torch.utils.data.dataset import TensorDataset
+    from op3_b200.torch.data_management.dataset import BlocksDataset
+    from op3_b200.torch.op3_modules.op3_model import create_model_v2
+    from op3_b200.torch.op3_modules.op3_trainer import OP3Trainer, TrainingScheduler
+    from gpu_util import VARIANT
+    torch.manual_seed(0)
+    feats = torch.randint(0, 256, (12, 5, 3, 64, 64)).float()                 # (s,T,3,D,D), values 0..255
+    actions = torch.randn(12, 5, 6)                                             # pickplace: 6-dim, cols [0,1,3,4] used
+    train = BlocksDataset(TensorDataset(feats, actions), batchsize=4)
+    train.action_dim = 4                                                        # train_op3.py:59-60
+    test = BlocksDataset(TensorDataset(feats[:4], actions[:4]), batchsize=4)
+    m = create_model_v2(dict(VARIANT, K=3), 64, 64, action_dim=train.action_dim)
+    m = torch.nn.DataParallel(m, device_ids=[0])
+    m.cuda()
+    t = OP3Trainer(train, test, m, TrainingScheduler(seed_steps=2, schedule_type="curriculum", max_T=5, T=3), batch_size=4, lr=3e-4)
+    before = {k: v.detach().clone() for k, v in m.module.named_parameters()}
+    stats = t.train_epoch(0)
+    assert np.isfinite(stats["train/loss"]) and np.isfinite(stats["train/mse"]) and stats["train/epoch"] == 0
+    assert any(not torch.equal(v, before[k]) for k, v in m.module.named_parameters())
+    ts = t.test_epoch(0, train=False, batches=1, save_reconstruction=False)
+    assert np.isfinite(ts["test/loss"])
+    t.save_model("final", directory=str(tmp_path))
+    sd = torch.load(os.path.join(str(tmp_path), "final_params.pkl"), map_location="cpu")
+    assert len(sd) == 85 and all(k.startswith("module.") for k in sd)
