@@ -126,6 +126,7 @@ class Engine:
         self._prep_key = None
         self.manual_version = 0         # bumped by the fused optimizer (writes through raw pointers)
         self._mix_sync = {}             # (device, stream) -> zeroed device word of the single-launch mixture forward
+        self._w_cache = {}              # (loss schedule, device) -> normalised loss weights on the device
         self.last_flat_grad = None
 
     # ------------------------------------------------------------------ parameters
@@ -180,6 +181,17 @@ class Engine:
         if t is None:
             t = self._mix_sync[key] = torch.zeros(4, device=dev, dtype=torch.int32)
         return t
+
+    def _loss_weights(self, lw, sw, dev):
+        """loss_schedule / sum(loss_schedule) as a device tensor, cached per schedule (an H2D copy per call would also
+        be illegal inside a CUDA-graph capture)."""
+        key = (tuple(lw), dev.index)
+        w = self._w_cache.get(key)
+        if w is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("op3_b200: run this schedule once eagerly before capturing it in a CUDA graph")
+            w = self._w_cache[key] = torch.tensor(lw, device=dev, dtype=torch.float32) / sw
+        return w
 
     def dims(self, B):
         m = self.model
@@ -263,8 +275,8 @@ class Engine:
         acts_t = None
         if actions is not None:
             a = actions.float()
-            if m.action_dim == 4 and a.shape[-1] == 6:            # physics_network.py:101-102
-                a = a[..., [0, 1, 3, 4]]
+            if m.action_dim == 4 and a.shape[-1] == 6:            # physics_network.py:101-102 (columns 0,1,3,4)
+                a = torch.cat([a[..., 0:2], a[..., 3:5]], -1)      # slices, not an index tensor: CUDA-graph capturable
             if m.action_dim > 0:
                 if a.shape[-1] != m.action_dim:
                     raise ValueError("actions last dim %d != action_dim %d" % (a.shape[-1], m.action_dim))
@@ -459,7 +471,7 @@ class Engine:
         if sw == 0:
             out["total_loss"] = out["kle_loss"] = out["clog_prob"] = None
         else:
-            w = torch.tensor(lw, **f32) / sw
+            w = self._loss_weights(lw, sw, dev)
             comb = (loss_rows[:T1, :3] * w[:, None]).sum(0)
             out["clog_prob"], out["kle_loss"], out["total_loss"] = comb[0], comb[1], comb[2]
         out["mse"] = loss_rows[T1 - 1, 3] if (T1 and images is not None) else torch.zeros((), **f32)

@@ -52,14 +52,15 @@ def all_gather_rows(local, n_total):
     return torch.cat(out)
 
 
-def sharded_rollout_costs(model, cost, goal_info, actions, initial_hidden_state, schedule):
-    """Pickplace-style CEM scoring (mpc_pickplace.py:321-340) with the candidate set split across ranks.
-    actions (Na,T,A) must be identical on every rank (same seed or broadcast).  Returns (sorted_costs, order) computed
-    from the gathered per-candidate costs, identical on every rank."""
-    Na = actions.shape[0]
+def sharded_rollout_costs(model, cost, goal_info, actions, initial_hidden_state, schedule, obs=None):
+    """CEM scoring with the candidate set split across ranks: pickplace style (mpc_pickplace.py:321-340: candidate
+    actions (Na,T,A) rolled out of a B=1 state) or stack style (mpc_stack.py:249-258: candidate after-images `obs`
+    (Na,T,3,D,D), no actions, no initial state).  The candidates must be identical on every rank (same seed or
+    broadcast).  Returns (sorted_costs, order) computed from the gathered per-candidate costs, identical on every rank."""
+    Na = actions.shape[0] if actions is not None else obs.shape[0]
     s, e = shard_range(Na)
-    pred = model.batch_internal_inference(obs=None, actions=actions[s:e], initial_hidden_state=initial_hidden_state,
-                                          schedule=schedule)
+    pred = model.batch_internal_inference(obs=None if obs is None else obs[s:e], actions=None if actions is None else actions[s:e],
+                                          initial_hidden_state=initial_hidden_state, schedule=schedule)
     if cost.core_type == "final_recon":
         goal, p = goal_info["goal_image"], pred["final_recon"].unsqueeze(1)
     else:

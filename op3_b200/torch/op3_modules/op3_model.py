@@ -125,6 +125,10 @@ class OP3Model(nn.Module):
     def _noise(self, B, K, Rs, dev):
         if self.deterministic_sampling:          # samples = means (op3_model.py:148-149)
             return torch.zeros(B, K, Rs, device=dev)
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture (OP3Trainer.use_cuda_graph) the draw must be a device-side philox kernel:
+            # every replay then gets fresh noise from the registered generator state
+            return torch.randn(B, K, Rs, device=dev)
         return ptu.randn(B, K, Rs).to(dev)
 
     def _state_to_tensors(self, s, B):

@@ -156,6 +156,8 @@ class OP3Trainer:
         self.vae_logger_stats_for_rl = {}
         self._extra_stats_to_log = None
         self.timing_info = defaultdict(list)
+        self.use_cuda_graph = False         # train_step replays one captured CUDA graph per (shapes, schedule) when set
+        self._graphs = {}
 
     def _core(self):
         return self.model.module if hasattr(self.model, "module") else self.model
@@ -185,9 +187,72 @@ class OP3Trainer:
             return imgs, tensors[1].to(dev, non_blocking=True)
         return imgs, None
 
-    def train_step(self, true_images, actions, schedule, loss_schedule):
-        """One optimisation step (op3_trainer.py:166-197).  Returns the four logged scalars as device tensors."""
+    # ------------------------------------------------------------------ CUDA-graph step
+    def _graph_entry(self, true_images, actions, schedule, loss_schedule):
+        """The captured forward+backward of one (shapes, schedule, precision) combination, or None while it is still
+        warming up eagerly (lazy one-time initialisations must not happen inside a capture)."""
+        import op3_b200
+        core = self._core()
+        if not (isinstance(true_images, torch.Tensor) and true_images.is_cuda and true_images.dtype == torch.float32):
+            return None
+        key = (tuple(true_images.shape), None if actions is None else (tuple(actions.shape), actions.dtype),
+               tuple(float(x) for x in schedule), tuple(float(x) for x in loss_schedule), true_images.device.index,
+               op3_b200.get_precision(), core.K, float(core.beta))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = {"eager": 0}
+        if "graph" in ent:
+            return ent
+        if ent["eager"] < 2:
+            ent["eager"] += 1
+            return None
+        eng = core.engine
+        dev = true_images.device
+        ent["images"] = true_images.clone()
+        ent["actions"] = None if actions is None else actions.clone()
+        sched, lw = np.asarray(schedule), np.asarray(loss_schedule)
+        torch.cuda.synchronize(dev)
+        eng._prep_key = None                      # op3_prepare must be part of the graph: the weights change every step
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev), torch.cuda.graph(graph):
+            out, tape = eng.forward(ent["images"], ent["actions"], None, sched, lw, core._noise, True)
+            gflat = eng.backward(tape, 1.0, 0.0, 0.0)
+            ent["scalars"] = torch.stack([out["total_loss"], out["clog_prob"], out["kle_loss"], out["mse"]])
+        del tape, out
+        ent["graph"], ent["gflat"] = graph, gflat
+        ent["grad_views"] = eng.grad_views(gflat)
+        return ent
+
+    def _graph_step(self, ent, true_images, actions):
         import torch.distributed as dist
+        core = self._core()
+        ent["images"].copy_(true_images)
+        if ent["actions"] is not None:
+            ent["actions"].copy_(actions)
+        ent["graph"].replay()
+        core.engine.last_flat_grad = ent["gflat"]
+        for p, v in zip(core.parameters(), ent["grad_views"]):
+            p.grad = v
+        scale, g = 1.0, None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            g = ent["gflat"]
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            scale = 1.0 / dist.get_world_size()
+        self.optimizer.step(grad_scale=scale, flat_grad=g if g is not None else ent["gflat"])
+        vals = ent["scalars"].clone()             # the graph's own buffer is overwritten by the next replay
+        return vals[0], vals[1], vals[2], vals[3]
+
+    def train_step(self, true_images, actions, schedule, loss_schedule):
+        """One optimisation step (op3_trainer.py:166-197).  Returns the four logged scalars as device tensors.
+
+        With `use_cuda_graph` the forward + backward of a recurring (batch shape, schedule) combination is captured once
+        (after two eager steps) and replayed: ~1000 kernel launches become one graph launch.  Gradient all-reduce and
+        the fused clip+Adam stay outside the graph (Adam's bias correction takes the step count from the host)."""
+        import torch.distributed as dist
+        if self.use_cuda_graph and torch.is_grad_enabled():
+            ent = self._graph_entry(true_images, actions, schedule, loss_schedule)
+            if ent is not None:
+                return self._graph_step(ent, true_images, actions)
         self.optimizer.zero_grad()
         _, _, _, total_loss, total_kle_loss, total_clog_prob, mse, _ = self.model.forward(
             true_images, actions, initial_hidden_state=None, schedule=schedule, loss_schedule=loss_schedule)
