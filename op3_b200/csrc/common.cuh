@@ -106,6 +106,10 @@ int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, int tran
 // weight + bias gradient of y = x W^T + b in one launch: gW[out,in] += dY^T X, gB[out] += sum_m dY[m,:]
 int gemm_wgrad(cudaStream_t st, int out, int in, int M, const float* dY, int lddy, const float* X, int ldx, float* gW,
                int ldgw, float* gB);
+// several gemm_wgrad problems in one launch (fused MLP chains: fused_mlp.cu)
+constexpr int WGRAD_BATCH_MAX = 28;
+struct WgradItem { const float* dY; const float* X; float* gW; float* gB; int out, in, rows, lddy, ldx, ldgw; };
+int gemm_wgrad_batch(cudaStream_t st, const WgradItem* items, int n);
 // dPre[m,n] = dY[m,n] * act'(Y[m,n]) in place on dY (Y is the activation OUTPUT)
 int act_backward(cudaStream_t st, int M, int N, float* dY, int ldd, const float* Y, int ldy, int act);
 // out[n] (+)= sum_m X[m,n]

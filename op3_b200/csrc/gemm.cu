@@ -14,10 +14,10 @@ constexpr int BM = 32, BN = 32, BK = 16, KG = 4;
 // split over the four 64-thread groups of the CTA (4x shorter serial chain), each group register-prefetching its next
 // 16-deep slab while it multiplies the current one; the four partial tiles are added in a fixed order through shared memory.
 template <int TA, int TB>
-__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                   const float* __restrict__ B, int ldb, float* __restrict__ C,
-                                                   int ldc, const float* __restrict__ bias, int act, int accumulate,
-                                                   float* __restrict__ colsum_out) {
+__device__ __forceinline__ void gemm_tile(int M, int N, int K, const float* __restrict__ A, int lda,
+                                          const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                          int ldc, const float* __restrict__ bias, int act, int accumulate,
+                                          float* __restrict__ colsum_out, int tile_x, int tile_y) {
   static_assert(BM == BN, "square tiles");
   __shared__ float sm[2 * KG * BK * (BM + 4)];
   float (*As)[BK][BM + 4] = reinterpret_cast<float (*)[BK][BM + 4]>(sm);
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
   const int tid = threadIdx.x;
   const int kg = tid >> 6, t = tid & 63;
   const int tx = t & 7, ty = t >> 3;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = tile_y * BM, n0 = tile_x * BN;
   const int Kq = ((K + KG * BK - 1) / (KG * BK)) * BK;      // K range of one group (multiple of BK)
   const int kbeg = kg * Kq, kend = min(K, kbeg + Kq);
   float acc[4][4];
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float ra[8], rb[8];
   // TA == 1 only (weight gradients dW = dY^T X): the first column of tiles also accumulates sum_k A[k][m] = the bias gradient
-  const bool do_cs = TA == 1 && colsum_out != nullptr && blockIdx.x == 0 && tx == 0;
+  const bool do_cs = TA == 1 && colsum_out != nullptr && tile_x == 0 && tx == 0;
   float cs[4] = {0.f, 0.f, 0.f, 0.f};
 
   auto fetch = [&](int k0) {
@@ -134,6 +134,30 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
   }
 }
 
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                   const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                   int ldc, const float* __restrict__ bias, int act, int accumulate,
+                                                   float* __restrict__ colsum_out) {
+  gemm_tile<TA, TB>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, colsum_out, blockIdx.x, blockIdx.y);
+}
+
+// All weight + bias gradients of a fused MLP chain in ONE launch: item i is gW[out][in] += dY^T X, gB[out] += colsum(dY)
+// over `rows` rows; its tiles are the blocks [tile0[i], tile0[i+1]).
+struct WgradBatch {
+  WgradItem it[WGRAD_BATCH_MAX];
+  int tile0[WGRAD_BATCH_MAX + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256) gemm_wgrad_batch_kernel(const __grid_constant__ WgradBatch b) {
+  int i = 0;
+  while (i + 1 < b.n && (int)blockIdx.x >= b.tile0[i + 1]) ++i;
+  const WgradItem& w = b.it[i];
+  const int t = blockIdx.x - b.tile0[i];
+  const int tiles_x = (w.in + BN - 1) / BN;
+  gemm_tile<1, 0>(w.out, w.in, w.rows, w.dY, w.lddy, w.X, w.ldx, w.gW, w.ldgw, nullptr, ACT_NONE, 1, w.gB, t % tiles_x, t / tiles_x);
+}
+
 __global__ void act_backward_kernel(int M, int N, float* __restrict__ dY, int ldd, const float* __restrict__ Y,
                                     int ldy, int act) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,6 +215,30 @@ int gemm_wgrad(cudaStream_t st, int out, int in, int M, const float* dY, int ldd
   ProfScope prof(st, KID_GEMM, 2.0 * out * in * M);
   dim3 grid(ceil_div(in, BN), ceil_div(out, BM));
   gemm_kernel<1, 0><<<grid, 256, 0, st>>>(out, in, M, dY, lddy, X, ldx, gW, ldgw, nullptr, ACT_NONE, 1, gB);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
+int gemm_wgrad_batch(cudaStream_t st, const WgradItem* items, int n) {
+  if (n <= 0) return OP3_OK;
+  OP3_REQUIRE(n <= WGRAD_BATCH_MAX, "gemm_wgrad_batch: %d items > %d", n, WGRAD_BATCH_MAX);
+  WgradBatch b;
+  double work = 0.0;
+  int tiles = 0, m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (items[i].out <= 0 || items[i].in <= 0 || items[i].rows <= 0) continue;
+    b.it[m] = items[i];
+    b.tile0[m] = tiles;
+    tiles += ceil_div(items[i].in, BN) * ceil_div(items[i].out, BM);
+    work += 2.0 * items[i].out * items[i].in * items[i].rows;
+    ++m;
+  }
+  b.tile0[m] = tiles;
+  b.n = m;
+  if (tiles == 0) return OP3_OK;
+  ProfScope prof(st, KID_GEMM, work);
+  gemm_wgrad_batch_kernel<<<tiles, 256, 0, st>>>(b);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;

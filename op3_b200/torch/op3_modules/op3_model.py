@@ -129,7 +129,9 @@ class OP3Model(nn.Module):
             # inside a CUDA-graph capture (OP3Trainer.use_cuda_graph) the draw must be a device-side philox kernel:
             # every replay then gets fresh noise from the registered generator state
             return torch.randn(B, K, Rs, device=dev)
-        return ptu.randn(B, K, Rs).to(dev)
+        # drawn on the inputs' device even when ptu.set_gpu_mode was never called: a CPU draw would cost a pageable
+        # host->device copy (= a host sync) per schedule step
+        return ptu.randn(B, K, Rs, torch_device=dev).to(dev)
 
     def _state_to_tensors(self, s, B):
         K, Rd, Rs = self.K, self.det_size, self.sto_size
@@ -335,7 +337,21 @@ class OP3Model(nn.Module):
         return info
 
     def get_activation_values(self, initial_hidden_state, actions, batch_size=10):
-        return self.get_all_activation_values(initial_hidden_state, actions, batch_size)[0]
+        """op3_model.py:645-664: state-action attention (B,K) of B probe actions on a B=1 state.  Reference quirk kept:
+        within each chunk of `batch_size` actions the rows are paired with `actions[chunk].repeat(K, 1)` (TILED, not
+        interleaved per slot), so state row (i, k) meets action (i*K + k) mod b of its chunk (:661) -- the attention is
+        a per-row quantity, so it is evaluated here with one action per row (K=1 rows of the dynamics kernels)."""
+        from op3_b200.torch.op3_modules._standalone import physics_forward
+        B, K = actions.shape[0], self.K
+        state = self.replicate_state(initial_hidden_state, B)
+        z = self._flatten_first_two(self.get_full_tensor_state(state)).contiguous()          # (B*K, R)
+        rows = []
+        for start in range(0, B, batch_size):
+            b = min(batch_size, B - start)
+            rows.append(actions[start:start + b].repeat(K, 1))                                 # (b*K, A), tiled
+        acts = torch.cat(rows)
+        act_att = physics_forward(self.dynamics_net, z, acts, K=1, engine=self.engine)[3]    # (B*K, 1)
+        return act_att.view(B, K).detach()
 
     def get_all_activation_values(self, initial_hidden_state, actions, batch_size=10):
         """op3_model.py:667-698: (state_action_attention (B,K), interaction_attention (B,K,K-1), |d enc| (B,K),
