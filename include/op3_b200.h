@@ -97,6 +97,10 @@ unsigned long long op3_launch_count(void);
 int op3_set_precision(int mode);
 int op3_get_precision(void);
 
+/* The dynamics network and the head of the refinement network run as CTA-resident chains of layers (one launch forward, one
+ * backward + one batched weight-gradient launch); 0 selects the layer-by-layer launches instead (A/B tests).  Default 1. */
+int op3_set_fused_mlp(int on);
+
 /* Optional timing of kernel families with CUDA events on the launch stream (used by bench.py for the roofline
  * numbers).  Families: 0 = conv5x5 forward/dgrad, 1 = conv5x5 wgrad, 2 = mixture kernels, 3 = small GEMMs.
  * collect() synchronises on the recorded events and returns, per family, the summed milliseconds, the summed

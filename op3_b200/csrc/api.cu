@@ -61,6 +61,10 @@ extern "C" int op3_set_precision(int mode) {
 }
 extern "C" int op3_get_precision(void) { return g_precision; }
 
+static bool g_fused_mlp = true;
+namespace op3 { bool fused_mlp_enabled() { return g_fused_mlp; } }
+extern "C" int op3_set_fused_mlp(int on) { g_fused_mlp = on != 0; return OP3_OK; }
+
 extern "C" const char* op3_version(void) { return "op3_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* op3_last_error(void) { return op3::g_err; }
 extern "C" unsigned long long op3_launch_count(void) { return op3::g_launch_count; }

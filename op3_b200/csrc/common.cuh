@@ -47,6 +47,10 @@ struct ProfScope {
   ~ProfScope() { if (on) profile_end(st); }
 };
 
+// fused row-tile MLP chains (fused_mlp.cuh) for the dynamics network and the refinement head; op3_set_fused_mlp(0) selects the
+// layer-by-layer launches (kept for A/B tests and for parameter buffers whose rows are not 16-byte aligned)
+bool fused_mlp_enabled();
+
 // ---- small device helpers -------------------------------------------------------------------
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 // derivative of ELU(alpha=1) expressed through its OUTPUT a: a>0 -> 1, else a+1 (= e^x)

@@ -3,6 +3,7 @@
 // FC+ELU, LSTM cell, two linear heads), the LayerNorm of the lambda gradients and extra_input assembly of
 // OP3Model.refine (op3_model.py:232-249), get_samples / _softplus_to_std (:130-153) and their backward.
 #include "layout.cuh"
+#include "fused_mlp.cuh"
 
 namespace op3 {
 
@@ -263,6 +264,230 @@ inline ConvInput one_src(const float4* p, int chunks) {
   return in;
 }
 
+
+// ===================================================================================================================
+// Fused head of the refinement network (refinement_network.py:203-219 + the extra_input assembly of op3_model.py:232-249):
+// one CTA owns a tile of slot rows and runs FC+ELU, the LayerNorm'd lambda gradients, both LSTM gate products, the cell and
+// the two linear heads with the row tile in shared memory (fused_mlp.cuh).
+// ===================================================================================================================
+using namespace fused;
+constexpr int XW_ = HID + 5 * 64;        // 448 columns of the LSTM input (Rs = 64)
+constexpr int LPO = PITCH(64), LXW = PITCH(XW_), LHH = PITCH(128), LG = PITCH(512);   // panel pitches (fused_mlp.cuh)
+constexpr int REF_FWD_SMEM_FLOATS = GEMM_SMEM_FLOATS + 16 * (LPO + LXW + LHH + LG + LHH);
+constexpr int REF_BWD_SMEM_FLOATS = GEMM_SMEM_FLOATS + 16 * (LPO + LHH + LG + LXW);
+
+// extra == nullptr: columns [128, 448) of X are built from the latent state (op3_refine_fwd); else copied from extra [N][320]
+__global__ void __launch_bounds__(FT) ref_head_fwd_kernel(int N, int R, int Rd, const __grid_constant__ Op3Params p,
+                                                          const __grid_constant__ Op3RefineIO io, float w_kl,
+                                                          const float* __restrict__ extra, const float* __restrict__ pooled,
+                                                          float* __restrict__ X, float* __restrict__ gates,
+                                                          float* __restrict__ xn, int rpc, int tc) {
+  extern __shared__ __align__(16) float sm[];
+  float* wt = sm;
+  float* PPOOL = wt + GEMM_SMEM_FLOATS;   // [16][LPO]
+  float* PX = PPOOL + 16 * LPO;           // [16][LXW]
+  float* PHP = PX + 16 * LXW;             // [16][LHH]  previous h
+  float* PG = PHP + 16 * LHH;             // [16][LG]   gate pre-activations
+  float* PH2 = PG + 16 * LG;              // [16][LHH]  new h
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int Rs = 64;
+  const int row0 = blockIdx.x * rpc, rows = min(rpc, N - row0);
+  zero_panel(PPOOL, REF_FWD_SMEM_FLOATS - GEMM_SMEM_FLOATS);   // rows the GEMMs compute but nobody owns must stay finite
+  __syncthreads();
+  load_panel(PPOOL, LPO, pooled + (size_t)row0 * Rs, Rs, rows, Rs);
+  load_panel(PHP, LHH, io.h + (size_t)row0 * LSTM, LSTM, rows, LSTM);
+  if (extra != nullptr) {
+    for (int e = tid; e < rows * 5 * Rs; e += FT) {
+      const int r = e / (5 * Rs), c = e - r * 5 * Rs;
+      const float v = extra[(size_t)(row0 + r) * 5 * Rs + c];
+      PX[r * LXW + HID + c] = v;
+      X[(size_t)(row0 + r) * XW_ + HID + c] = v;
+    }
+  } else {
+    const float *sc1 = p.ln1d_scale[0], *ce1 = p.ln1d_center[0], *sc2 = p.ln1d_scale[1], *ce2 = p.ln1d_center[1];
+    for (int r = warp; r < rows; r += FT / 32) {             // one warp per slot row: see refine_extras_kernel
+      const int n = row0 + r;
+      float g1[2], g2[2];
+      float* xr = PX + r * LXW + HID;
+      float* xg = X + (size_t)n * XW_ + HID;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = lane + 32 * t;
+        const size_t i = (size_t)n * Rs + j;
+        const float l2v = io.l2[i], l1v = io.l1[i];
+        const float s2 = sp_std(l2v), ds2 = sp_std_grad(l2v, s2);
+        const float dsmp = io.dz[(size_t)n * R + Rd + j];
+        float a = dsmp, b = dsmp * io.eps[i] * ds2;
+        if (!io.prior_is_post && w_kl != 0.f) {
+          const float s1 = sp_std(io.prior2[i]);
+          const float dm = l1v - io.prior1[i];
+          a += w_kl * dm / (s1 * s1);
+          b += w_kl * (-1.f / s2 + s2 / (s1 * s1)) * ds2;
+        }
+        g1[t] = a; g2[t] = b;
+        const float zs = io.z[(size_t)n * R + Rd + j];
+        xr[2 * Rs + j] = l1v; xr[3 * Rs + j] = l2v; xr[4 * Rs + j] = zs;
+        xg[2 * Rs + j] = l1v; xg[3 * Rs + j] = l2v; xg[4 * Rs + j] = zs;
+      }
+      const float m1 = warp_sum(g1[0] + g1[1]) / 64.f, m2 = warp_sum(g2[0] + g2[1]) / 64.f;
+      const float v1 = warp_sum((g1[0] - m1) * (g1[0] - m1) + (g1[1] - m1) * (g1[1] - m1)) / 63.f;
+      const float v2 = warp_sum((g2[0] - m2) * (g2[0] - m2) + (g2[1] - m2) * (g2[1] - m2)) / 63.f;
+      const float i1 = 1.f / (sqrtf(v1) + 1e-6f), i2 = 1.f / (sqrtf(v2) + 1e-6f);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = lane + 32 * t;
+        const float a = (g1[t] - m1) * i1, b = (g2[t] - m2) * i2;
+        xn[(size_t)n * 2 * Rs + j] = a;
+        xn[(size_t)n * 2 * Rs + Rs + j] = b;
+        const float ya = a * sc1[j] + ce1[j], yb = b * sc2[j] + ce2[j];
+        xr[j] = ya; xr[Rs + j] = yb;
+        xg[j] = ya; xg[Rs + j] = yb;
+      }
+    }
+  }
+  __syncthreads();
+  cta_gemm<false>(tc, PPOOL, LPO, rows, p.ref_fc.w, Rs, Rs, HID, wt, epi_fwd(p.ref_fc.b, ACT_ELU, PX, LXW, X + (size_t)row0 * XW_, XW_));
+  cta_gemm<false>(tc, PX, LXW, rows, p.lstm_w_ih, XW_, XW_, 4 * LSTM, wt, epi_fwd(p.lstm_b_ih, ACT_NONE, PG, LG, nullptr, 0));
+  {
+    Epi e = epi_fwd(p.lstm_b_hh, ACT_NONE, PG, LG, gates + (size_t)row0 * 4 * LSTM, 4 * LSTM);
+    e.so_acc = 1;
+    cta_gemm<false>(tc, PHP, LHH, rows, p.lstm_w_hh, LSTM, LSTM, 4 * LSTM, wt, e);
+  }
+  for (int e = tid; e < rows * LSTM; e += FT) {               // LSTM cell, gate order i,f,g,o
+    const int r = e / LSTM, j = e - r * LSTM;
+    const float* g = PG + r * LG;
+    const float gi = sigmoid_f(g[j]), gf = sigmoid_f(g[LSTM + j]), gg = tanhf(g[2 * LSTM + j]), go = sigmoid_f(g[3 * LSTM + j]);
+    const size_t i = (size_t)(row0 + r) * LSTM + j;
+    const float cn = gf * io.c[i] + gi * gg;
+    const float hn = go * tanhf(cn);
+    io.c_out[i] = cn;
+    io.h_out[i] = hn;
+    PH2[r * LHH + j] = hn;
+  }
+  __syncthreads();
+  cta_gemm<false>(tc, PH2, LHH, rows, p.ref_last_fc.w, LSTM, LSTM, Rs, wt,
+                  epi_fwd(p.ref_last_fc.b, ACT_NONE, nullptr, 0, io.l1_out + (size_t)row0 * Rs, Rs));
+  cta_gemm<false>(tc, PH2, LHH, rows, p.ref_last_fc2.w, LSTM, LSTM, Rs, wt,
+                  epi_fwd(p.ref_last_fc2.b, ACT_NONE, nullptr, 0, io.l2_out + (size_t)row0 * Rs, Rs));
+}
+
+// Backward of the head for a row tile.  Writes dgates and dX (columns [0,128) already multiplied by ELU' of the FC output:
+// the operands of the batched weight-gradient launch), dpool; adds the direct paths into dl1, dl2, dz_acc, dh, dc.
+__global__ void __launch_bounds__(FT) ref_head_bwd_kernel(int N, int R, int Rd, const __grid_constant__ Op3Params p,
+                                                          const float* __restrict__ gates, const float* __restrict__ Xa,
+                                                          const float* __restrict__ c_prev, const float* __restrict__ d_l1n,
+                                                          const float* __restrict__ d_l2n, const float* __restrict__ d_h,
+                                                          const float* __restrict__ d_c, float* __restrict__ dgates,
+                                                          float* __restrict__ dX, float* __restrict__ dpool, float* dl1,
+                                                          float* dl2, float* dz_acc, float* dh, float* dc, int rpc, int tc) {
+  extern __shared__ __align__(16) float sm[];
+  float* wt = sm;
+  float* PU = wt + GEMM_SMEM_FLOATS;      // [16][LPO]
+  float* PDH2 = PU + 16 * LPO;            // [16][LHH]
+  float* PDG = PDH2 + 16 * LHH;           // [16][LG]
+  float* PDX = PDG + 16 * LG;             // [16][LXW]
+  const int tid = threadIdx.x;
+  constexpr int Rs = 64;
+  const int row0 = blockIdx.x * rpc, rows = min(rpc, N - row0);
+  zero_panel(PU, REF_BWD_SMEM_FLOATS - GEMM_SMEM_FLOATS);      // rows the GEMMs compute but nobody owns must stay finite
+  __syncthreads();
+  for (int e = tid; e < rows * LSTM; e += FT) PDH2[(e / LSTM) * LHH + (e % LSTM)] = d_h ? d_h[(size_t)row0 * LSTM + e] : 0.f;
+  for (int hd = 0; hd < 2; ++hd) {
+    const float* up = hd == 0 ? d_l1n : d_l2n;
+    if (up == nullptr) continue;
+    __syncthreads();
+    load_panel(PU, LPO, up + (size_t)row0 * Rs, Rs, rows, Rs);
+    __syncthreads();
+    cta_gemm<true>(tc, PU, LPO, rows, hd == 0 ? p.ref_last_fc.w : p.ref_last_fc2.w, LSTM, Rs, LSTM, wt,
+                   epi_bwd(nullptr, 0, PDH2, LHH, 1, nullptr, 0, 0));
+  }
+  __syncthreads();
+  for (int e = tid; e < rows * LSTM; e += FT) {               // LSTM cell backward
+    const int r = e / LSTM, j = e - r * LSTM;
+    const size_t i = (size_t)(row0 + r) * LSTM + j;
+    const float* g = gates + (size_t)(row0 + r) * 4 * LSTM;
+    const float gi = sigmoid_f(g[j]), gf = sigmoid_f(g[LSTM + j]), gg = tanhf(g[2 * LSTM + j]), go = sigmoid_f(g[3 * LSTM + j]);
+    const float cp = c_prev[i];
+    const float cn = gf * cp + gi * gg;
+    const float tc = tanhf(cn);
+    const float dhv = PDH2[r * LHH + j];
+    const float dcn = (d_c ? d_c[i] : 0.f) + dhv * go * (1.f - tc * tc);
+    const float a0 = dcn * gg * gi * (1.f - gi), a1 = dcn * cp * gf * (1.f - gf), a2 = dcn * gi * (1.f - gg * gg),
+                a3 = dhv * tc * go * (1.f - go);
+    float* pg = PDG + r * LG;
+    float* dg = dgates + (size_t)(row0 + r) * 4 * LSTM;
+    pg[j] = a0; pg[LSTM + j] = a1; pg[2 * LSTM + j] = a2; pg[3 * LSTM + j] = a3;
+    dg[j] = a0; dg[LSTM + j] = a1; dg[2 * LSTM + j] = a2; dg[3 * LSTM + j] = a3;
+    dc[i] += dcn * gf;
+  }
+  __syncthreads();
+  {
+    Epi e = epi_bwd(Xa + (size_t)row0 * XW_, XW_, PDX, LXW, 0, dX + (size_t)row0 * XW_, XW_, 0);
+    e.gy_cols = HID;                      // ELU' of the FC output for its 128 columns only
+    cta_gemm<true>(tc, PDG, LG, rows, p.lstm_w_ih, XW_, 4 * LSTM, XW_, wt, e);
+  }
+  for (int e = tid; e < rows * 3 * Rs; e += FT) {   // direct paths into the previous state's lambdas / samples (op3_model.py:244-248)
+    const int r = e / (3 * Rs), c = e - r * 3 * Rs;
+    const float v = PDX[r * LXW + HID + 2 * Rs + c];
+    if (c < Rs) dl1[(size_t)(row0 + r) * Rs + c] += v;
+    else if (c < 2 * Rs) dl2[(size_t)(row0 + r) * Rs + c - Rs] += v;
+    else dz_acc[(size_t)(row0 + r) * R + Rd + c - 2 * Rs] += v;
+  }
+  cta_gemm<true>(tc, PDG, LG, rows, p.lstm_w_hh, LSTM, 4 * LSTM, LSTM, wt,
+                 epi_bwd(nullptr, 0, nullptr, 0, 0, dh + (size_t)row0 * LSTM, LSTM, 1));
+  cta_gemm<true>(tc, PDX, LXW, rows, p.ref_fc.w, Rs, HID, Rs, wt, epi_bwd(nullptr, 0, nullptr, 0, 0, dpool + (size_t)row0 * Rs, Rs, 0));
+}
+
+// LayerNorm (modules.py:19-46) parameter gradients of the two lambda-gradient inputs in one launch:
+// scale[j][n] += sum_m dX[m][128 + 64 j + n] * xn[m][64 j + n]; center[j][n] += sum_m dX[m][128 + 64 j + n].  Deterministic.
+__global__ void __launch_bounds__(256) ln1d_grad_kernel(int M, const float* __restrict__ dX, const float* __restrict__ xn,
+                                                        float* s0, float* c0, float* s1, float* c1) {
+  __shared__ float part[2][8][33];
+  const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+  const int j = blockIdx.x >> 1, n = (blockIdx.x & 1) * 32 + lane;
+  float a = 0.f, b = 0.f;
+  for (int m = w; m < M; m += 8) {
+    const float d = dX[(size_t)m * XW_ + HID + j * 64 + n];
+    a += d * xn[(size_t)m * 128 + j * 64 + n];
+    b += d;
+  }
+  part[0][w][lane] = a; part[1][w][lane] = b;
+  __syncthreads();
+  if (w < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[w][i][lane];
+    float* out = w == 0 ? (j == 0 ? s0 : s1) : (j == 0 ? c0 : c1);
+    out[n] += t;
+  }
+}
+
+inline bool ref_head_fusable(const Op3Params* p) {
+  return aligned16(p->ref_fc.w) && aligned16(p->lstm_w_ih) && aligned16(p->lstm_w_hh) && aligned16(p->ref_last_fc.w) &&
+         aligned16(p->ref_last_fc2.w);
+}
+inline int head_rows_per_cta(int N) {
+  int r = ((ceil_div(N, device_sm_count()) + 3) / 4) * 4;
+  return r < 4 ? 4 : (r > RTM ? RTM : r);
+}
+inline double ref_head_flops(int N) { return 2.0 * N * (64.0 * HID + (double)XW_ * 512 + 128.0 * 512 + 2 * 128.0 * 64); }
+
+int ref_head_fwd_fused(cudaStream_t st, const Op3Dims* d, const Op3Params* p, const Op3RefineIO& io, const float* extra,
+                       const RefActs& A) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
+    OP3_CHECK(cudaFuncSetAttribute(ref_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   REF_FWD_SMEM_FLOATS * (int)sizeof(float)));
+  const int N = d->B * d->K, rpc = head_rows_per_cta(N);
+  ProfScope prof(st, KID_GEMM, ref_head_flops(N));
+  ref_head_fwd_kernel<<<ceil_div(N, rpc), FT, REF_FWD_SMEM_FLOATS * sizeof(float), st>>>(
+      N, d->Rd + d->Rs, d->Rd, *p, io, d->beta / (float)d->B, extra, A.pooled, A.X, A.gates, A.xn, rpc,
+      op3_get_precision() != OP3_PREC_FP32);
+  OP3_COUNT_LAUNCH();
+  OP3_LAUNCH_CHECK();
+  return OP3_OK;
+}
+
 }  // namespace
 }  // namespace op3
 
@@ -339,6 +564,7 @@ extern "C" int op3_refine_fwd(const Op3Dims* d, const Op3Params* p, const float*
   avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
+  if (fused_mlp_enabled() && ref_head_fusable(p)) return ref_head_fwd_fused(st, d, p, *io, nullptr, A);
   // X = [ ELU(fc(pooled)) | LN(g_l1) | LN(g_l2) | l1 | l2 | samples ]
   OP3_TRY(gemm(st, N, HID, Rs, A.pooled, Rs, 0, p->ref_fc.w, Rs, 1, A.X, XW, p->ref_fc.b, ACT_ELU, 0));
   refine_extras_kernel<<<ceil_div(N, 4), 128, 0, st>>>(N, R, d->Rd, Rs, *io, d->beta / (float)d->B, p->ln1d_scale[0],
@@ -389,6 +615,11 @@ extern "C" int op3_refine_net_fwd(const Op3Dims* d, const Op3Params* p, const fl
   avgpool_kernel<<<dim3(Rs / 4, N), 256, 0, st>>>(A.r3, Rs / 4, DD, A.pooled);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
+  if (fused_mlp_enabled() && ref_head_fusable(p) && aligned16(h)) {
+    Op3RefineIO io{};
+    io.h = h; io.c = c; io.l1_out = l1_out; io.l2_out = l2_out; io.h_out = h_out; io.c_out = c_out;
+    return ref_head_fwd_fused(st, d, p, io, extra, A);
+  }
   OP3_TRY(gemm(st, N, HID, Rs, A.pooled, Rs, 0, p->ref_fc.w, Rs, 1, A.X, XW, p->ref_fc.b, ACT_ELU, 0));
   OP3_CHECK(cudaMemcpy2DAsync(A.X + HID, (size_t)XW * sizeof(float), extra, (size_t)5 * Rs * sizeof(float),
                               (size_t)5 * Rs * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
@@ -434,6 +665,32 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   float* tcs = scratch + o;               // fp16-mode operand maxima
   (void)dfc;
 
+  if (fused_mlp_enabled() && ref_head_fusable(p) && (!d_l1n || aligned16(d_l1n)) && (!d_l2n || aligned16(d_l2n))) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first())
+      OP3_CHECK(cudaFuncSetAttribute(ref_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     REF_BWD_SMEM_FLOATS * (int)sizeof(float)));
+    const int rpc = head_rows_per_cta(N);
+    {
+      ProfScope prof(st, KID_GEMM, 2.0 * ref_head_flops(N));
+      ref_head_bwd_kernel<<<ceil_div(N, rpc), FT, REF_BWD_SMEM_FLOATS * sizeof(float), st>>>(
+          N, R, d->Rd, *p, A.gates, A.X, io->c, d_l1n, d_l2n, d_h, d_c, dgates, dX, dpool, dl1, dl2, dz_acc, dh, dc, rpc,
+          op3_get_precision() != OP3_PREC_FP32);
+      OP3_COUNT_LAUNCH();
+      OP3_LAUNCH_CHECK();
+    }
+    WgradItem it[5];
+    int n = 0;
+    if (d_l1n) it[n++] = {d_l1n, io->h_out, g->ref_last_fc.w, g->ref_last_fc.b, Rs, LSTM, N, Rs, LSTM, LSTM};
+    if (d_l2n) it[n++] = {d_l2n, io->h_out, g->ref_last_fc2.w, g->ref_last_fc2.b, Rs, LSTM, N, Rs, LSTM, LSTM};
+    it[n++] = {dgates, A.X, g->lstm_w_ih, g->lstm_b_ih, 4 * LSTM, XW, N, 4 * LSTM, XW, XW};
+    it[n++] = {dgates, io->h, g->lstm_w_hh, g->lstm_b_hh, 4 * LSTM, LSTM, N, 4 * LSTM, LSTM, LSTM};
+    it[n++] = {dX, A.pooled, g->ref_fc.w, g->ref_fc.b, HID, Rs, N, XW, Rs, Rs};
+    OP3_TRY(gemm_wgrad_batch(st, it, n));
+    ln1d_grad_kernel<<<4, 256, 0, st>>>(N, dX, A.xn, g->ln1d_scale[0], g->ln1d_center[0], g->ln1d_scale[1], g->ln1d_center[1]);
+    OP3_COUNT_LAUNCH();
+    OP3_LAUNCH_CHECK();
+  } else {
   // heads: lam = h2 W^T + b
   OP3_CHECK(cudaMemsetAsync(dh2, 0, (size_t)N * LSTM * sizeof(float), st));
   if (d_h) OP3_TRY(axpy(st, (long long)N * LSTM, d_h, dh2));
@@ -471,6 +728,7 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   OP3_TRY(act_backward(st, N, HID, dX, XW, A.X, XW, ACT_ELU));
   OP3_TRY(gemm(st, N, Rs, HID, dX, XW, 0, p->ref_fc.w, Rs, 0, dpool, Rs, nullptr, ACT_NONE, 0));
   OP3_TRY(gemm_wgrad(st, HID, Rs, N, dX, XW, A.pooled, Rs, g->ref_fc.w, Rs, g->ref_fc.b));
+  }
   // conv stack
   // fp16 mode: maxima of r1, r2 come from the forward pass (acts), those of g3, g2, g1 are recorded in slots 1..3 here
   const bool f16 = op3_get_precision() == OP3_PREC_F16X3;

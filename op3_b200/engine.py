@@ -65,6 +65,15 @@ def _param_field_map(action_dim, det):
     return m
 
 
+def _split_slot(name):
+    """'decode_net.models.2.broadcast_net...' -> (2, 'decode_net.broadcast_net...'); names of shared tensors -> (None, name).
+    The *_No_Sharing networks keep one sub-network per slot under `models.<k>` (decoder_network.py:113-131)."""
+    parts = name.split(".")
+    if len(parts) > 2 and parts[1] == "models" and parts[2].isdigit():
+        return int(parts[2]), ".".join(parts[:1] + parts[3:])
+    return None, name
+
+
 def _set_field(struct, path, value):
     obj = struct
     for p in path[:-1]:
@@ -102,7 +111,7 @@ class _State:
 
 
 class _Decode:
-    __slots__ = ("state", "acts", "dec_out", "io", "keep", "weight", "t_index", "has_stats", "refine_after", "losses")
+    __slots__ = ("state", "acts", "dec_out", "io", "keep", "weight", "t_index", "has_stats", "refine_after", "losses", "zp")
 
 
 class _Step:
@@ -128,6 +137,17 @@ class Engine:
         self._mix_sync = {}             # (device, stream) -> zeroed device word of the single-launch mixture forward
         self._w_cache = {}              # (loss schedule, device) -> normalised loss weights on the device
         self.last_flat_grad = None
+        # *_No_Sharing networks: one weight set per slot, same kernels launched once per slot
+        self.ns_dec = bool(getattr(model.decode_net, "no_sharing", False))
+        self.ns_ref = bool(getattr(model.refinement_net, "no_sharing", False))
+        self.ns_dyn = bool(getattr(model.dynamics_net, "no_sharing", False))
+        self._pstructs = None
+        self._preps = None
+
+    @property
+    def n_slots(self):
+        """Number of distinct weight sets: K when any sub-network is a *_No_Sharing one, else 1."""
+        return self.model.K if (self.ns_dec or self.ns_ref or self.ns_dyn) else 1
 
     # ------------------------------------------------------------------ parameters
     def _named_params(self):
@@ -162,17 +182,25 @@ class Engine:
             self._prep_key = None
         return self._flat
 
-    def _struct_for(self, flat):
-        """Op3Params struct pointing into `flat` (parameter buffer or a gradient buffer of the same layout)."""
+    def _structs_for(self, flat):
+        """One Op3Params struct per weight set, pointing into `flat` (parameter buffer or a gradient buffer of the same
+        layout).  Struct k holds the shared tensors plus the `models.<k>` tensors of the *_No_Sharing networks."""
         m = self.model
         fmap = _param_field_map(m.action_dim, m.det_size)
-        s = Op3Params()
+        structs = [Op3Params() for _ in range(self.n_slots)]
         base = flat.data_ptr()
         for name, off in zip(self._names, self._offsets):
-            if name not in fmap:
-                raise RuntimeError("op3_b200: unexpected parameter %r (only the shared-weight 'reg' networks are built)" % name)
-            _set_field(s, fmap[name], base + 4 * off)
-        return s
+            slot, key = _split_slot(name)
+            if key not in fmap or (slot is not None and slot >= len(structs)):
+                raise RuntimeError("op3_b200: unexpected parameter %r" % name)
+            for k, s in enumerate(structs):
+                if slot is None or slot == k:
+                    _set_field(s, fmap[key], base + 4 * off)
+        return structs
+
+    def _struct_for(self, flat):
+        """Op3Params struct of weight set 0 (the only one for the shared-weight networks)."""
+        return self._structs_for(flat)[0]
 
     def mix_sync(self, dev, stream):
         """The self-resetting 'samples done' word of op3_mixture_fwd's single-launch path (Op3MixtureIO.sync)."""
@@ -197,32 +225,43 @@ class Engine:
         m = self.model
         return Op3Dims(B=B, K=m.K, D=m.image_size, Rd=m.det_size, Rs=m.sto_size, A=m.action_dim, beta=float(m.beta))
 
-    def params_struct(self):
+    def params_structs(self):
         flat = self.flat_params()
-        key = flat.data_ptr()
+        key = (flat.data_ptr(), self.n_slots)
         if self._pstruct_key != key:
-            self._pstruct = self._struct_for(flat)
+            self._pstructs = self._structs_for(flat)
+            self._pstruct = self._pstructs[0]
             self._pstruct_key = key
-        return self._pstruct
+        return self._pstructs
+
+    def params_struct(self):
+        return self.params_structs()[0]
 
     def _version_key(self):
         return (self._flat.data_ptr(), sum(p._version for _, p in self._named_params()), self.manual_version,
                 self.lib.op3_get_precision())
 
-    def prepared(self, stream):
-        """Derived weights (op3_prepare), refreshed whenever the parameters changed."""
-        ps = self.params_struct()
-        key = self._version_key()
-        if self._prep is None or self._prep_key != key or self._prep.device != self._flat.device:
+    def prepared_all(self, stream):
+        """Derived weights (op3_prepare) of every weight set, refreshed whenever the parameters changed."""
+        pss = self.params_structs()
+        nprep = len(pss) if (self.ns_dec or self.ns_ref) else 1      # only the conv networks have derived weights
+        key = self._version_key() + (nprep,)
+        if self._preps is None or self._prep_key != key or self._preps[0].device != self._flat.device:
             d = self.dims(1)
             n = self.lib.op3_prepared_floats(C.byref(d))
             if n == 0:
                 check(-1, "op3_prepared_floats")
-            if self._prep is None or self._prep.numel() != n or self._prep.device != self._flat.device:
-                self._prep = torch.empty(n, device=self._flat.device, dtype=torch.float32)
-            check(self.lib.op3_prepare(C.byref(d), C.byref(ps), ptr(self._prep), stream), "op3_prepare")
+            if (self._preps is None or len(self._preps) != nprep or self._preps[0].numel() != n
+                    or self._preps[0].device != self._flat.device):
+                self._preps = [torch.empty(n, device=self._flat.device, dtype=torch.float32) for _ in range(nprep)]
+            for k in range(nprep):
+                check(self.lib.op3_prepare(C.byref(d), C.byref(pss[k]), ptr(self._preps[k]), stream), "op3_prepare")
+            self._prep = self._preps[0]
             self._prep_key = key
-        return self._prep
+        return self._preps
+
+    def prepared(self, stream):
+        return self.prepared_all(stream)[0]
 
     # ------------------------------------------------------------------ forward
     def forward(self, images, actions, init_state, schedule, loss_schedule, noise_fn, need_grad):
@@ -262,10 +301,19 @@ class Engine:
                 raise ValueError("Invalid schedule entry: {}".format(s))
         st = torch.cuda.current_stream(dev).cuda_stream
         d = self.dims(B)
-        ps = self.params_struct()
-        prep = self.prepared(st)
+        pss = self.params_structs()
+        preps = self.prepared_all(st)
+        ps, prep = pss[0], preps[0]
         f32 = dict(device=dev, dtype=torch.float32)
         DD = D * D
+        # *_No_Sharing networks: slot k's rows (b, k) are gathered slot-major, the kernels run once per slot on B rows with
+        # weight set k, and the K results stay slot-major (row k*B + b) -- the reference's torch.cat row order, which the rest
+        # of the model reads as (b, k)-major again (decoder_network.py:146-162; kept as is)
+        ns_dec, ns_ref, ns_dyn = self.ns_dec, self.ns_ref, self.ns_dyn
+        d1 = Op3Dims(B=B, K=1, D=D, Rd=Rd, Rs=Rs, A=m.action_dim, beta=float(m.beta))     # one slot's B rows
+
+        def slot_major(t):
+            return t.view(B, K, *t.shape[1:]).transpose(0, 1).contiguous()                # (K, B, ...)
 
         if images is not None:
             images = images.contiguous().float()
@@ -323,18 +371,26 @@ class Engine:
         loss_rows = torch.zeros(max(T1, 1), 4, **f32)
 
         mix_sync = self.mix_sync(dev, st)
-        n_dec_acts = lib.op3_decoder_acts_floats(C.byref(d), N)
+        n_dec_acts = lib.op3_decoder_acts_floats(C.byref(d1), B) if ns_dec else lib.op3_decoder_acts_floats(C.byref(d), N)
         n_stats = lib.op3_mixture_stats_floats(C.byref(d))
-        n_ref_acts = lib.op3_refine_acts_floats(C.byref(d))
+        n_ref_acts = lib.op3_refine_acts_floats(C.byref(d1 if ns_ref else d))
         n_dyn_acts = lib.op3_dynamics_acts_floats(C.byref(d))
         dec_scratch = torch.empty(lib.op3_decoder_scratch_floats(C.byref(d), N), **f32)
 
         def decode(state, t_index, image, weight, refine_after, is_last):
             rec = _Decode()
             rec.state, rec.weight, rec.t_index, rec.refine_after = state, weight, t_index, refine_after
-            rec.acts = torch.empty(n_dec_acts, **f32)
             rec.dec_out = torch.empty(N, DD, 4, **f32)
-            check(lib.op3_decoder_fwd(C.byref(d), N, ptr(prep), ptr(state.z), ptr(rec.acts), ptr(rec.dec_out), st), "decoder_fwd")
+            if not ns_dec:
+                rec.acts = torch.empty(n_dec_acts, **f32)
+                check(lib.op3_decoder_fwd(C.byref(d), N, ptr(prep), ptr(state.z), ptr(rec.acts), ptr(rec.dec_out), st), "decoder_fwd")
+            else:
+                rec.zp = slot_major(state.z)
+                rec.acts = [torch.empty(n_dec_acts, **f32) for _ in range(K)]
+                out_v = rec.dec_out.view(K, B, DD, 4)
+                for k in range(K):
+                    check(lib.op3_decoder_fwd(C.byref(d1), B, ptr(preps[k]), ptr(rec.zp[k]), ptr(rec.acts[k]), ptr(out_v[k]), st),
+                          "decoder_fwd")
             want_stats = (weight != 0.0) or refine_after or (is_last and images is not None)
             rec.has_stats = want_stats
             io = Op3MixtureIO()
@@ -376,21 +432,47 @@ class Engine:
             step.kind, step.src, step.dec = "refine", state, dec
             step.dz = torch.empty(N, R, **f32)
             seed = dec.keep[-1]
-            check(lib.op3_decoder_bwd(C.byref(d), N, ptr(prep), ptr(state.z), ptr(dec.acts), ptr(seed), ptr(dec_scratch),
-                                      ptr(step.dz), 0, None, st), "decoder_bwd(latent)")
+            if not ns_dec:
+                check(lib.op3_decoder_bwd(C.byref(d), N, ptr(prep), ptr(state.z), ptr(dec.acts), ptr(seed), ptr(dec_scratch),
+                                          ptr(step.dz), 0, None, st), "decoder_bwd(latent)")
+            else:
+                seed_v, dzp = seed.view(K, B, DD, 4), torch.empty(K, B, R, **f32)
+                for k in range(K):
+                    check(lib.op3_decoder_bwd(C.byref(d1), B, ptr(preps[k]), ptr(dec.zp[k]), ptr(dec.acts[k]), ptr(seed_v[k]),
+                                              ptr(dec_scratch), ptr(dzp[k]), 0, None, st), "decoder_bwd(latent)")
+                step.dz = dzp.transpose(0, 1).reshape(N, R)
             new = _State()
             new.l1, new.l2 = torch.empty(N, Rs, **f32), torch.empty(N, Rs, **f32)
             new.h, new.c = torch.empty(N, LSTM, **f32), torch.empty(N, LSTM, **f32)
             new.z, new.eps = torch.empty(N, R, **f32), eps_new
-            step.acts = torch.empty(n_ref_acts, **f32)
             p1, p2 = state.prior_tensors()
-            io = Op3RefineIO()
-            io.dec_out, io.mix1, io.mix2, io.smp = dec.io.dec_out, dec.io.mix1, dec.io.mix2, dec.io.smp
-            io.dz, io.z, io.l1, io.l2, io.eps = ptr(step.dz), ptr(state.z), ptr(state.l1), ptr(state.l2), ptr(state.eps)
-            io.prior1, io.prior2, io.prior_is_post = ptr(p1), ptr(p2), 1 if state.prior_kind == "alias" else 0
-            io.h, io.c, io.acts = ptr(state.h), ptr(state.c), ptr(step.acts)
-            io.l1_out, io.l2_out, io.h_out, io.c_out = ptr(new.l1), ptr(new.l2), ptr(new.h), ptr(new.c)
-            check(lib.op3_refine_fwd(C.byref(d), C.byref(ps), ptr(prep), C.byref(io), st), "refine_fwd")
+            if not ns_ref:
+                step.acts = torch.empty(n_ref_acts, **f32)
+                io = Op3RefineIO()
+                io.dec_out, io.mix1, io.mix2, io.smp = dec.io.dec_out, dec.io.mix1, dec.io.mix2, dec.io.smp
+                io.dz, io.z, io.l1, io.l2, io.eps = ptr(step.dz), ptr(state.z), ptr(state.l1), ptr(state.l2), ptr(state.eps)
+                io.prior1, io.prior2, io.prior_is_post = ptr(p1), ptr(p2), 1 if state.prior_kind == "alias" else 0
+                io.h, io.c, io.acts = ptr(state.h), ptr(state.c), ptr(step.acts)
+                io.l1_out, io.l2_out, io.h_out, io.c_out = ptr(new.l1), ptr(new.l2), ptr(new.h), ptr(new.c)
+                check(lib.op3_refine_fwd(C.byref(d), C.byref(ps), ptr(prep), C.byref(io), st), "refine_fwd")
+            else:
+                # refinement_network.py:291-307: network k sees the rows (b, k) of every input; outputs stay slot-major
+                mix1, mix2 = dec.keep[-4], dec.keep[-3]
+                pin = [slot_major(t) for t in (dec.dec_out, mix1, mix2, step.dz, state.z, state.l1, state.l2, state.eps,
+                                               p1, p2, state.h, state.c)]
+                step.acts = [torch.empty(n_ref_acts, **f32) for _ in range(K)]
+                outs = [t.view(K, B, -1) for t in (new.l1, new.l2, new.h, new.c)]
+                io = []
+                for k in range(K):
+                    o = Op3RefineIO()
+                    o.dec_out, o.mix1, o.mix2, o.smp = ptr(pin[0][k]), ptr(pin[1][k]), ptr(pin[2][k]), dec.io.smp
+                    o.dz, o.z, o.l1, o.l2, o.eps = ptr(pin[3][k]), ptr(pin[4][k]), ptr(pin[5][k]), ptr(pin[6][k]), ptr(pin[7][k])
+                    o.prior1, o.prior2, o.prior_is_post = ptr(pin[8][k]), ptr(pin[9][k]), 1 if state.prior_kind == "alias" else 0
+                    o.h, o.c, o.acts = ptr(pin[10][k]), ptr(pin[11][k]), ptr(step.acts[k])
+                    o.l1_out, o.l2_out, o.h_out, o.c_out = ptr(outs[0][k]), ptr(outs[1][k]), ptr(outs[2][k]), ptr(outs[3][k])
+                    check(lib.op3_refine_fwd(C.byref(d1), C.byref(pss[k]), ptr(preps[k]), C.byref(o), st), "refine_fwd")
+                    io.append(o)
+                step.keep = pin
             check(lib.op3_sample_fwd(C.byref(d), N, ptr(new.l1), ptr(new.l2), ptr(new.eps), ptr(state.z), ptr(new.z), st), "sample")
             # the prior is carried over unchanged (op3_model.py:255)
             if state.prior_kind == "alias":
@@ -409,9 +491,22 @@ class Engine:
             new.l1, new.l2 = torch.empty(N, Rs, **f32), torch.empty(N, Rs, **f32)
             new.z, new.eps = torch.empty(N, R, **f32), eps_new
             new.h, new.c = torch.zeros(N, LSTM, **f32), torch.zeros(N, LSTM, **f32)   # op3_model.py:277-278
-            step.acts = torch.empty(n_dyn_acts, **f32)
-            check(lib.op3_dynamics_fwd(C.byref(d), C.byref(ps), ptr(state.z), ptr(act), ptr(step.acts),
-                                       ptr(new.z) if Rd else None, ptr(new.l1), ptr(new.l2), st), "dynamics_fwd")
+            if not ns_dyn:
+                step.acts = torch.empty(n_dyn_acts, **f32)
+                check(lib.op3_dynamics_fwd(C.byref(d), C.byref(ps), ptr(state.z), ptr(act), ptr(step.acts),
+                                           ptr(new.z) if Rd else None, ptr(new.l1), ptr(new.l2), st), "dynamics_fwd")
+            else:
+                # physics_network.py:221-232: model i runs on ALL rows; its rows (b, i) become output rows i*B + b
+                step.acts = [torch.empty(n_dyn_acts, **f32) for _ in range(K)]
+                z_all = torch.empty(K, N, R, **f32)
+                l1_all, l2_all = torch.empty(K, N, Rs, **f32), torch.empty(K, N, Rs, **f32)
+                for i in range(K):
+                    check(lib.op3_dynamics_fwd(C.byref(d), C.byref(pss[i]), ptr(state.z), ptr(act), ptr(step.acts[i]),
+                                               ptr(z_all[i]) if Rd else None, ptr(l1_all[i]), ptr(l2_all[i]), st), "dynamics_fwd")
+                pick = lambda t, w: t.view(K, B, K, w).diagonal(dim1=0, dim2=2).permute(2, 0, 1).reshape(N, w)
+                new.l1, new.l2 = pick(l1_all, Rs).contiguous(), pick(l2_all, Rs).contiguous()
+                if Rd:
+                    new.z[:, :Rd] = pick(z_all, R)[:, :Rd]
             check(lib.op3_sample_fwd(C.byref(d), N, ptr(new.l1), ptr(new.l2), ptr(new.eps), None, ptr(new.z), st), "sample")
             new.prior_kind = "alias"                                                  # op3_model.py:284-287
             step.dst = new
@@ -498,11 +593,16 @@ class Engine:
         dev = flat.device
         st = torch.cuda.current_stream(dev).cuda_stream
         f32 = dict(device=dev, dtype=torch.float32)
-        ps = self.params_struct()
-        prep = self.prepared(st)
+        pss = self.params_structs()
+        preps = self.prepared_all(st)
+        ps, prep = pss[0], preps[0]
         gflat = torch.zeros_like(flat)
-        gs = self._struct_for(gflat)
-        pg = torch.zeros_like(prep)
+        gss = self._structs_for(gflat)
+        gs = gss[0]
+        pgs = [torch.zeros_like(p) for p in preps]
+        pg = pgs[0]
+        ns_dec, ns_ref, ns_dyn = self.ns_dec, self.ns_ref, self.ns_dyn
+        d1 = Op3Dims(B=B, K=1, D=D, Rd=Rd, Rs=Rs, A=m.action_dim, beta=float(m.beta))
         dec_scratch = torch.empty(lib.op3_decoder_scratch_floats(C.byref(d), N), **f32)
         ref_scratch = None
         dyn_scratch = None
@@ -528,8 +628,15 @@ class Engine:
             if dc is not None and (w_clog != 0.0 or d_in is not None):
                 check(lib.op3_mixture_bwd(C.byref(d), C.byref(dc.io), w_clog, ptr(d_in), ptr(d_dec), C.byref(gs), None, st),
                       "mixture_bwd")
-                check(lib.op3_decoder_bwd(C.byref(d), N, ptr(prep), ptr(s.z), ptr(dc.acts), ptr(d_dec), ptr(dec_scratch),
-                                          ptr(s.dz), 1, ptr(pg), st), "decoder_bwd")
+                if not ns_dec:
+                    check(lib.op3_decoder_bwd(C.byref(d), N, ptr(prep), ptr(s.z), ptr(dc.acts), ptr(d_dec), ptr(dec_scratch),
+                                              ptr(s.dz), 1, ptr(pg), st), "decoder_bwd")
+                else:
+                    dd_v, dzp = d_dec.view(K, B, DD, 4), torch.empty(K, B, R, **f32)
+                    for k in range(K):
+                        check(lib.op3_decoder_bwd(C.byref(d1), B, ptr(preps[k]), ptr(dc.zp[k]), ptr(dc.acts[k]), ptr(dd_v[k]),
+                                                  ptr(dec_scratch), ptr(dzp[k]), 0, ptr(pgs[k]), st), "decoder_bwd")
+                    s.dz.view(B, K, R).add_(dzp.transpose(0, 1))
             # samples = eps*std(l2)+l1 and the KL term of this decode's loss
             owner = s.prior_owner() if w_kl != 0.0 else None
             if owner is not None:
@@ -545,21 +652,48 @@ class Engine:
             if step.kind == "refine":
                 if ref_scratch is None:
                     ref_scratch = torch.empty(lib.op3_refine_scratch_floats(C.byref(d)), **f32)
-                d_in_new = torch.empty(N, 5, DD, 4, **f32)
                 if Rd:
                     prev.dz[:, :Rd] += s.dz[:, :Rd]          # deter_state is carried over (op3_model.py:257)
-                check(lib.op3_refine_bwd(C.byref(d), C.byref(ps), ptr(prep), C.byref(step.io), ptr(s.dl1), ptr(s.dl2),
-                                         ptr(s.dh), ptr(s.dc), ptr(d_in_new), ptr(prev.dl1), ptr(prev.dl2), ptr(prev.dz),
-                                         ptr(prev.dh), ptr(prev.dc), C.byref(gs), ptr(pg), ptr(ref_scratch), st), "refine_bwd")
+                if not ns_ref:
+                    d_in_new = torch.empty(N, 5, DD, 4, **f32)
+                    check(lib.op3_refine_bwd(C.byref(d), C.byref(ps), ptr(prep), C.byref(step.io), ptr(s.dl1), ptr(s.dl2),
+                                             ptr(s.dh), ptr(s.dc), ptr(d_in_new), ptr(prev.dl1), ptr(prev.dl2), ptr(prev.dz),
+                                             ptr(prev.dh), ptr(prev.dc), C.byref(gs), ptr(pg), ptr(ref_scratch), st), "refine_bwd")
+                else:
+                    d_in_p = torch.empty(K, B, 5, DD, 4, **f32)
+                    tl1, tl2, tz = torch.zeros(K, B, Rs, **f32), torch.zeros(K, B, Rs, **f32), torch.zeros(K, B, R, **f32)
+                    th, tc = torch.zeros(K, B, LSTM, **f32), torch.zeros(K, B, LSTM, **f32)
+                    up = [t.view(K, B, -1) for t in (s.dl1, s.dl2, s.dh, s.dc)]          # output rows are slot-major
+                    for k in range(K):
+                        check(lib.op3_refine_bwd(C.byref(d1), C.byref(pss[k]), ptr(preps[k]), C.byref(step.io[k]), ptr(up[0][k]),
+                                                 ptr(up[1][k]), ptr(up[2][k]), ptr(up[3][k]), ptr(d_in_p[k]), ptr(tl1[k]), ptr(tl2[k]),
+                                                 ptr(tz[k]), ptr(th[k]), ptr(tc[k]), C.byref(gss[k]), ptr(pgs[k]), ptr(ref_scratch),
+                                                 st), "refine_bwd")
+                    d_in_new = d_in_p.transpose(0, 1).contiguous().view(N, 5, DD, 4)
+                    for dst, t in ((prev.dl1, tl1), (prev.dl2, tl2), (prev.dz, tz), (prev.dh, th), (prev.dc, tc)):
+                        dst.view(B, K, -1).add_(t.transpose(0, 1))
                 d_in_for[id(step.dec)] = d_in_new
             else:
                 if dyn_scratch is None:
                     dyn_scratch = torch.empty(lib.op3_dynamics_scratch_floats(C.byref(d)), **f32)
                 dz_tmp = torch.empty(N, R, **f32)
-                check(lib.op3_dynamics_bwd(C.byref(d), C.byref(ps), ptr(step.src.z), ptr(step.actions), ptr(step.acts),
-                                           ptr(s.dz), ptr(s.dl1), ptr(s.dl2), ptr(dz_tmp), C.byref(gs), ptr(dyn_scratch), st),
-                      "dynamics_bwd")
-                prev.dz += dz_tmp
+                if not ns_dyn:
+                    check(lib.op3_dynamics_bwd(C.byref(d), C.byref(ps), ptr(step.src.z), ptr(step.actions), ptr(step.acts),
+                                               ptr(s.dz), ptr(s.dl1), ptr(s.dl2), ptr(dz_tmp), C.byref(gs), ptr(dyn_scratch), st),
+                          "dynamics_bwd")
+                    prev.dz += dz_tmp
+                else:
+                    # output row i*B + b came from row (b, i) of model i: that model sees this gradient there, zero elsewhere
+                    def spread(t, w):
+                        u = torch.zeros(K, B, K, w, **f32)
+                        u.diagonal(dim1=0, dim2=2).copy_(t.view(K, B, w).permute(1, 2, 0))
+                        return u.view(K, N, w)
+                    uz, u1, u2 = spread(s.dz, R), spread(s.dl1, Rs), spread(s.dl2, Rs)
+                    for i in range(K):
+                        check(lib.op3_dynamics_bwd(C.byref(d), C.byref(pss[i]), ptr(step.src.z), ptr(step.actions), ptr(step.acts[i]),
+                                                   ptr(uz[i]), ptr(u1[i]), ptr(u2[i]), ptr(dz_tmp), C.byref(gss[i]), ptr(dyn_scratch),
+                                                   st), "dynamics_bwd")
+                        prev.dz += dz_tmp
             s.dz = s.dl1 = s.dl2 = s.dh = s.dc = None
         # initial state parameters (op3_model.py:168-171)
         s0 = tape.s0
@@ -572,7 +706,8 @@ class Engine:
             gview("initial_lambdas2", Rs).add_(s0.dl2.sum(0))
             if Rd:
                 gview("inital_deter_state", Rd).add_(s0.dz[:, :Rd].sum(0))
-        check(lib.op3_finalize_grads(C.byref(d), ptr(pg), C.byref(gs), st), "finalize_grads")
+        for k in range(len(pgs)):        # per weight set; the shared networks' accumulators live in set 0 only
+            check(lib.op3_finalize_grads(C.byref(d), ptr(pgs[k]), C.byref(gss[k]), st), "finalize_grads")
         s0.dz = s0.dl1 = s0.dl2 = s0.dh = s0.dc = None
         self.last_flat_grad = gflat
         return gflat

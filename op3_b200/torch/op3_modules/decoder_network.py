@@ -55,8 +55,36 @@ class DecoderNetwork(nn.Module):
         return decoder_forward(self, latents)
 
 
+def _ith_slot(x, K, i):
+    """rows (b, i) of a (bs*K, ...) tensor (decoder_network.py:156-162)."""
+    return None if x is None else x.view([-1, K] + list(x.shape[1:]))[:, i]
+
+
 class DecoderNetwork_v2_No_Sharing(nn.Module):
-    """decoder_network.py:92-162 (one decoder per slot).  Listed as 'next' in SURVEY.md section 8f; not built."""
-    def __init__(self, *args, **kwargs):
+    """decoder_network.py:92-162: one DecoderNetwork per slot (`models.<k>.broadcast_net...` state_dict keys).  Slot k decodes
+    the rows (b, k) of the (b, k)-major input; the K outputs are concatenated slot-major, i.e. output row k*bs + b holds
+    Dec_k(latents[b*K + k]) -- the reference's row order, which OP3Model then reads as (b, k)-major again (kept as is).
+    Inside OP3Model the engine runs the same kernels once per slot with that slot's weights (engine.py)."""
+    no_sharing = True
+
+    def __init__(self, input_width, input_height, input_channels, output_size, kernel_sizes, n_channels, strides,
+                 paddings, hidden_sizes=None, added_fc_input_size=0, batch_norm_conv=False, batch_norm_fc=False,
+                 init_w=1e-4, hidden_init=nn.init.xavier_uniform_, hidden_activation=nn.ReLU(),
+                 output_activation=identity, k=None):
         super().__init__()
-        raise NotImplementedError("DecoderNetwork_v2_No_Sharing ('reg_no_share') is not built in op3_b200 yet")
+        if k is None:
+            raise ValueError("A value of k is needed to initialize this model!")
+        self.K = k
+        self.input_width = input_width
+        self.models = nn.ModuleList([
+            DecoderNetwork(input_width, input_height, input_channels, output_size, kernel_sizes, n_channels, strides, paddings,
+                           hidden_sizes, added_fc_input_size, batch_norm_conv, batch_norm_fc, init_w, hidden_init,
+                           hidden_activation, output_activation) for _ in range(k)])
+
+    def forward(self, latents):
+        """latents (B*K,R) -> mask_logits (B*K,1,D,D), colors (B*K,3,D,D), rows slot-major (see class docstring)."""
+        outs = [self.models[i](self._get_ith_input(latents, i).contiguous()) for i in range(self.K)]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
+    def _get_ith_input(self, x, i):
+        return _ith_slot(x, self.K, i)

@@ -218,7 +218,10 @@ class OP3Model(nn.Module):
         from op3_b200.torch.op3_modules._standalone import decoder_forward
         B, K = hidden_states["post"]["samples"].shape[:2]
         z = self._flatten_first_two(self.get_full_tensor_state(hidden_states))
-        logits, colors = decoder_forward(self.decode_net, z, engine=self.engine)
+        if getattr(self.decode_net, "no_sharing", False):
+            logits, colors = self.decode_net(z.contiguous())             # one decoder per slot, rows slot-major
+        else:
+            logits, colors = decoder_forward(self.decode_net, z, engine=self.engine)
         D = self.image_size
         logits = logits.view(B, K, 1, D, D)
         return colors.view(B, K, 3, D, D), torch.softmax(logits, dim=1), logits

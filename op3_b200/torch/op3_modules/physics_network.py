@@ -74,7 +74,34 @@ class PhysicsNetwork(nn.Module):
 
 
 class PhysicsNetwork_v2_No_Sharing(nn.Module):
-    """physics_network.py:192-249.  Listed as 'next' in SURVEY.md section 8f; not built."""
-    def __init__(self, *args, **kwargs):
+    """physics_network.py:192-249: K full PhysicsNetworks (`models.<k>...` state_dict keys).  Model k is run on ALL rows
+    (every slot interacts with every other through model k's weights) and only its rows (b, k) are kept; the K results are
+    concatenated slot-major (output row k*bs + b), the reference's row order."""
+    no_sharing = True
+
+    def __init__(self, det_size, sto_size, action_size, action_enc_size, hidden_activation=nn.ELU(),
+                 deterministic_state_activation=identity, lambda_output_activation=identity, k=None):
         super().__init__()
-        raise NotImplementedError("PhysicsNetwork_v2_No_Sharing is not built in op3_b200 yet")
+        if k is None:
+            raise ValueError("A value of k is needed to initialize this model!")
+        self.K = k
+        self.det_size, self.sto_size, self.action_size = det_size, sto_size, action_size
+        self.models = nn.ModuleList([
+            PhysicsNetwork(det_size, sto_size, action_size, action_enc_size, hidden_activation, deterministic_state_activation,
+                           lambda_output_activation, k=k) for _ in range(k)])
+
+    def forward(self, sampled_state, actions):
+        """sampled_state (B*K,R), actions (B*K,A) or None -> (deter (B*K,Rd) or None, lambdas1, lambdas2), rows slot-major."""
+        det, l1, l2 = [], [], []
+        for i in range(self.K):
+            vals = self.models[i](sampled_state, actions)
+            det.append(self._get_ith_input(vals[0], i))
+            l1.append(self._get_ith_input(vals[1], i))
+            l2.append(self._get_ith_input(vals[2], i))
+        return (None if det[0] is None else torch.cat(det)), torch.cat(l1), torch.cat(l2)
+
+    def _get_ith_input(self, x, i):
+        return None if x is None else x.view([-1, self.K] + list(x.shape[1:]))[:, i]
+
+    def set_k(self, k):
+        assert k == self.K

@@ -54,6 +54,15 @@ class RefinementNetwork(nn.Module):
                      and list(hidden_sizes) == [128] and lstm_size == 128 and added_fc_input_size == 0
                      and isinstance(hidden_activation, nn.ELU) and input_width == input_height
                      and lstm_input_size == output_size * 5 + 128)
+        # the reference probes its conv stack with a zero image and AvgPool2d(input_width) in __init__ (:150-158): the
+        # 'large_reg' (paddings 0 -> 52x52 map) and 'large_sequence' (stride 2 -> 1x1 map) registry entries fail right there
+        side = input_width
+        for ks, stride, pad in zip(kernel_sizes, strides, paddings):
+            side = (side + 2 * pad - ks) // stride + 1
+        if side < input_width:
+            raise RuntimeError("Given input size: (%dx%dx%d). Calculated output size: (%dx0x0). Output size is too small "
+                               "(AvgPool2d(%d) after the conv stack; this registry entry does not construct in the reference "
+                               "either, refinement_network.py:157)" % (n_channels[-1], side, side, n_channels[-1], input_width))
         if not supported:
             raise NotImplementedError("only the 'size_dependent_conv' refinement architecture "
                                       "(refinement_network.py:31-46) is built")
@@ -92,7 +101,38 @@ class RefinementNetwork(nn.Module):
 
 
 class RefinementNetwork_v2_No_Sharing(nn.Module):
-    """refinement_network.py:235-322.  Listed as 'next' in SURVEY.md section 8f; not built."""
-    def __init__(self, *args, **kwargs):
+    """refinement_network.py:235-322: one RefinementNetwork per slot (`models.<k>...` state_dict keys); slot k refines the
+    rows (b, k) and the K outputs are concatenated slot-major (output row k*bs + b), the reference's row order."""
+    no_sharing = True
+
+    def __init__(self, input_width, input_height, input_channels, output_size, kernel_sizes, n_channels, strides,
+                 paddings, hidden_sizes, lstm_size, lstm_input_size, added_fc_input_size=0, batch_norm_conv=False,
+                 batch_norm_fc=False, init_w=1e-4, hidden_init=nn.init.xavier_uniform_, hidden_activation=nn.ReLU(),
+                 lambda_output_activation=identity, k=None):
         super().__init__()
-        raise NotImplementedError("RefinementNetwork_v2_No_Sharing is not built in op3_b200 yet")
+        if k is None:
+            raise ValueError("A value of k is needed to initialize this model!")
+        self.K = k
+        self.input_width, self.lstm_size = input_width, lstm_size
+        self.models = nn.ModuleList([
+            RefinementNetwork(input_width, input_height, input_channels, output_size, kernel_sizes, n_channels, strides,
+                              paddings, hidden_sizes, lstm_size, lstm_input_size, added_fc_input_size, batch_norm_conv,
+                              batch_norm_fc, init_w, hidden_init, hidden_activation, lambda_output_activation, k=None)
+            for _ in range(k)])
+
+    def forward(self, input, hidden1, hidden2, extra_input=None, add_fc_input=None):
+        """input (B*K,15,D,D), hidden1/2 (B*K,128), extra_input (B*K,5*Rs) -> (lambdas1, lambdas2, h, c), rows slot-major."""
+        g = self._get_ith_input
+        c = lambda t: None if t is None else t.contiguous()
+        outs = [self.models[i](c(g(input, i)), c(g(hidden1, i)), c(g(hidden2, i)), c(g(extra_input, i)), c(g(add_fc_input, i)))
+                for i in range(self.K)]
+        # the per-slot hidden outputs are (1, bs, lstm): torch.cat gives (K, bs, lstm) as in the reference (:304-305), which
+        # OP3Model.refine flattens to rows k*bs + b (op3_model.py:240-241)
+        return (torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs]),
+                torch.cat([o[2] for o in outs]), torch.cat([o[3] for o in outs]))
+
+    def _get_ith_input(self, x, i):
+        return None if x is None else x.view([-1, self.K] + list(x.shape[1:]))[:, i]
+
+    def initialize_hidden(self, bs):
+        return ptu.zeros((1, bs, self.lstm_size)), ptu.zeros((1, bs, self.lstm_size))

@@ -112,6 +112,45 @@ def make_params(action_dim, det=64, sto=64, seed=0, dtype=torch.float32, generic
     return p
 
 
+NETS = ("decode_net", "refinement_net", "dynamics_net")
+
+
+def make_params_no_share(action_dim, K, nets=NETS, det=64, sto=64, seed=0, dtype=torch.float32):
+    """Weights of a model whose sub-networks in ``nets`` are the *_No_Sharing variants: one weight set per slot under
+    ``<net>.models.<k>.`` (decoder_network.py:113-131, refinement_network.py:268-287, physics_network.py:208-216); slot k's
+    set comes from make_params(seed + 1000 (k + 1)), everything else from make_params(seed)."""
+    base = make_params(action_dim, det, sto, seed, dtype)
+    slots = [make_params(action_dim, det, sto, seed + 1000 * (k + 1), dtype) for k in range(K)]
+    out = OrderedDict()
+    for key, v in base.items():
+        net = key.split(".")[0]
+        if net in nets:
+            for k in range(K):
+                out["%s.models.%d.%s" % (net, k, key[len(net) + 1:])] = slots[k][key]
+        else:
+            out[key] = v
+    return out
+
+
+def _n_slots(p, net):
+    """Number of per-slot weight sets of ``net`` in a state dict (0 = shared weights)."""
+    pre = net + ".models."
+    return len({key[len(pre):].split(".")[0] for key in p if key.startswith(pre)})
+
+
+def _slot_view(p, net, k):
+    """``p`` with the keys ``<net>.models.<k>.x`` exposed as ``<net>.x`` (the k-th sub-network as a shared-weight one)."""
+    pre = "%s.models.%d." % (net, k)
+    q = {key: v for key, v in p.items() if not key.startswith(net + ".models.")}
+    q.update({net + "." + key[len(pre):]: v for key, v in p.items() if key.startswith(pre)})
+    return q
+
+
+def _ith(x, K, i):
+    """rows (b, i) of a (bs*K, ...) tensor: the *_No_Sharing `_get_ith_input` (decoder_network.py:156-162)."""
+    return None if x is None else x.reshape([-1, K] + list(x.shape[1:]))[:, i]
+
+
 def make_noise(B, K, sto, n_draws, seed=5, dtype=torch.float32):
     """Pre-generated sampling noise, one (B,K,sto) tensor per ``ptu.randn`` draw
     (op3_model.py:151, called from :172, :253, :282).  Seeds 5+i as in SURVEY.md section 8d."""
@@ -158,8 +197,11 @@ def elu(x):
 def decoder(p, z, D=64):
     """Spatial-broadcast decoder (decoder_network.py:83-88, conv_networks.py:326-350).
     z (N,R) -> (N,4,D,D), channels [r,g,b,mask_logit]."""
+    Kn = _n_slots(p, "decode_net")
+    if Kn:      # DecoderNetwork_v2_No_Sharing.forward (decoder_network.py:144-154): slot-major torch.cat of the K outputs
+        return torch.cat([decoder(_slot_view(p, "decode_net", k), _ith(z, Kn, k), D) for k in range(Kn)])
     N, R = z.shape
-    h = torch.cat([z.view(N, R, 1, 1).expand(N, R, D, D), coord_planes(D, z.dtype).expand(N, 2, D, D)], 1)
+    h = torch.cat([z.reshape(N, R, 1, 1).expand(N, R, D, D), coord_planes(D, z.dtype).expand(N, 2, D, D)], 1)
     for i in range(5):
         pre = "decode_net.broadcast_net.conv_layers.%d." % i
         h = F.conv2d(h, p[pre + "weight"], p[pre + "bias"], padding=2)
@@ -227,6 +269,11 @@ def layernorm1d(x, scale, center, eps=1e-6):
 
 def refinement_net(p, a, h, c, extra):
     """refinement_network.py:189-219 ('size_dependent_conv').  a (N,15,D,D), h/c (N,128), extra (N,5*sto)."""
+    Kn = _n_slots(p, "refinement_net")
+    if Kn:      # RefinementNetwork_v2_No_Sharing.forward (refinement_network.py:291-307); h, c come back as rows k*bs + b
+        outs = [refinement_net(_slot_view(p, "refinement_net", k), _ith(a, Kn, k), _ith(h, Kn, k), _ith(c, Kn, k),
+                               _ith(extra, Kn, k)) for k in range(Kn)]
+        return tuple(torch.cat([o[j] for o in outs]) for j in range(4))
     N, _, D, _ = a.shape
     x = torch.cat([a, coord_planes(D, a.dtype).expand(N, 2, D, D)], 1)
     for i in range(3):
@@ -259,6 +306,11 @@ def _mlp(p, name, x, out_act):
 
 def dynamics_net(p, z, actions, K, det=64, return_probes=False):
     """physics_network.py:94-141 (and :156-187 for the attention probes).  z (B*K,R), actions (B*K,A) or None."""
+    Kn = _n_slots(p, "dynamics_net")
+    if Kn:      # PhysicsNetwork_v2_No_Sharing.forward (physics_network.py:221-232): model i on ALL rows, its rows (b, i) kept
+        assert Kn == K and not return_probes
+        outs = [dynamics_net(_slot_view(p, "dynamics_net", i), z, actions, K, det) for i in range(K)]
+        return tuple(None if outs[0][j] is None else torch.cat([_ith(outs[i][j], K, i) for i in range(K)]) for j in range(3))
     N, R = z.shape
     B = N // K
     enc_flat = _mlp(p, "inertia_encoder", z, "elu")

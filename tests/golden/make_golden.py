@@ -111,6 +111,62 @@ def train_case(name, variant, K, action_dim, B, T, schedule, full_masks):
     print(name, "loss", res["total_loss"], "gnorm", res["grad_total_norm"])
 
 
+def noshare_case(name, variant, nets, K, action_dim, B, T, schedule):
+    """(f3) the *_No_Sharing registry entries (decoder_network.py:92, refinement_network.py:235, physics_network.py:192): one
+    training step of the unmodified reference with per-slot weight sets from orc.make_params_no_share."""
+    a = dict(variant["op3_args"])
+    a["K"] = K
+    types = {"decode_net": ("decoder_model_type", "reg_no_share"), "refinement_net": ("refinement_model_type", "size_dependent_conv_no_share"),
+             "dynamics_net": ("dynamics_model_type", "reg_ac32_no_share")}
+    for n in nets:
+        a[types[n][0]] = types[n][1]
+    m = ref_model.create_model_v2(a, a["det_repsize"], a["sto_repsize"], action_dim)
+    p = orc.make_params_no_share(action_dim, K, nets=nets, seed=0)
+    m.load_state_dict(p, strict=True)
+    frames = synth_frames(B, T)
+    actions = synth_actions(B, T) if action_dim else None
+    schedule = np.array(schedule, dtype=np.float64)
+    lw = np.arange(1, len(schedule) + 1)
+    NOISE.load(orc.make_noise(B, K, 64, len(schedule) + 1))
+    out = m.forward(frames, actions, None, schedule, lw)
+    out[3].backward()
+    res = {"schedule": schedule, "loss_schedule": lw, "B": B, "K": K, "T": T, "action_dim": action_dim, "nets": np.array(nets),
+           "total_loss": out[3].item(), "kle_loss": out[4].item(), "clog_prob": out[5].item(), "mse": out[6].item(),
+           "masks_list": out[1].detach().numpy(), "final_recon": out[2].detach().numpy()}
+    summarize("colors_list", out[0], res)
+    for k in ["lambdas1", "lambdas2", "samples", "deter_state"]:
+        summarize("state/" + k, out[7]["post"][k], res)
+    summarize("state/h", out[7]["post"]["extra_info"][0], res)
+    summarize("state/c", out[7]["post"]["extra_info"][1], res)
+    for k, v in m.named_parameters():
+        summarize("grad/" + k, v.grad if v.grad is not None else torch.zeros_like(v), res)
+    res["grad_total_norm"] = float(torch.nn.utils.clip_grad_norm_(list(m.parameters()), 5.0))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
+    print(name, "loss", res["total_loss"], "gnorm", res["grad_total_norm"])
+
+
+def noshare_cases():
+    noshare_case("noshare_all", pickplace_variant, orc.NETS, K=3, action_dim=4, B=2, T=3, schedule=[0, 0, 1, 0, 1])
+    noshare_case("noshare_dec_ref", stack_variant, ("decode_net", "refinement_net"), K=3, action_dim=0, B=3, T=2, schedule=[0, 0, 1])
+    noshare_case("noshare_dyn", pickplace_variant, ("dynamics_net",), K=4, action_dim=4, B=2, T=2, schedule=[0, 1, 0])
+    # the other two registry entries of refinement_network.py:15-62 cannot even be constructed in the reference: the shape
+    # probe of RefinementNetwork.__init__ (:150-158) runs AvgPool2d(input_width) on a 52x52 (large_reg: paddings 0) / 1x1
+    # (large_sequence: stride 2) feature map and raises
+    errs = {}
+    for key in ("large_reg", "large_sequence"):
+        a = dict(pickplace_variant["op3_args"])
+        a["K"] = 2
+        a["refinement_model_type"] = key
+        try:
+            m = ref_model.create_model_v2(a, a["det_repsize"], a["sto_repsize"], 4)       # already fails in __init__ (:157)
+            m.forward(synth_frames(1, 2), synth_actions(1, 2), None, np.array([0.0, 1.0]), np.array([1.0, 2.0]))
+            errs[key] = "ran"
+        except RuntimeError as e:
+            errs[key] = "RuntimeError: " + str(e)[:120]
+    np.savez_compressed(os.path.join(HERE, "registry_unrunnable.npz"), **{k: np.array(v) for k, v in errs.items()})
+    print(errs)
+
+
 def module_case():
     """Per-module forward goldens (decoder, refinement net, dynamics net) + refine-input pieces."""
     m, p = build_reference(pickplace_variant, 3, 4, seed=3)
@@ -345,7 +401,7 @@ if __name__ == "__main__":
     if only:                       # e.g. `make_golden.py mpc_stack pretrained`: regenerate selected (slow) cases only
         for name in only:
             {"mpc_stack": mpc_stack_case, "pretrained": pretrained_case, "mpc_large": mpc_large_case,
-             "mpc_stack_small": lambda: mpc_stack_case(Na=40), "activations": activation_case}[name]()
+             "mpc_stack_small": lambda: mpc_stack_case(Na=40), "activations": activation_case, "noshare": noshare_cases}[name]()
         sys.exit(0)
     schedule_case()
     train_case("stack_small", stack_variant, K=3, action_dim=0, B=2, T=2, schedule=[0, 0, 1], full_masks=True)
@@ -358,6 +414,7 @@ if __name__ == "__main__":
     mpc_case()
     mpc_large_case()
     activation_case()
+    noshare_cases()
     pretrained_case()
     mpc_stack_case(Na=40)
     mpc_stack_case()               # ~30-60 min of CPU: 4096 candidates x (5 decodes + 4 refinements), K=7
