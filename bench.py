@@ -381,12 +381,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    debug_steps = bool(os.environ.get("OP3_BENCH_DEBUG"))
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
+            if debug_steps:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
             fn(i)
+            if debug_steps:
+                t1 = time.perf_counter()
+                torch.cuda.synchronize()
+                print("[bench debug] %s step %d: host %.1f ms, host+device %.1f ms, allocated %.2f GB, reserved %.2f GB"
+                      % (fn.__name__, i, 1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t0), torch.cuda.memory_allocated() / 2**30,
+                         torch.cuda.memory_reserved() / 2**30), file=sys.stderr)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
