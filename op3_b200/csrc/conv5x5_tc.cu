@@ -363,10 +363,15 @@ constexpr int TQ_SMEM = TQ_A_BYTES + TQ_W_BYTES + 2 * TQ_XCH * 4 + EPI_WARPS * 1
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
                    float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
-                   const float4* __restrict__ ref, const uint32_t* __restrict__ maxbits, const float* __restrict__ wscale) {
-  const int P = D + TQ_PAD;   // pitch D + 2: the two right-hand pad columns of a row double as the left-hand pad of the next (3 % padding rows instead of 6 %)
-  const int tiles_img = (D * P + TQ_TS - 1) / TQ_TS;
-  const long long total = (long long)N * tiles_img;
+                   const float4* __restrict__ ref, const uint32_t* __restrict__ maxbits, const float* __restrict__ wscale,
+                   int W, int nstrips) {
+  // An "item" is one image (nstrips == 1, W == D) or one vertical strip of W output columns of an image (D = 128: two
+  // strips of 64, so that 128 + 4 P rows still fit four chunks of the ring).  Whole images use pitch D + 2: the two
+  // right-hand pad columns of a row double as the left-hand pad of the next (3 % padding rows instead of 6 %).  Strips carry
+  // REAL neighbour pixels in their halo columns, so both halos are stored: pitch W + 4.
+  const int P = nstrips == 1 ? D + TQ_PAD : W + 4;
+  const int tiles_img = (D * P + TQ_TS - 1) / TQ_TS;       // tiles per item
+  const long long total = (long long)N * nstrips * tiles_img;
   const int g0 = (int)(total * blockIdx.x / gridDim.x), g1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
   const int ngroups = (in.total_chunks + 3) / 4;           // K groups of 16 channels (1 or 2)
   // the warp index is broadcast with a shuffle so that the compiler KNOWS the role branches are warp-uniform (it then keeps
@@ -423,7 +428,8 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     int c = 0;                                             // running chunk counter of this CTA
     for (int g = g0; g < g1;) {
-      const int n = g / tiles_img, ta = g - n * tiles_img;
+      const int it = g / tiles_img, ta = g - it * tiles_img;
+      const int n = it / nstrips, x0 = (it - n * nstrips) * W;
       const int T = min(tiles_img - ta, g1 - g);
       const float sc = __uint_as_float(f16_scale_bits(maxbits[n]));
       const float4* s0[3];
@@ -441,8 +447,8 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
       auto load_chunk = [&](float4 (*dst)[2]) {            // loads the chunk at the current coordinates, then advances them
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          const bool ok = (unsigned)iy[u] < (unsigned)D && (unsigned)ix[u] < (unsigned)D;
-          const size_t off = (size_t)iy[u] * D + ix[u];
+          const bool ok = (unsigned)iy[u] < (unsigned)D && (unsigned)(ix[u] + x0) < (unsigned)D;
+          const size_t off = (size_t)iy[u] * D + ix[u] + x0;
           dst[u][0] = (ok && s0[u]) ? __ldg(s0[u] + off) : zero4;
           dst[u][1] = (ok && s1[u]) ? __ldg(s1[u] + off) : zero4;
           ix[u] += TQ_TS;
@@ -495,7 +501,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
       const unsigned long long t_begin = clock64();
 #endif
       for (int g = g0; g < g1;) {
-        const int n = g / tiles_img, ta = g - n * tiles_img;
+        const int ta = g % tiles_img;
         const int T = min(tiles_img - ta, g1 - g);
         const int c0 = c_run;
         int ready = c0 - 1;                                // last chunk known to be in shared memory
@@ -580,7 +586,8 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     const float m1 = lane < 31 ? 1.f : 0.f, m2 = lane < 30 ? 1.f : 0.f, m3 = lane < 29 ? 1.f : 0.f, m4 = lane < 28 ? 1.f : 0.f;
     int j = 0;
     for (int g = g0; g < g1;) {
-      const int n = g / tiles_img, ta = g - n * tiles_img;
+      const int it = g / tiles_img, ta = g - it * tiles_img;
+      const int n = it / nstrips, x0 = (it - n * nstrips) * W;
       const int T = min(tiles_img - ta, g1 - g);
       const float inv_scale = 1.f / (__uint_as_float(f16_scale_bits(maxbits[n])) * __ldg(wscale));   // powers of two: exact
       float omax = 0.f;
@@ -590,8 +597,8 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         const int r = quad * 32 + lane;
         const int p = TQ_TS * (ta + tau) + r;
         const int y = p / P, x = p - y * P;
-        const bool valid = r < TQ_TS && y < D && x < D;
-        const size_t obase = (((size_t)n * out_planes + out_chunk0) * D + (valid ? y : 0)) * D + (valid ? x : 0);
+        const bool valid = r < TQ_TS && y < D && x < W;
+        const size_t obase = (((size_t)n * out_planes + out_chunk0) * D + (valid ? y : 0)) * D + (valid ? x + x0 : 0);
         float4 ra[8];
         if (epi == EPI_MUL_ELUGRAD) {
 #pragma unroll
@@ -778,6 +785,18 @@ int launch_tc(cudaStream_t st, int N, int D, const ConvInput& in, const float* w
   return OP3_OK;
 }
 
+// Strip decomposition of a D x D image for the quint-tap kernel: one item if 128 + 4 (D + 2) rows fit four chunks of the
+// activation ring (D <= 90), else the fewest equal strips of W columns (W a multiple of 8) with 128 + 4 (W + 4) <= 4 * 124.
+bool tq_strips(int D, int* W, int* nstrips) {
+  if (128 + 4 * (D + TQ_PAD) <= 4 * TQ_TS) { *W = D; *nstrips = 1; return true; }
+  for (int ns = 2; ns <= 16; ++ns) {
+    if (D % ns) continue;
+    const int w = D / ns;
+    if (w % 8 == 0 && 128 + 4 * (w + 4) <= 4 * TQ_TS) { *W = w; *nstrips = ns; return true; }
+  }
+  return false;
+}
+
 int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* wt, const float* bias, int cout_real,
                float4* out, int out_planes, int out_chunk0, int out_chunks, int epi, const float4* ref,
                const uint32_t* maxbits, const float* wscale) {
@@ -786,19 +805,25 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
   }
   const int g_num_sms = device_sm_count();
-  const int P = D + TQ_PAD;
-  const long long total = (long long)N * ((D * P + TQ_TS - 1) / TQ_TS);
+  int W = 0, nstrips = 0;
+  OP3_REQUIRE(tq_strips(D, &W, &nstrips), "conv5x5_tcq: D=%d has no strip decomposition", D);
+  const int P = nstrips == 1 ? D + TQ_PAD : W + 4;
+  const long long total = (long long)N * nstrips * ((D * P + TQ_TS - 1) / TQ_TS);
   const int grid = total < g_num_sms ? (int)total : g_num_sms;
   conv5x5_tcq_kernel<<<grid, TC_THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
-                                                        out_chunks, epi, ref, maxbits, wscale);
+                                                        out_chunks, epi, ref, maxbits, wscale, W, nstrips);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
 }
 }  // namespace
 
-// the quint-tap kernel needs 128 + 4*P rows inside four 124-row chunks and at most two 16-channel K groups
-bool tc_quint_fits(int D, int total_chunks) { return 128 + 4 * (D + TQ_PAD) <= 4 * TQ_TS && total_chunks <= 8; }
+// the quint-tap kernel needs 128 + 4*P rows inside four 124-row chunks (whole images up to D = 90, column strips beyond)
+// and at most two 16-channel K groups
+bool tc_quint_fits(int D, int total_chunks) {
+  int W, ns;
+  return tq_strips(D, &W, &ns) && total_chunks <= 8;
+}
 
 #ifdef OP3_TC_TRACE
 extern "C" int op3_debug_tcq_epi(unsigned long long* out /*[8] host*/, int reset) {

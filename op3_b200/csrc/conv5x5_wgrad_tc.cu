@@ -684,14 +684,16 @@ constexpr int RB_SMEM = RB_RING_BYTES + 2 * RB_A_BYTES;
 __global__ void __launch_bounds__(RB_THREADS, 1)
 conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__ dpre, int g_planes,
                           int g_chunk0, int g_chunks, int cout_total, int co0, const uint32_t* __restrict__ xmax, int xmax_n,
-                          const uint32_t* __restrict__ gmax, int gmax_n, float* __restrict__ partial) {
+                          const uint32_t* __restrict__ gmax, int gmax_n, float* __restrict__ partial, int W, int nstrips) {
   constexpr int NCO = 32;
-  const int P = D + 8;                                     // multiple of 8
-  const int QN = (D + 4) * P;                              // padded-linear input pixels per image
+  // An "image" below is one item: a whole image (nstrips == 1, W == D) or one vertical strip of W output columns (D = 128:
+  // two strips of 64 -- the G ring holds 4 rows of pitch W + 8).  The X window of a strip reads its real neighbour columns.
+  const int P = W + 8;                                     // multiple of 8
+  const int QN = (D + 4) * P;                              // padded-linear input pixels per item
   const int NBLK = (QN + HG_BP - 1) / HG_BP;
   // Each CTA owns a contiguous range [g0, g1) of the global block sequence (image-major), balanced to one block; an
   // "item" is one image's share of that range.  Only the first item of a CTA can start inside an image.
-  const long long total_blocks = (long long)N * NBLK;
+  const long long total_blocks = (long long)N * nstrips * NBLK;
   const int g0 = (int)(total_blocks * blockIdx.x / gridDim.x), g1 = (int)(total_blocks * (blockIdx.x + 1) / gridDim.x);
   const int item0 = g0 / NBLK;
   const int n_items = g1 > g0 ? (g1 + NBLK - 1) / NBLK : 0;   // one past the last image this CTA touches
@@ -752,10 +754,10 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
 #pragma unroll
         for (int e = 0; e < 9; ++e) xv[e] = zero4;
         if (!act || vb_ < item_b0(item_)) return;
-        const int n = item_, q = vb_ * HG_BP + 8 * j;
+        const int n = item_ / nstrips, x0 = (item_ - n * nstrips) * W, q = vb_ * HG_BP + 8 * j;
         const float4* src = tc_src_chunk_ptr(in, cc, n, D);
         const int r = (int)__umulhi((uint32_t)q, magic);
-        const int iy = r - 2, ix = q - r * P - 2;          // q..q+7 share a row (q and P are multiples of 8)
+        const int iy = r - 2, ix = q - r * P - 2 + x0;     // q..q+7 share a row (q and P are multiples of 8)
         if (q < QN && (unsigned)iy < (unsigned)D) {
           const float4* rp = src + (size_t)iy * D + ix;
 #pragma unroll
@@ -763,7 +765,7 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
             if ((unsigned)(ix + e) < (unsigned)D) xv[e] = __ldg(rp + e);
         }
         int ix8 = ix + 8, iy8 = iy;
-        if (ix8 >= P - 2) { ix8 -= P; ++iy8; }
+        if (ix8 - x0 >= P - 2) { ix8 -= P; ++iy8; }
         if (q + 8 < QN && (unsigned)iy8 < (unsigned)D && (unsigned)ix8 < (unsigned)D) xv[8] = __ldg(src + (size_t)iy8 * D + ix8);
       };
       float4 xv[9], xn[9];
@@ -827,13 +829,13 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
 #pragma unroll
         for (int e = 0; e < 12; ++e) gv[e] = zero4;
         if (!act) return;
-        const int n = item_;
+        const int n = item_ / nstrips, x0 = (item_ - n * nstrips) * W;
         const float4* src = dpre + ((size_t)n * g_planes + g_chunk0 + cc) * D * D;
         const int p0 = vb_ * HG_BP + 8 * j;
         if (p0 >= 0) {
           const int y = (int)__umulhi((uint32_t)p0, magic), x = p0 - y * P;
-          if (y < D && x < D) {                            // x and D are multiples of 8: all 8 pixels are valid or none
-            const float4* rp = src + (size_t)y * D + x;
+          if (y < D && x < W) {                            // x and W are multiples of 8: all 8 pixels are valid or none
+            const float4* rp = src + (size_t)y * D + x + x0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) gv[4 + e] = __ldg(rp + e);
           }
@@ -841,8 +843,8 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
         const int pm = p0 - 8;                             // the chunk before: only its last 4 pixels are needed
         if (pm >= 0) {
           const int y = (int)__umulhi((uint32_t)pm, magic), x = pm - y * P;
-          if (y < D && x < D) {
-            const float4* rp = src + (size_t)y * D + x;
+          if (y < D && x < W) {
+            const float4* rp = src + (size_t)y * D + x + x0;
 #pragma unroll
             for (int e = 4; e < 8; ++e) gv[e - 4] = __ldg(rp + e);
           }
@@ -1145,6 +1147,18 @@ int launch_wgrad_f16(cudaStream_t st, int N, int D, const ConvInput& in, const f
 }
 
 // returns the number of per-CTA partial slabs written (the grid size)
+// Strip decomposition for the ring kernel: the refill of RB_PRE blocks must cover the 4-row halo of G chunks,
+// 4 (W + 8) / 8 <= 8 RB_PRE, i.e. W <= 72: whole images up to D = 72, else the fewest equal strips (W a multiple of 8).
+bool ring_strips(int D, int* W, int* nstrips) {
+  if (D % 8) return false;
+  for (int ns = 1; ns <= 16; ++ns) {
+    if (D % ns) continue;
+    const int w = D / ns;
+    if (w % 8 == 0 && 4 * ((w + 8) / 8) <= 8 * RB_PRE) { *W = w; *nstrips = ns; return true; }
+  }
+  return false;
+}
+
 int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const float4* dpre, int g_planes, int g_chunk0,
                       int g_chunks, int cout_total, int co0, const uint32_t* xmax, int xmax_n, const uint32_t* gmax,
                       int gmax_n, float* scratch, int* grid_out) {
@@ -1153,11 +1167,13 @@ int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const 
     OP3_CHECK(cudaFuncSetAttribute(conv5x5_wgrad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   }
   const int g_wg_sms = device_sm_count() > 148 ? 148 : device_sm_count();   // scratch is sized for 148 slabs
-  const int P = D + 8, NBLK = ((D + 4) * P + HG_BP - 1) / HG_BP;
-  const long long total_blocks = (long long)N * NBLK;
+  int W = 0, nstrips = 0;
+  OP3_REQUIRE(ring_strips(D, &W, &nstrips), "conv5x5_wgrad_ring: D=%d has no strip decomposition", D);
+  const int P = W + 8, NBLK = ((D + 4) * P + HG_BP - 1) / HG_BP;
+  const long long total_blocks = (long long)N * nstrips * NBLK;
   const int grid = total_blocks < g_wg_sms ? (int)total_blocks : g_wg_sms;
   conv5x5_wgrad_ring_kernel<<<grid, RB_THREADS, RB_SMEM, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total,
-                                                              co0, xmax, xmax_n, gmax, gmax_n, scratch);
+                                                              co0, xmax, xmax_n, gmax, gmax_n, scratch, W, nstrips);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   *grid_out = grid;
@@ -1192,7 +1208,8 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
   const size_t slab = (size_t)25 * cin_pad * cout + cout;
   int n_slabs = wg_sets();
   const bool f16 = precision == OP3_PREC_F16X3 && (cout >= 32 || cout == 4) && D % 8 == 0;
-  const bool use_ring = f16 && 4 * ((D + 8) / 8) <= 8 * RB_PRE;
+  int ring_w = 0, ring_ns = 0;
+  const bool use_ring = f16 && ring_strips(D, &ring_w, &ring_ns);
   const size_t zero_slabs = use_ring ? 148 : (size_t)wg_sets();
   // The per-row kernels leave padding entries of their slabs untouched (they must read as zero); the ring kernel writes
   // every entry of every slab it owns, so only the 8 operand-maxima words behind the slabs are cleared for it.
@@ -1218,7 +1235,7 @@ int conv5x5_wgrad_tc(cudaStream_t st, int precision, int N, int D, const ConvInp
       gmax = mx + 4; gmax_n = 1;
     }
     OP3_LAUNCH_CHECK();
-    if (4 * ((D + 8) / 8) <= 8 * RB_PRE) {               // ring kernel: its refill covers the 4-row halo of G chunks
+    if (use_ring) {                                      // ring kernel: its refill covers the 4-row halo of G chunks
       int grid = 0;
       for (int h = 0; h * 32 < cout; ++h)
         OP3_TRY(launch_wgrad_ring(st, N, D, in, dpre, planes, 8 * h, planes - 8 * h < 8 ? planes - 8 * h : 8, cout, 32 * h, xmax, xmax_n,
