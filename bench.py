@@ -573,7 +573,7 @@ def main():
     if cfg["kind"] == "train":
         line["roofline_mixture"] = mixture_roofline(model, dev, cfg, hbm, which, backward=False)
         line["roofline_mixture_bwd"] = mixture_roofline(model, dev, cfg, hbm, which, backward=True)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # the CPU oracle port is timed at N = 1 only (rank 0, host cores)
         threads = os.cpu_count() or 1
         if cfg["kind"] == "train":
             Bs = cfg["cpu_B"] if args.config == "c1" else min(cfg["cpu_B"], 4)
