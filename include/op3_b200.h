@@ -100,6 +100,10 @@ int op3_get_precision(void);
 /* The dynamics network and the head of the refinement network run as CTA-resident chains of layers (one launch forward, one
  * backward + one batched weight-gradient launch); 0 selects the layer-by-layer launches instead (A/B tests).  Default 1. */
 int op3_set_fused_mlp(int on);
+/* 1: the quint-tap convolution kernel of the fp16 mode runs as clusters of two CTAs sharing the weight operand of one
+ * tcgen05.mma.cta_group::2 stream (bit-identical results; its MMA stream is 27 % faster but the kernel is not, yet: its
+ * loaders and epilogue are issue-bound).  Default 0 = the single-CTA form. */
+int op3_set_tcq_pair(int on);
 
 /* Optional timing of kernel families with CUDA events on the launch stream (used by bench.py for the roofline
  * numbers).  Families: 0 = conv5x5 forward/dgrad, 1 = conv5x5 wgrad, 2 = mixture kernels, 3 = small GEMMs.

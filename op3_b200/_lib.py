@@ -64,6 +64,7 @@ SIGNATURES = {
     "op3_set_precision": (C.c_int, [C.c_int]),
     "op3_get_precision": (C.c_int, []),
     "op3_set_fused_mlp": (C.c_int, [C.c_int]),
+    "op3_set_tcq_pair": (C.c_int, [C.c_int]),
     "op3_profile_enable": (C.c_int, [C.c_int]),
     "op3_profile_collect": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
     "op3_prepared_floats": (C.c_size_t, [_P(Op3Dims)]),

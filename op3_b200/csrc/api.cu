@@ -64,6 +64,9 @@ extern "C" int op3_get_precision(void) { return g_precision; }
 static bool g_fused_mlp = true;
 namespace op3 { bool fused_mlp_enabled() { return g_fused_mlp; } }
 extern "C" int op3_set_fused_mlp(int on) { g_fused_mlp = on != 0; return OP3_OK; }
+static bool g_tcq_pair = false;   // opt-in: same results bit for bit, not faster yet (conv5x5_tc.cu, TqRoles)
+namespace op3 { bool tcq_pair_enabled() { return g_tcq_pair; } }
+extern "C" int op3_set_tcq_pair(int on) { g_tcq_pair = on != 0; return OP3_OK; }
 
 extern "C" const char* op3_version(void) { return "op3_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* op3_last_error(void) { return op3::g_err; }

@@ -50,6 +50,8 @@ struct ProfScope {
 // fused row-tile MLP chains (fused_mlp.cuh) for the dynamics network and the refinement head; op3_set_fused_mlp(0) selects the
 // layer-by-layer launches (kept for A/B tests and for parameter buffers whose rows are not 16-byte aligned)
 bool fused_mlp_enabled();
+// quint-tap conv kernel as CTA pairs (tcgen05 cta_group::2); op3_set_tcq_pair(0) selects the single-CTA form
+bool tcq_pair_enabled();
 
 // ---- small device helpers -------------------------------------------------------------------
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }

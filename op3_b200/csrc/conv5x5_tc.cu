@@ -342,8 +342,6 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
 // 124 pixels per tile -- the kernel's bottleneck once the tensor core needed only 2400 cycles per tile.
 __device__ __forceinline__ float elu_tc(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
-constexpr int TQ_IDLE_WARP = MMA_WARP + 4;           // the loader-range warp on the issuer's scheduler
-constexpr int TQ_LOAD_THREADS = LOAD_THREADS - 32;
 #ifndef OP3_TCQ_SMEM_A
 #define OP3_TCQ_TMEM_A 1      /* x_hi staged in TMEM once per kernel row (define OP3_TCQ_SMEM_A for the all-smem form) */
 #endif
@@ -358,9 +356,28 @@ constexpr int TQ_NQ = 160;                          // 5 taps x 32 output channe
 constexpr int TQ_W_SLAB = 2 * TQ_NQ * 16;           // one (K group, ky, hi/lo) slab: [k-chunk 2][160 rows][16 B]
 constexpr int TQ_W_BYTES = 2 * 5 * 2 * TQ_W_SLAB;
 constexpr int TQ_XCH = 4 * 2 * 10 * 16;             // floats per exchange buffer: [quad][half][(kx, lane < kx)][16]
-constexpr int TQ_SMEM = TQ_A_BYTES + TQ_W_BYTES + 2 * TQ_XCH * 4 + EPI_WARPS * 128 * 4;
+constexpr int TQ_SMEM = TQ_A_BYTES + TQ_W_BYTES + 2 * TQ_XCH * 4 + 8 * 128 * 4;          // single-CTA form, two epilogue groups
+constexpr int TQ_PAIR_NEG = 2;                      // epilogue groups of the pair form (3 fits its shared memory but not the issue slots, see below)
+constexpr int TQ_SMEM_PAIR = TQ_A_BYTES + TQ_W_BYTES / 2 + TQ_PAIR_NEG * TQ_XCH * 4 + 4 * TQ_PAIR_NEG * 128 * 4;
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// PAIR: the kernel runs as clusters of two CTAs driving ONE tcgen05.mma.cta_group::2 stream (M = 256): the two CTAs work on
+// two different items (images / strips) at the same tile position, so their operand rows sit at the same ring offsets; each
+// holds HALF of every weight slab (80 of the 160 stacked rows), which halves the weight bytes the tensor core fetches from each
+// CTA's shared memory (15.5 instead of 23 KB per kernel row and K group) -- the crossbar the loaders' stores and the
+// epilogue's shuffles compete for.  The leader (cluster rank 0) issues; loaders and epilogue warps of both CTAs report to the
+// leader's barriers (mapa + arrive.release.cluster), tcgen05.commit multicasts the completions back to both.
+// NEG epilogue groups of four warps (one per TMEM lane quadrant) take the tiles round-robin.  The single-CTA form has room for
+// two exchange buffer sets in its 227 KB.  Measured for the pair form (tools/tc_trace.py, decoder forward at N = 256): with two
+// groups the leader issues at 62 cycles per MMA (85 single-CTA) but waits 31 % of its loop for accumulators and 19 % for
+// operands -- 0.647 vs 0.615 ms; with three groups (640 threads, 96 registers) the accumulator wait disappears and the six
+// loader warps starve (64 % operand wait, 0.93 ms): loaders + epilogue are bound by instruction issue, not by the tensor pipe.
+template <int NEG> struct TqRoles {
+  static constexpr int EPI = 4 * NEG, MMA = EPI, IDLE = MMA + 4, LOAD0 = MMA + 1, NLOAD = 6;   // IDLE: the loader-range warp on the issuer's scheduler
+  static constexpr int THREADS = (LOAD0 + NLOAD + 1) * 32;
+  static constexpr int SMEM_X = NEG * TQ_XCH * 4 + EPI * 128 * 4;                              // exchange buffers + per-warp fix-up rows
+};
+template <bool PAIR, int NEG>
+__global__ void __launch_bounds__(TqRoles<NEG>::THREADS, 1)
 conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
                    float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
                    const float4* __restrict__ ref, const uint32_t* __restrict__ maxbits, const float* __restrict__ wscale,
@@ -371,40 +388,55 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   // REAL neighbour pixels in their halo columns, so both halos are stored: pitch W + 4.
   const int P = nstrips == 1 ? D + TQ_PAD : W + 4;
   const int tiles_img = (D * P + TQ_TS - 1) / TQ_TS;       // tiles per item
-  const long long total = (long long)N * nstrips * tiles_img;
-  const int g0 = (int)(total * blockIdx.x / gridDim.x), g1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  // PAIR: the tile sequence counts item PAIRS; CTA `rank` of pair blockIdx.x / 2 takes item 2 * (g / tiles_img) + rank
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int n_workers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x, worker = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const long long total = (long long)(PAIR ? N * nstrips / 2 : N * nstrips) * tiles_img;
+  const int g0 = (int)(total * worker / n_workers), g1 = (int)(total * (worker + 1) / n_workers);
+  constexpr int NQL = PAIR ? TQ_NQ / 2 : TQ_NQ;            // weight rows per slab held by this CTA
   const int ngroups = (in.total_chunks + 3) / 4;           // K groups of 16 channels (1 or 2)
   // the warp index is broadcast with a shuffle so that the compiler KNOWS the role branches are warp-uniform (it then keeps
   // the issuer's descriptor arithmetic in uniform registers)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
+  using Roles = TqRoles<NEG>;
+  constexpr int EPI_WARPS = Roles::EPI, MMA_WARP = Roles::MMA, TQ_IDLE_WARP = Roles::IDLE, LOAD_WARP0 = Roles::LOAD0,
+                TQ_LOAD_THREADS = Roles::NLOAD * 32, TC_THREADS = Roles::THREADS;
+  constexpr int W_BYTES = PAIR ? TQ_W_BYTES / 2 : TQ_W_BYTES;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* a_s = smem_raw;
   uint4* w_s = reinterpret_cast<uint4*>(smem_raw + TQ_A_BYTES);
-  float* xch = reinterpret_cast<float*>(smem_raw + TQ_A_BYTES + TQ_W_BYTES);
-  float* fixb = xch + 2 * TQ_XCH;                            // per epilogue warp: [4 target lanes][32] boundary sums
+  float* xch = reinterpret_cast<float*>(smem_raw + TQ_A_BYTES + W_BYTES);
+  float* fixb = xch + NEG * TQ_XCH;                            // per epilogue warp: [4 target lanes][32] boundary sums
   __shared__ uint64_t full_bar[TQ_NSLOT], empty_bar[TQ_NSLOT], acc_full[3], acc_empty[3];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[32];
 
   if (tid < 32) s_bias[tid] = (bias != nullptr && tid < cout_real) ? bias[tid] : 0.f;
   if (tid == 0) {
-    for (int s = 0; s < TQ_NSLOT; ++s) { mbar_init(&full_bar[s], TQ_LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS * 16); }
+    // PAIR: the leader's full / acc_empty barriers collect the arrivals of BOTH CTAs (the peer's own copies stay unused)
+    for (int s = 0; s < TQ_NSLOT; ++s) { mbar_init(&full_bar[s], (PAIR ? 2 : 1) * TQ_LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], (PAIR ? 2 : 1) * 128); }
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
+  if (warp == MMA_WARP) {
+    if (PAIR) tmem_alloc2<512>(&tmem_base_s);
+    else tmem_alloc<512>(&tmem_base_s);
+  }
   {   // resident weights: ordinary slab [K group][tap][k-chunk][64 rows: hi 0..31, lo 32..63] -> [K group][ky][hi/lo][k-chunk][kx*32 + co]
+    // (PAIR: only this CTA's half of the 160 stacked rows, [rank * 80, rank * 80 + 80))
     const uint4* wsrc = reinterpret_cast<const uint4*>(wt);
     for (int e = tid; e < ngroups * 25 * 2 * 64; e += TC_THREADS) {
       const int row64 = e & 63, kc = (e >> 6) & 1, tap = (e >> 7) % 25, cg = e / (128 * 25);
       const int hl = row64 >> 5, co = row64 & 31, ky = tap / 5, kx = tap - 5 * ky;
-      w_s[((((cg * 5 + ky) * 2 + hl) * 2 + kc) * TQ_NQ) + kx * 32 + co] = __ldg(wsrc + e);
+      const int r160 = kx * 32 + co, rl = r160 - (int)rank * NQL;
+      if (rl >= 0 && rl < NQL) w_s[((((cg * 5 + ky) * 2 + hl) * 2 + kc) * NQL) + rl] = __ldg(wsrc + e);
     }
   }
   fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();                            // both CTAs' barriers and TMEM exist before any remote arrive / MMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -428,7 +460,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     int c = 0;                                             // running chunk counter of this CTA
     for (int g = g0; g < g1;) {
-      const int it = g / tiles_img, ta = g - it * tiles_img;
+      const int itw = g / tiles_img, ta = g - itw * tiles_img, it = PAIR ? 2 * itw + (int)rank : itw;
       const int n = it / nstrips, x0 = (it - n * nstrips) * W;
       const int T = min(tiles_img - ta, g1 - g);
       const float sc = __uint_as_float(f16_scale_bits(maxbits[n]));
@@ -475,7 +507,8 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
             if (row < 128) { ph[row + TQ_RING] = hi; pl[row + TQ_RING] = lo; }
           }
         fence_proxy_async();
-        mbar_arrive(&full_bar[slot]);
+        if (PAIR) mbar_arrive_cluster(&full_bar[slot], 0);
+        else mbar_arrive(&full_bar[slot]);
 #pragma unroll
         for (int u = 0; u < 3; ++u) { v[u][0] = vn[u][0]; v[u][1] = vn[u][1]; }
       }
@@ -487,12 +520,12 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     // descriptor words computed by all lanes from loop counters and kernel parameters stay in UNIFORM registers.  Issued
     // from inside an `if (lane == 0)` region instead, every MMA is wrapped in an ELECT / R2UR.BROADCAST waterfall of ~12
     // instructions (~25 cycles per MMA: the whole gap between the isolated and the in-situ MMA rate).
-    {
+    if (!PAIR || rank == 0) {
       const bool leader = elect_one();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t idesc = make_idesc_f16(128, TQ_NQ);
+      const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, TQ_NQ);
       const uint64_t ad = make_smem_desc(smem_u32(a_s), TQ_ROWS, 8);
-      const uint64_t bd = make_smem_desc(smem_u32(w_s), TQ_NQ, 8);
+      const uint64_t bd = make_smem_desc(smem_u32(w_s), NQL, 8);
       const uint32_t a_lo32 = (uint32_t)ad, a_hi32 = (uint32_t)(ad >> 32);
       const uint32_t b_lo32 = (uint32_t)bd, b_hi32 = (uint32_t)(bd >> 32);
       int c_run = 0, j = 0;
@@ -538,31 +571,46 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
               for (int ky = 0; ky < 5; ++ky) {
                 const uint32_t a_hi_op = arow[ky] + (uint32_t)((2 * cg) * TQ_ROWS);             // 16-byte units
                 const uint32_t a_lo_op = arow[ky] + (uint32_t)((4 + 2 * cg) * TQ_ROWS);
-                const uint32_t b_hi_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 0) * 2 * TQ_NQ);
-                const uint32_t b_lo_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 1) * 2 * TQ_NQ);
+                const uint32_t b_hi_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 0) * 2 * NQL);
+                const uint32_t b_lo_op = b_lo32 + (uint32_t)(((cg * 5 + ky) * 2 + 1) * 2 * NQL);
                 if (leader) {
+                  if (PAIR) {
+                    tc2_cp_a128(tmem_u + 480u, a_hi_op, a_hi32);
+                    if (cg == 0 && ky == 0) mma2_f16_ts(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc, 0u);
+                    else mma2_f16_ts_acc(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc);
+                    mma2_f16_ts_acc(dcol, tmem_u + 480u, b_lo_op, b_hi32, idesc);
+                    mma2_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+                  } else {
 #ifdef OP3_TCQ_TMEM_A
-                  // x_hi feeds two MMAs: staged once in the 8 TMEM columns behind the accumulators (tcgen05.cp, in issue order
-                  // with the MMAs), so they fetch only their 5 KB of weights from shared memory
-                  tc_cp_a128(tmem_u + 480u, a_hi_op, a_hi32);
-                  if (cg == 0 && ky == 0) mma_f16_ts(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc, 0u);
-                  else mma_f16_ts_acc(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc);
-                  mma_f16_ts_acc(dcol, tmem_u + 480u, b_lo_op, b_hi32, idesc);
+                    // x_hi feeds two MMAs: staged once in the 8 TMEM columns behind the accumulators (tcgen05.cp, in issue order
+                    // with the MMAs), so they fetch only their 5 KB of weights from shared memory
+                    tc_cp_a128(tmem_u + 480u, a_hi_op, a_hi32);
+                    if (cg == 0 && ky == 0) mma_f16_ts(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc, 0u);
+                    else mma_f16_ts_acc(dcol, tmem_u + 480u, b_hi_op, b_hi32, idesc);
+                    mma_f16_ts_acc(dcol, tmem_u + 480u, b_lo_op, b_hi32, idesc);
 #else
-                  if (cg == 0 && ky == 0) mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, 0u);
-                  else mma_f16_acc(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc);
-                  mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
+                    if (cg == 0 && ky == 0) mma_f16(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc, 0u);
+                    else mma_f16_acc(dcol, a_hi_op, a_hi32, b_hi_op, b_hi32, idesc);
+                    mma_f16_acc(dcol, a_hi_op, a_hi32, b_lo_op, b_hi32, idesc);
 #endif
-                  mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+                    mma_f16_acc(dcol, a_lo_op, a_hi32, b_hi_op, b_hi32, idesc);
+                  }
                 }
               }
             }
           }
           if (leader) {
-            tc_commit(&empty_bar[(c0 + tau) % TQ_NSLOT]);  // chunk c0+tau is dead once these MMAs have read it
-            if (tau == T - 1)
-              for (int x = 0; x < 3; ++x) tc_commit(&empty_bar[(c0 + T + x) % TQ_NSLOT]);   // the tail halo chunks of the item
-            tc_commit(&acc_full[slot]);
+            if (PAIR) {                                    // the same barrier offsets in both CTAs
+              tc2_commit(&empty_bar[(c0 + tau) % TQ_NSLOT]);
+              if (tau == T - 1)
+                for (int x = 0; x < 3; ++x) tc2_commit(&empty_bar[(c0 + T + x) % TQ_NSLOT]);
+              tc2_commit(&acc_full[slot]);
+            } else {
+              tc_commit(&empty_bar[(c0 + tau) % TQ_NSLOT]);  // chunk c0+tau is dead once these MMAs have read it
+              if (tau == T - 1)
+                for (int x = 0; x < 3; ++x) tc_commit(&empty_bar[(c0 + T + x) % TQ_NSLOT]);   // the tail halo chunks of the item
+              tc_commit(&acc_full[slot]);
+            }
           }
           __syncwarp();
         }
@@ -586,24 +634,19 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     const float m1 = lane < 31 ? 1.f : 0.f, m2 = lane < 30 ? 1.f : 0.f, m3 = lane < 29 ? 1.f : 0.f, m4 = lane < 28 ? 1.f : 0.f;
     int j = 0;
     for (int g = g0; g < g1;) {
-      const int it = g / tiles_img, ta = g - it * tiles_img;
+      const int itw = g / tiles_img, ta = g - itw * tiles_img, it = PAIR ? 2 * itw + (int)rank : itw;
       const int n = it / nstrips, x0 = (it - n * nstrips) * W;
       const int T = min(tiles_img - ta, g1 - g);
       const float inv_scale = 1.f / (__uint_as_float(f16_scale_bits(maxbits[n])) * __ldg(wscale));   // powers of two: exact
       float omax = 0.f;
       for (int tau = 0; tau < T; ++tau, ++j) {
-        if ((j & 1) != grp) continue;
+        if ((j % NEG) != grp) continue;
         const int slot = j % 3;
         const int r = quad * 32 + lane;
         const int p = TQ_TS * (ta + tau) + r;
         const int y = p / P, x = p - y * P;
         const bool valid = r < TQ_TS && y < D && x < W;
         const size_t obase = (((size_t)n * out_planes + out_chunk0) * D + (valid ? y : 0)) * D + (valid ? x + x0 : 0);
-        float4 ra[8];
-        if (epi == EPI_MUL_ELUGRAD) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ra[i] = (valid && i < out_chunks) ? __ldg(&ref[obase + i * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
-        }
 #ifdef OP3_TC_TRACE
         const unsigned long long te0 = clock64();
 #endif
@@ -657,7 +700,15 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[slot]);                       // every TMEM read of this tile is done
+        if (PAIR) mbar_arrive_cluster(&acc_empty[slot], 0);  // every TMEM read of this tile is done (the leader collects both CTAs)
+        else mbar_arrive(&acc_empty[slot]);
+        // dgrad: the activation outputs whose ELU' multiplies the result -- requested only now (the tap-shift temporaries are
+        // dead), their latency hides behind the group barrier and the boundary fix-up
+        float4 ra[8];
+        if (epi == EPI_MUL_ELUGRAD) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ra[i] = (valid && i < out_chunks) ? __ldg(&ref[obase + i * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
 #ifdef OP3_TC_TRACE
         const unsigned long long te2 = clock64();
 #endif
@@ -735,8 +786,13 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
+  if (PAIR) {
+    cluster_sync_all();                                    // nobody leaves while its peer may still arrive on its barriers / use its TMEM
+    if (warp == MMA_WARP) tmem_dealloc2<512>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
+  }
 }
 
 
@@ -802,16 +858,49 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
                const uint32_t* maxbits, const float* wscale) {
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<true, TQ_PAIR_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM_PAIR));
   }
   const int g_num_sms = device_sm_count();
   int W = 0, nstrips = 0;
   OP3_REQUIRE(tq_strips(D, &W, &nstrips), "conv5x5_tcq: D=%d has no strip decomposition", D);
   const int P = nstrips == 1 ? D + TQ_PAD : W + 4;
-  const long long total = (long long)N * nstrips * ((D * P + TQ_TS - 1) / TQ_TS);
+  const int tiles_img = (D * P + TQ_TS - 1) / TQ_TS;
+  const long long items = (long long)N * nstrips;
+  if (tcq_pair_enabled() && items % 2 == 0 && items >= 2) {
+    // CTA pairs (cta_group::2): one cluster of two CTAs per TPC, each pair owns a contiguous range of item-pair tiles
+    const long long total = items / 2 * tiles_img;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(TqRoles<TQ_PAIR_NEG>::THREADS);
+    cfg.dynamicSmemBytes = TQ_SMEM_PAIR;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent pairs: as many clusters as can be resident at once (a pair needs both SMs of a TPC), cached per device
+    static int max_pairs[OP3_MAX_DEVICES] = {};
+    int dev = 0;
+    OP3_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < OP3_MAX_DEVICES && max_pairs[dev] == 0) {
+      cfg.gridDim = dim3(2 * (g_num_sms / 2));
+      int nc = 0;
+      OP3_CHECK(cudaOccupancyMaxActiveClusters(&nc, conv5x5_tcq_kernel<true, TQ_PAIR_NEG>, &cfg));
+      max_pairs[dev] = nc > 0 ? nc : 1;
+    }
+    int pairs = (dev >= 0 && dev < OP3_MAX_DEVICES) ? max_pairs[dev] : g_num_sms / 2;
+    if (total < pairs) pairs = (int)total;
+    cfg.gridDim = dim3(2 * pairs);
+    OP3_CHECK(cudaLaunchKernelEx(&cfg, conv5x5_tcq_kernel<true, TQ_PAIR_NEG>, in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
+                                 out_chunks, epi, ref, maxbits, wscale, W, nstrips));
+    OP3_COUNT_LAUNCH();
+    return OP3_OK;
+  }
+  const long long total = items * tiles_img;
   const int grid = total < g_num_sms ? (int)total : g_num_sms;
-  conv5x5_tcq_kernel<<<grid, TC_THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
-                                                        out_chunks, epi, ref, maxbits, wscale, W, nstrips);
+  conv5x5_tcq_kernel<false, 2><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
+                                                               out_chunks, epi, ref, maxbits, wscale, W, nstrips);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;

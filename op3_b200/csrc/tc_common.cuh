@@ -82,6 +82,70 @@ __device__ __forceinline__ void mma_f16_ts_acc(uint32_t d_tmem, uint32_t a_tmem,
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, 1;\n\t}\n"
       :: "r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
 }
+// ---- cta_group::2: one MMA over a CTA PAIR (tests/probes/probe_2cta.cu).  M = 256: each CTA supplies its own 128 A rows
+// at the same shared-memory offset and receives its 128 accumulator rows in its own TMEM; B has N rows in total, each CTA
+// supplies N/2 of them (rank 0 the first half) from the same offset.  Issued by the leader CTA (cluster rank 0) only.
+__device__ __forceinline__ void mma2_f16(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_acc(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n\t}\n"
+      :: "r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void tc2_cp_a128(uint32_t a_tmem, uint32_t alo, uint32_t ahi) {     // in both CTAs, each from its own smem
+  asm volatile("{\n\t.reg .b64 da;\n\tmov.b64 da, {%1, %2};\n\ttcgen05.cp.cta_group::2.128x256b [%0], da;\n\t}\n"
+               :: "r"(a_tmem), "r"(alo), "r"(ahi) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ts_acc(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, 1;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the preceding MMAs / copies completed
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// arrive (release at cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem) {  // one whole warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(COLS) : "memory");
+}
+
 // Power-of-two scale that brings a tensor whose largest magnitude has the fp32 bit pattern `maxbits` into [2^13, 2^14)
 // (fp16 overflows at 2^16; products are accumulated in fp32).  Zero / denormal maxima get scale 1.
 __host__ __device__ __forceinline__ uint32_t f16_scale_bits(uint32_t maxbits) {

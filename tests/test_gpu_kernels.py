@@ -316,3 +316,37 @@ def test_prepare_frames_and_device_dataset():
     assert torch.allclose(item.cpu(), ref[7] * 255.0) and torch.equal(ai.cpu(), acts[:, 7])
     with pytest.raises(RuntimeError):
         frames_to_float(planar.cpu())
+
+
+def test_quint_pair_kernel_is_bit_identical_to_single_cta():
+    """The cta_group::2 form of the quint-tap kernel (CTA pairs sharing the weight operand) issues the same MMAs in the same
+    order on the same operands as the single-CTA form: decoder forward + latent gradient must agree bit for bit."""
+    import op3_b200
+    lib = _lib().load()
+    from op3_b200._lib import check, ptr
+    op3_b200.set_precision("f16x3")
+    try:
+        for K, B in ((4, 6), (3, 2), (7, 9)):
+            m, p = build_model(0, K, seed=9)
+            eng = m.engine
+            N, R = B * K, 128
+            z = (torch.randn(N, R, generator=torch.Generator().manual_seed(K)) * 0.7).cuda()
+            st = torch.cuda.current_stream().cuda_stream
+            d = eng.dims(B)
+            prep = eng.prepared(st)
+            seed = torch.randn(N, 64 * 64, 4, generator=torch.Generator().manual_seed(B)).cuda()
+            res = []
+            for pair in (0, 1):
+                lib.op3_set_tcq_pair(pair)
+                acts = torch.empty(lib.op3_decoder_acts_floats(C.byref(d), N), device="cuda")
+                out = torch.empty(N, 64 * 64, 4, device="cuda")
+                check(lib.op3_decoder_fwd(C.byref(d), N, ptr(prep), ptr(z), ptr(acts), ptr(out), st))
+                scratch = torch.empty(lib.op3_decoder_scratch_floats(C.byref(d), N), device="cuda")
+                dz = torch.empty(N, R, device="cuda")
+                check(lib.op3_decoder_bwd(C.byref(d), N, ptr(prep), ptr(z), ptr(acts), ptr(seed), ptr(scratch), ptr(dz), 0, None, st))
+                torch.cuda.synchronize()
+                res.append((out, dz))
+            assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), (K, B)
+    finally:
+        lib.op3_set_tcq_pair(0)
+        op3_b200.set_precision("fp32")

@@ -35,6 +35,8 @@ def main():
     out = torch.empty(N, 64 * 64, 4, device=dev)
     f = lib.op3_debug_tc_trace
     f.argtypes = [C.c_void_p, C.c_int]
+    if os.environ.get("TCQ_PAIR"):
+        lib.op3_set_tcq_pair(int(os.environ["TCQ_PAIR"]))
     for _ in range(3):
         check(lib.op3_decoder_fwd(C.byref(d), N, ptr(prep), ptr(z), ptr(acts), ptr(out), st), "decoder_fwd")
     torch.cuda.synchronize()
