@@ -251,6 +251,10 @@ int op3_adam_clip(long long n, float* params, const float* grads, float* exp_avg
  * argk [G][Na] (int).  Fixed reduction order: results are bit-reproducible run to run. */
 int op3_mpc_cost(int Na, int Kp, int G, int D, const float* pred, const float* goal, float* cost, int* argk,
                  void* stream);
+/* General form (mpc_stack.py:60-100): rows of n_el elements (3*D*D for sub-images, R for core_type 'latent');
+ * compare 0 = 'mse', 1 = 'psuedo_intersect'; post 0 = 'raw', 1 = 'negative_exp' (applied before the min over Kp). */
+int op3_mpc_cost_ex(int Na, int Kp, int G, int n_el, int compare, int post, const float* pred, const float* goal, float* cost,
+                    int* argk, void* stream);
 /* Standalone OP3Model.get_loss (op3_model.py:313-327): colors [B][K][3][D][D], mask [B][K][1][D][D] (post-softmax),
  * image [B][3][D][D], lambdas [B*K][Rs] -> color_probs [B][K][D][D], pixel_ll [B][D][D] (pixel_complete_log_likelihood),
  * losses[3] = (kle_loss, complete_log_likelihood, total_loss).  scratch: op3_get_loss_scratch_floats, 8-byte aligned. */

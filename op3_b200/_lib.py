@@ -97,6 +97,7 @@ SIGNATURES = {
     "op3_adam_clip": (C.c_int, [C.c_longlong, c_fp, c_fp, c_fp, c_fp, C.c_int, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, c_fp, c_fp]),
     "op3_mpc_cost": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "op3_mpc_cost_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "op3_get_loss_scratch_floats": (C.c_size_t, [_P(Op3Dims)]),
     "op3_get_loss": (C.c_int, [_P(Op3Dims), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "op3_sub_images": (C.c_int, [C.c_longlong, C.c_int, c_fp, c_fp, c_fp, c_fp]),

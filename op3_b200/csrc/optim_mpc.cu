@@ -52,49 +52,74 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restric
   }
 }
 
-// sums[(a*Kp+k)*G + g] = sum over (3,D,D) of (goal_g - pred_{a,k})^2 ; one CTA per (a,k); fixed-order reduction
-template <int GMAX>
+// sums[(a*Kp+k)*G + g] = distance of goal g and prediction (a,k) over n_el elements, before the mean; one CTA per (a,k);
+// fixed-order reduction.  CMP 0: sum of squared differences (Cost.image_mse / Cost.mse, mpc_stack.py:103-127).
+// CMP 1: 'psuedo_intersect' (mpc_stack.py:84-92): 1 - |{g > .01, p > .01, (g-p)^2 < .08}| / (|{g > .01}| + |{p > .01}|).
+template <int GMAX, int CMP>
 __global__ void __launch_bounds__(256) mpc_sqerr_kernel(int G, int n_el, const float* __restrict__ pred,
                                                         const float* __restrict__ goal, double* __restrict__ sums) {
   __shared__ double red[256];
   const float* pp = pred + (size_t)blockIdx.x * n_el;
-  float acc[GMAX];
+  float acc[GMAX], cg[GMAX];
+  float cp = 0.f;
 #pragma unroll
-  for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
+  for (int g = 0; g < GMAX; ++g) { acc[g] = 0.f; cg[g] = 0.f; }
   for (int i = threadIdx.x; i < n_el; i += 256) {
     float pv = pp[i];
+    if (CMP == 1) cp += pv > 0.01f ? 1.f : 0.f;
 #pragma unroll
     for (int g = 0; g < GMAX; ++g)
       if (g < G) {
-        float dlt = __ldg(goal + (size_t)g * n_el + i) - pv;
-        acc[g] = fmaf(dlt, dlt, acc[g]);
+        const float gv = __ldg(goal + (size_t)g * n_el + i);
+        const float dlt = gv - pv;
+        if (CMP == 0) {
+          acc[g] = fmaf(dlt, dlt, acc[g]);
+        } else {
+          const bool m1 = gv > 0.01f;
+          cg[g] += m1 ? 1.f : 0.f;
+          acc[g] += (m1 && pv > 0.01f && dlt * dlt < 0.08f) ? 1.f : 0.f;
+        }
       }
   }
-  for (int g = 0; g < G; ++g) {
-    double mine = 0.0;
-#pragma unroll
-    for (int q = 0; q < GMAX; ++q)
-      if (q == g) mine = (double)acc[q];
+  auto block_sum = [&](double mine) {
     red[threadIdx.x] = mine;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
       if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) sums[(size_t)blockIdx.x * G + g] = red[0];
+    const double r = red[0];
     __syncthreads();
+    return r;
+  };
+  const double pcount = CMP == 1 ? block_sum((double)cp) : 0.0;
+  for (int g = 0; g < G; ++g) {
+    double mine = 0.0, mg = 0.0;
+#pragma unroll
+    for (int q = 0; q < GMAX; ++q)
+      if (q == g) { mine = (double)acc[q]; mg = (double)cg[q]; }
+    const double a = block_sum(mine);
+    if (CMP == 0) {
+      if (threadIdx.x == 0) sums[(size_t)blockIdx.x * G + g] = a;
+    } else {
+      const double gcount = block_sum(mg);
+      // counts are small integers: the float division below is the reference's (0/0 = NaN when both images are empty)
+      if (threadIdx.x == 0) sums[(size_t)blockIdx.x * G + g] = (double)(1.f - (float)a / ((float)gcount + (float)pcount));
+    }
   }
 }
 
-__global__ void mpc_min_kernel(int Na, int Kp, int G, int n_el, const double* __restrict__ sums, float* __restrict__ cost,
-                               int* __restrict__ argk) {
+// min over the Kp predictions of post(dist): post 0 = raw, 1 = -exp(-dist) ('negative_exp', mpc_stack.py:94-100)
+__global__ void mpc_min_kernel(int Na, int Kp, int G, double inv_n, int post, const double* __restrict__ sums,
+                               float* __restrict__ cost, int* __restrict__ argk) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Na * G) return;
   int a = i % Na, g = i / Na;
   float best = 0.f;
   int bk = 0;
   for (int k = 0; k < Kp; ++k) {
-    float c = (float)(sums[((size_t)a * Kp + k) * G + g] / (double)n_el);
+    float c = (float)(sums[((size_t)a * Kp + k) * G + g] * inv_n);
+    if (post == 1) c = -expf(-c);
     if (k == 0 || c < best) { best = c; bk = k; }   // ties -> lowest k, like torch.min
   }
   cost[(size_t)g * Na + a] = best;
@@ -216,22 +241,33 @@ extern "C" int op3_adam_clip(long long n, float* params, const float* grads, flo
   return OP3_OK;
 }
 
-extern "C" int op3_mpc_cost(int Na, int Kp, int G, int D, const float* pred, const float* goal, float* cost, int* argk,
-                            void* stream) {
-  OP3_REQUIRE(Na > 0 && Kp > 0 && G > 0 && G <= 16 && D > 0 && pred && goal && cost, "op3_mpc_cost: bad argument (G<=16)");
+extern "C" int op3_mpc_cost_ex(int Na, int Kp, int G, int n_el, int compare, int post, const float* pred, const float* goal,
+                               float* cost, int* argk, void* stream) {
+  OP3_REQUIRE(Na > 0 && Kp > 0 && G > 0 && G <= 16 && n_el > 0 && pred && goal && cost, "op3_mpc_cost: bad argument (G<=16)");
+  OP3_REQUIRE((compare == 0 || compare == 1) && (post == 0 || post == 1), "op3_mpc_cost: compare %d / post %d not in {0,1}", compare, post);
   cudaStream_t st = (cudaStream_t)stream;
-  const int n_el = 3 * D * D;
   double* sums = nullptr;
   OP3_CHECK(cudaMallocAsync((void**)&sums, (size_t)Na * Kp * G * sizeof(double), st));  // stream-ordered temp, freed below
-  if (G <= 4) mpc_sqerr_kernel<4><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
-  else mpc_sqerr_kernel<16><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
+  if (compare == 0) {
+    if (G <= 4) mpc_sqerr_kernel<4, 0><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
+    else mpc_sqerr_kernel<16, 0><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
+  } else {
+    if (G <= 4) mpc_sqerr_kernel<4, 1><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
+    else mpc_sqerr_kernel<16, 1><<<Na * Kp, 256, 0, st>>>(G, n_el, pred, goal, sums);
+  }
   OP3_COUNT_LAUNCH();
-  mpc_min_kernel<<<ceil_div(Na * G, 256), 256, 0, st>>>(Na, Kp, G, n_el, sums, cost, argk);
+  mpc_min_kernel<<<ceil_div(Na * G, 256), 256, 0, st>>>(Na, Kp, G, compare == 0 ? 1.0 / (double)n_el : 1.0, post, sums, cost, argk);
   OP3_COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(sums, st);
   OP3_CHECK(e);
   return OP3_OK;
+}
+
+extern "C" int op3_mpc_cost(int Na, int Kp, int G, int D, const float* pred, const float* goal, float* cost, int* argk,
+                            void* stream) {
+  OP3_REQUIRE(D > 0, "op3_mpc_cost: bad argument");
+  return op3_mpc_cost_ex(Na, Kp, G, 3 * D * D, 0, 0, pred, goal, cost, argk, stream);
 }
 
 extern "C" int op3_sub_images(long long n_slots, int D, const float* colors, const float* mask, float* out, void* stream) {

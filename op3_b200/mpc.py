@@ -1,6 +1,7 @@
 """MPC glue: `Cost` mirrors the ranking class of exps/stack_exps/mpc_stack.py:27-228 (== exps/pickplace_exps/
-mpc_pickplace.py:36-236) for compare_func='mse', post_process='raw'; the (Na,K) x G squared-error reduction and the
-min over K run in op3_mpc_cost with a fixed reduction order, the final sort stays on the host like the reference
+mpc_pickplace.py:36-236): core_type subimage / final_recon / latent, compare_func mse / psuedo_intersect, post_process raw /
+negative_exp, aggregate sum / min; the (Na,K) x G distance reduction and the min over K run in op3_mpc_cost_ex with a fixed
+reduction order, the final sort stays on the host like the reference
 (it returns numpy arrays).  `shard_candidates` / `gather_costs` split CEM candidates across ranks."""
 import ctypes as C
 
@@ -12,27 +13,34 @@ from op3_b200._lib import check, ptr
 
 
 class Cost:
+    COMPARE = {"mse": 0, "psuedo_intersect": 1}
+    POST = {"raw": 0, "negative_exp": 1}
+
     def __init__(self, logging_directory, core_type="subimage", compare_func="mse", post_process="raw", aggregate="sum"):
         if core_type not in ["subimage", "final_recon", "latent"]:
             raise ValueError("Invalid value of core_type: {}".format(core_type))
-        if core_type == "latent" or compare_func != "mse" or post_process != "raw":
-            raise NotImplementedError("only core_type in {subimage, final_recon} with mse/raw is built")
-        if aggregate not in ("sum", "min"):
-            raise KeyError(aggregate)
+        if compare_func not in self.COMPARE or post_process not in self.POST or aggregate not in ("sum", "min"):
+            raise KeyError((compare_func, post_process, aggregate))
+        if core_type == "latent" and compare_func != "mse":
+            raise KeyError(compare_func)                       # compare_latents knows 'mse' only (mpc_stack.py:73-77)
         self.logging_directory, self.core_type = logging_directory, core_type
         self.compare_func, self.post_process, self.aggregate = compare_func, post_process, aggregate
 
-    def pair_costs(self, goal_latents_recon, pred_latents_recon):
-        """(G,3,D,D), (Na,K,3,D,D) -> costs (G,Na) = min_k mse, latent_idx (G,Na)."""
+    def pair_costs(self, goal_rows, pred_rows):
+        """goal (G, ...), pred (Na,K, ...) with equal trailing shapes -- sub-images (3,D,D) or latents (R,) --
+        -> costs (G,Na) = min_k post(compare(goal_g, pred_a,k)), latent_idx (G,Na)  (mpc_stack.py:60-100)."""
         lib = _lib.load()
-        goal = goal_latents_recon.detach().contiguous().float()
-        pred = pred_latents_recon.detach().contiguous().float()
-        Na, Kp, _, D, _ = pred.shape
-        G = goal.shape[0]
+        goal = goal_rows.detach().contiguous().float()
+        pred = pred_rows.detach().contiguous().float()
+        Na, Kp = pred.shape[:2]
+        G, n_el = goal.shape[0], goal[0].numel()
+        if pred[0, 0].numel() != n_el:
+            raise ValueError("goal rows %s do not match prediction rows %s" % (tuple(goal.shape[1:]), tuple(pred.shape[2:])))
         cost = torch.empty(G, Na, device=pred.device)
         argk = torch.empty(G, Na, device=pred.device, dtype=torch.int32)
         st = torch.cuda.current_stream(pred.device).cuda_stream
-        check(lib.op3_mpc_cost(Na, Kp, G, D, ptr(pred), ptr(goal), ptr(cost), ptr(argk), st), "op3_mpc_cost")
+        check(lib.op3_mpc_cost_ex(Na, Kp, G, n_el, self.COMPARE[self.compare_func], self.POST[self.post_process], ptr(pred),
+                                  ptr(goal), ptr(cost), ptr(argk), st), "op3_mpc_cost")
         return cost, argk.long()
 
     def get_action_rankings(self, goal_latents, goal_latents_recon, goal_image, pred_latents, pred_latents_recon,
@@ -40,7 +48,10 @@ class Cost:
         if self.core_type == "final_recon":                   # pretend K = 1 (mpc_stack.py:46-48)
             goal_latents_recon = goal_image
             pred_latents_recon = pred_image.unsqueeze(1)
-        costs, latent_idxs = self.pair_costs(goal_latents_recon, pred_latents_recon)
+        if self.core_type == "latent":                        # one cost row per goal latent RECON (mpc_stack.py:116-122)
+            costs, latent_idxs = self.pair_costs(goal_latents[:goal_latents_recon.shape[0]], pred_latents)
+        else:
+            costs, latent_idxs = self.pair_costs(goal_latents_recon, pred_latents_recon)
         if self.aggregate == "sum":
             sorted_costs, order = costs.sum(0).sort()
             return sorted_costs.cpu().numpy(), order.cpu().numpy(), np.zeros(len(sorted_costs))

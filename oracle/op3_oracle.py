@@ -509,16 +509,33 @@ def clip_adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=3e-4, max_norm=5
 # ----------------------------------------------------------------------------------------------
 # MPC cost (exps/stack_exps/mpc_stack.py:41-228 == exps/pickplace_exps/mpc_pickplace.py:50-236)
 # ----------------------------------------------------------------------------------------------
-def mpc_cost(goal_recon, goal_image, pred_sub_images, pred_final_recon, core_type="final_recon", aggregate="sum"):
-    """Restates Cost.get_action_rankings with compare_func='mse', post_process='raw'.
-    goal_recon (G,3,D,D), goal_image (1,3,D,D), pred_sub_images (Na,K,3,D,D), pred_final_recon (Na,3,D,D).
+def mpc_cost(goal_recon, goal_image, pred_sub_images, pred_final_recon, core_type="final_recon", aggregate="sum",
+             compare_func="mse", post_process="raw", goal_latents=None, pred_latents=None):
+    """Restates Cost.get_action_rankings (exps/stack_exps/mpc_stack.py:41-228).
+    goal_recon (G,3,D,D), goal_image (1,3,D,D), pred_sub_images (Na,K,3,D,D), pred_final_recon (Na,3,D,D); for
+    core_type 'latent' also goal_latents (G,R), pred_latents (Na,K,R).
     Returns (sorted_costs, action_index_order, goal_latent_idx) as torch tensors."""
     if core_type == "final_recon":                                  # mpc_stack.py:46-48
         goal_recon = goal_image
         pred_sub_images = pred_final_recon.unsqueeze(1)
     costs = []
     for g in range(goal_recon.shape[0]):
-        d = ((goal_recon[g].view(1, 1, *goal_recon.shape[1:]) - pred_sub_images) ** 2).mean((-1, -2, -3))  # (Na,K)
+        if core_type == "latent":                                   # compare_latents :73-77, mse over the last axis :103-107
+            d = ((goal_latents[g].view(1, 1, -1) - pred_latents) ** 2).mean(-1)
+        elif compare_func == "mse":                                 # image_mse :109-127
+            d = ((goal_recon[g].view(1, 1, *goal_recon.shape[1:]) - pred_sub_images) ** 2).mean((-1, -2, -3))  # (Na,K)
+        elif compare_func == "psuedo_intersect":                    # :84-92
+            gr = goal_recon[g]
+            m1, m2 = (gr > 0.01).float(), (pred_sub_images > 0.01).float()
+            union = m1.sum((-3, -2, -1)) + m2.sum((-3, -2, -1))
+            ti = (m1 * m2 * ((gr - pred_sub_images) ** 2 < 0.08).float()).sum((-3, -2, -1))
+            d = 1 - ti / union
+        else:
+            raise KeyError(compare_func)
+        if post_process == "negative_exp":                          # :94-100
+            d = -torch.exp(-d)
+        elif post_process != "raw":
+            raise KeyError(post_process)
         costs.append(d.min(-1)[0])
     costs = torch.stack(costs)                                      # (G,Na)
     if aggregate == "sum":

@@ -200,6 +200,11 @@ def module_case():
     print("modules ok")
 
 
+COST_OPTION_CASES = [("latent", "mse", "raw", "sum"), ("latent", "mse", "raw", "min"), ("subimage", "psuedo_intersect", "raw", "sum"),
+                     ("subimage", "psuedo_intersect", "raw", "min"), ("subimage", "mse", "negative_exp", "sum"),
+                     ("final_recon", "mse", "negative_exp", "sum"), ("latent", "mse", "negative_exp", "min")]
+
+
 def mpc_case():
     """pickplace-style MPC rollout: B=1 state from [0,0,1,0] on real-shaped synthetic frames, then Na candidate
     actions through schedule [1] in chunks of 10 (op3_model.py:569-642) and Cost ranking (mpc_pickplace.py:50)."""
@@ -229,6 +234,14 @@ def mpc_case():
         res["cost/%s_%s/sorted" % (core, agg)] = np.asarray(sc)
         res["cost/%s_%s/order" % (core, agg)] = np.asarray(order)
         res["cost/%s_%s/gidx" % (core, agg)] = np.asarray(gidx)
+    # the remaining Cost options (mpc_stack.py:60-100): latent distances, 'psuedo_intersect', 'negative_exp'
+    for core, cmp_, post, agg in COST_OPTION_CASES:
+        cost = ref_mpc.Cost(None, core_type=core, compare_func=cmp_, post_process=post, aggregate=agg)
+        sc, order, gidx = cost.get_action_rankings(info["state"]["post"]["samples"][0], info["sub_images"][0],
+                                                   goal_image, pred["state"]["post"]["samples"], pred["sub_images"],
+                                                   pred["final_recon"], plot_actions=0)
+        key = "costx/%s_%s_%s_%s/" % (core, cmp_, post, agg)
+        res[key + "sorted"], res[key + "order"], res[key + "gidx"] = np.asarray(sc), np.asarray(order), np.asarray(gidx)
     np.savez_compressed(os.path.join(HERE, "mpc.npz"), **res)
     print("mpc ok", res["cost/final_recon_sum/order"][:5])
 
@@ -401,7 +414,7 @@ if __name__ == "__main__":
     if only:                       # e.g. `make_golden.py mpc_stack pretrained`: regenerate selected (slow) cases only
         for name in only:
             {"mpc_stack": mpc_stack_case, "pretrained": pretrained_case, "mpc_large": mpc_large_case,
-             "mpc_stack_small": lambda: mpc_stack_case(Na=40), "activations": activation_case, "noshare": noshare_cases}[name]()
+             "mpc_stack_small": lambda: mpc_stack_case(Na=40), "activations": activation_case, "noshare": noshare_cases, "mpc": mpc_case}[name]()
         sys.exit(0)
     schedule_case()
     train_case("stack_small", stack_variant, K=3, action_dim=0, B=2, T=2, schedule=[0, 0, 1], full_masks=True)

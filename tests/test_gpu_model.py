@@ -139,6 +139,15 @@ def test_mpc_rollout_and_ranking_match_golden():
         assert np.abs(np.asarray(sc) - g[key + "sorted"]).max() <= 2e-6
         if agg == "min":
             assert np.array_equal(np.asarray(gidx), g[key + "gidx"])
+    # the remaining Cost options (mpc_stack.py:60-100) through op3_mpc_cost_ex
+    from helpers import check_ranking, COST_OPTION_CASES
+    for core, cmp_, post, agg in COST_OPTION_CASES:
+        cost = Cost(None, core_type=core, compare_func=cmp_, post_process=post, aggregate=agg)
+        sc, order, gidx = cost.get_action_rankings(info["state"]["post"]["samples"][0], info["sub_images"][0], goal_image,
+                                                   pred["state"]["post"]["samples"], pred["sub_images"], pred["final_recon"],
+                                                   plot_actions=0)
+        key = "costx/%s_%s_%s_%s/" % (core, cmp_, post, agg)
+        check_ranking(sc, order, g[key + "sorted"], g[key + "order"], exact=cmp_ == "mse", what=key)
 
 
 def test_get_loss_standalone_matches_oracle():

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import op3_oracle as orc
-from helpers import load_golden, check_summary
+from helpers import load_golden, check_summary, check_ranking, COST_OPTION_CASES
 
 CASES = [("stack_small", 0), ("pickplace_small", 4), ("stack_c1", 0), ("pickplace_nextstep", 4)]
 
@@ -103,3 +103,9 @@ def test_mpc_rollout_and_ranking_match_reference():
         assert np.abs(sc.numpy() - g[key + "sorted"]).max() <= 1e-6
         if agg == "min":
             assert np.array_equal(gidx.numpy(), g[key + "gidx"])
+    # the remaining Cost options (mpc_stack.py:60-100): latent distances, 'psuedo_intersect', 'negative_exp'
+    for core, cmp_, post, agg in COST_OPTION_CASES:
+        sc, order, gidx = orc.mpc_cost(goal_sub, goal_image, sub, pred["final_recon"], core, agg, cmp_, post,
+                                       goal_latents=st["post"]["samples"][0].detach(), pred_latents=pred["state"]["post"]["samples"])
+        key = "costx/%s_%s_%s_%s/" % (core, cmp_, post, agg)
+        check_ranking(sc.numpy(), order.numpy(), g[key + "sorted"], g[key + "order"], exact=cmp_ == "mse", what=key)
