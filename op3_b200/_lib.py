@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libop3_b200.so")
+LIB_PATH = os.environ.get("OP3_B200_LIB") or os.path.join(_HERE, "libop3_b200.so")   # env override: experiment builds (tools/)
 
 c_fp = C.c_void_p  # device pointers are passed as integers
 

@@ -336,8 +336,14 @@ mix_emit_kernel(Op3MixtureIO io, const float* __restrict__ g0, const float* __re
 // the gradient seed.  The loss scalars are reduced by rank 0 of each cluster; the last sample (self-resetting counter
 // `sync`, zero before the first call, left zero by every call) sums the samples in index order.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int MIXF_CL = 8;
-constexpr int MIXF_THREADS = 128;
+#ifndef OP3_MIXF_CL
+#define OP3_MIXF_CL 8
+#endif
+#ifndef OP3_MIXF_THREADS
+#define OP3_MIXF_THREADS 128
+#endif
+constexpr int MIXF_CL = OP3_MIXF_CL;
+constexpr int MIXF_THREADS = OP3_MIXF_THREADS;
 constexpr int MIXF_WARPS = MIXF_THREADS / 32;
 constexpr int MIXF_NQMAX = 6 * 16 + 4;
 
