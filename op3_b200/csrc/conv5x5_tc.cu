@@ -357,7 +357,14 @@ constexpr int TQ_W_SLAB = 2 * TQ_NQ * 16;           // one (K group, ky, hi/lo) 
 constexpr int TQ_W_BYTES = 2 * 5 * 2 * TQ_W_SLAB;
 constexpr int TQ_XCH = 4 * 2 * 10 * 16;             // floats per exchange buffer: [quad][half][(kx, lane < kx)][16]
 constexpr int TQ_SMEM = TQ_A_BYTES + TQ_W_BYTES + 2 * TQ_XCH * 4 + 8 * 128 * 4;          // single-CTA form, two epilogue groups
-constexpr int TQ_PAIR_NEG = 2;                      // epilogue groups of the pair form (3 fits its shared memory but not the issue slots, see below)
+#ifndef OP3_TQ_LEAN
+#define OP3_TQ_LEAN 0
+#endif
+constexpr bool TQ_LEAN = OP3_TQ_LEAN != 0;          // half-wise epilogue (see the kernel)
+#ifndef OP3_TQ_PAIR_NEG
+#define OP3_TQ_PAIR_NEG 2
+#endif
+constexpr int TQ_PAIR_NEG = OP3_TQ_PAIR_NEG;                      // epilogue groups of the pair form (3 fits its shared memory but not the issue slots, see below)
 constexpr int TQ_SMEM_PAIR = TQ_A_BYTES + TQ_W_BYTES / 2 + TQ_PAIR_NEG * TQ_XCH * 4 + 4 * TQ_PAIR_NEG * 128 * 4;
 
 // PAIR: the kernel runs as clusters of two CTAs driving ONE tcgen05.mma.cta_group::2 stream (M = 256): the two CTAs work on
@@ -371,12 +378,20 @@ constexpr int TQ_SMEM_PAIR = TQ_A_BYTES + TQ_W_BYTES / 2 + TQ_PAIR_NEG * TQ_XCH 
 // groups the leader issues at 62 cycles per MMA (85 single-CTA) but waits 31 % of its loop for accumulators and 19 % for
 // operands -- 0.647 vs 0.615 ms; with three groups (640 threads, 96 registers) the accumulator wait disappears and the six
 // loader warps starve (64 % operand wait, 0.93 ms): loaders + epilogue are bound by instruction issue, not by the tensor pipe.
+#ifndef OP3_TQ_NLOAD
+#define OP3_TQ_NLOAD 6
+#endif
+#ifndef OP3_TQ_IDLE
+#define OP3_TQ_IDLE 1
+#endif
 template <int NEG> struct TqRoles {
-  static constexpr int EPI = 4 * NEG, MMA = EPI, IDLE = MMA + 4, LOAD0 = MMA + 1, NLOAD = 6;   // IDLE: the loader-range warp on the issuer's scheduler
-  static constexpr int THREADS = (LOAD0 + NLOAD + 1) * 32;
+  static constexpr bool HAS_IDLE = OP3_TQ_IDLE != 0;
+  static constexpr int EPI = 4 * NEG, MMA = EPI, IDLE = HAS_IDLE ? MMA + 4 : 1000, LOAD0 = MMA + 1, NLOAD = OP3_TQ_NLOAD;   // IDLE: the loader-range warp on the issuer's scheduler
+  static constexpr int NROUND = (TQ_TS * 4 + NLOAD * 32 - 1) / (NLOAD * 32);                  // (pixel, k-chunk) tasks per loader thread
+  static constexpr int THREADS = (LOAD0 + NLOAD + (HAS_IDLE ? 1 : 0)) * 32;
   static constexpr int SMEM_X = NEG * TQ_XCH * 4 + EPI * 128 * 4;                              // exchange buffers + per-warp fix-up rows
 };
-template <bool PAIR, int NEG>
+template <bool PAIR, int NEG, bool LEAN>
 __global__ void __launch_bounds__(TqRoles<NEG>::THREADS, 1)
 conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
                    float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
@@ -448,10 +463,11 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     // is converted and stored (one exposed global latency per item, not per chunk); pixel coordinates advance incrementally.
     const int lt = tid - LOAD_WARP0 * 32 - (warp > TQ_IDLE_WARP ? 32 : 0);
     const int ntask = TQ_TS * 2 * ngroups;                 // task = (pixel, k-chunk of 8 channels)
-    int ti[3], tk[3];
-    bool tact[3];
+    constexpr int NR = Roles::NROUND;
+    int ti[NR], tk[NR];
+    bool tact[NR];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
+    for (int u = 0; u < NR; ++u) {
       const int e = lt + u * TQ_LOAD_THREADS;
       tact[u] = e < ntask;
       tk[u] = tact[u] ? e / TQ_TS : 0;
@@ -464,21 +480,21 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
       const int n = it / nstrips, x0 = (it - n * nstrips) * W;
       const int T = min(tiles_img - ta, g1 - g);
       const float sc = __uint_as_float(f16_scale_bits(maxbits[n]));
-      const float4* s0[3];
-      const float4* s1[3];
-      int iy[3], ix[3];
+      const float4* s0[NR];
+      const float4* s1[NR];
+      int iy[NR], ix[NR];
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
+      for (int u = 0; u < NR; ++u) {
         s0[u] = (tact[u] && 2 * tk[u] < in.total_chunks) ? tc_src_chunk_ptr(in, 2 * tk[u], n, D) : nullptr;
         s1[u] = (tact[u] && 2 * tk[u] + 1 < in.total_chunks) ? tc_src_chunk_ptr(in, 2 * tk[u] + 1, n, D) : nullptr;
         const int q = TQ_TS * ta + ti[u];
         const int r = q / P;
         iy[u] = r - 2; ix[u] = q - r * P - 2;
       }
-      float4 v[3][2], vn[3][2];
+      float4 v[NR][2], vn[NR][2];
       auto load_chunk = [&](float4 (*dst)[2]) {            // loads the chunk at the current coordinates, then advances them
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < NR; ++u) {
           const bool ok = (unsigned)iy[u] < (unsigned)D && (unsigned)(ix[u] + x0) < (unsigned)D;
           const size_t off = (size_t)iy[u] * D + ix[u] + x0;
           dst[u][0] = (ok && s0[u]) ? __ldg(s0[u] + off) : zero4;
@@ -493,7 +509,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         if (jc + 1 < T + 3) load_chunk(vn);
         if (c >= TQ_NSLOT) mbar_wait_warp(&empty_bar[slot], ((c / TQ_NSLOT) - 1) & 1);
 #pragma unroll
-        for (int u = 0; u < 3; ++u)
+        for (int u = 0; u < NR; ++u)
           if (tact[u]) {
             uint4 hi, lo;
             f16_split2(v[u][0].x * sc, v[u][0].y * sc, hi.x, lo.x);
@@ -510,7 +526,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         if (PAIR) mbar_arrive_cluster(&full_bar[slot], 0);
         else mbar_arrive(&full_bar[slot]);
 #pragma unroll
-        for (int u = 0; u < 3; ++u) { v[u][0] = vn[u][0]; v[u][1] = vn[u][1]; }
+        for (int u = 0; u < NR; ++u) { v[u][0] = vn[u][0]; v[u][1] = vn[u][1]; }
       }
       g += T;
     }
@@ -660,6 +676,107 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         // the tensor core is busy; one wait per load made the epilogue the bottleneck).  out[p] = sum_kx D_kx[p + kx]: the
         // shift is a warp shuffle; the rows that cross a quadrant boundary (lane l < kx of D_kx, read by lane 32 - kx + l of
         // the previous quadrant) travel through shared memory and are added after the group barrier.
+        if constexpr (LEAN) {
+          // Half-wise form: 16 output channels at a time run through the WHOLE pipeline (TMEM -> tap shift -> boundary exchange
+          // -> bias / ELU -> stores) with the 16-column units double-buffered against the shuffles: 48 live accumulator
+          // registers instead of 96, which is what lets three epilogue groups share the register file with eight loader warps.
+          // Same arithmetic in the same order as the form below (bit-identical results).  The two halves use the two halves of
+          // the exchange buffer, so one group barrier per half is enough: a region is rewritten only after every warp of the
+          // group has passed the other half's barrier, i.e. after its last read.
+          float* fx = fixb + warp * 128;                     // [4 target lanes][16 columns]
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float acc[16], va[16], vb[16];
+            float4* dst4 = reinterpret_cast<float4*>(xb + ((quad * 2 + half) * 10) * 16);
+            tmem_ld16(trow + 16 * half, acc);
+            tmem_ld16(trow + 32 + 16 * half, va);
+            tmem_ld_wait();
+            tmem_ld16(trow + 64 + 16 * half, vb);
+            if (lane < 1) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst4[(0 + lane) * 4 + i] = make_float4(va[4 * i], va[4 * i + 1], va[4 * i + 2], va[4 * i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(__shfl_down_sync(0xffffffffu, va[i], 1), m1, acc[i]);
+            tmem_ld_wait();
+            tmem_ld16(trow + 96 + 16 * half, va);
+            if (lane < 2) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst4[(1 + lane) * 4 + i] = make_float4(vb[4 * i], vb[4 * i + 1], vb[4 * i + 2], vb[4 * i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(__shfl_down_sync(0xffffffffu, vb[i], 2), m2, acc[i]);
+            tmem_ld_wait();
+            tmem_ld16(trow + 128 + 16 * half, vb);
+            if (lane < 3) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst4[(3 + lane) * 4 + i] = make_float4(va[4 * i], va[4 * i + 1], va[4 * i + 2], va[4 * i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(__shfl_down_sync(0xffffffffu, va[i], 3), m3, acc[i]);
+            tmem_ld_wait();
+            if (lane < 4) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst4[(6 + lane) * 4 + i] = make_float4(vb[4 * i], vb[4 * i + 1], vb[4 * i + 2], vb[4 * i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(__shfl_down_sync(0xffffffffu, vb[i], 4), m4, acc[i]);
+            if (half == 1) {
+              tc_fence_before();
+              if (PAIR) mbar_arrive_cluster(&acc_empty[slot], 0);    // every TMEM read of this tile is done
+              else mbar_arrive(&acc_empty[slot]);
+            }
+            float4 rh[4];                                    // dgrad: activation outputs whose ELU' multiplies this half
+            if (epi == EPI_MUL_ELUGRAD) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                rh[i] = (valid && 4 * half + i < out_chunks) ? __ldg(&ref[obase + (4 * half + i) * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+            asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory");      // the four warps of this group
+            if (quad < 3) {
+              // rows whose shifted sources live in the next quadrant (lanes 28..31): lane = (target pair, column) sums the kx
+              // terms two targets are missing, the targets then pick up their 16 sums with four LDS.128
+              const float* src = xb + (((quad + 1) * 2 + half) * 10) * 16 + (lane & 15);
+#pragma unroll
+              for (int t2 = 0; t2 < 2; ++t2) {
+                const int tt = 2 * (lane >> 4) + t2;         // target lane 28 + tt misses kx = 4 - tt .. 4 (source lane tt + kx - 4)
+                float sl = 0.f;
+#pragma unroll
+                for (int kx = 1; kx <= 4; ++kx)
+                  if (kx >= 4 - tt) sl += src[((kx * (kx - 1)) / 2 + (tt + kx - 4)) * 16];
+                fx[tt * 16 + (lane & 15)] = sl;
+              }
+              __syncwarp();
+              if (lane >= 28) {
+                const float4* f4 = reinterpret_cast<const float4*>(fx + (lane - 28) * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 t = f4[i];
+                  acc[4 * i] += t.x; acc[4 * i + 1] += t.y; acc[4 * i + 2] += t.z; acc[4 * i + 3] += t.w;
+                }
+              }
+              __syncwarp();
+            }
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int c4 = 4 * half + i;
+                if (c4 >= out_chunks) continue;
+                const float4 bb = *reinterpret_cast<const float4*>(&s_bias[16 * half + 4 * i]);
+                float4 o = make_float4(fmaf(acc[4 * i], inv_scale, bb.x), fmaf(acc[4 * i + 1], inv_scale, bb.y),
+                                       fmaf(acc[4 * i + 2], inv_scale, bb.z), fmaf(acc[4 * i + 3], inv_scale, bb.w));
+                if (epi == EPI_ELU) {
+                  o.x = elu_tc(o.x); o.y = elu_tc(o.y); o.z = elu_tc(o.z); o.w = elu_tc(o.w);
+                } else if (epi == EPI_MUL_ELUGRAD) {
+                  o.x *= elu_grad_from_out(rh[i].x); o.y *= elu_grad_from_out(rh[i].y);
+                  o.z *= elu_grad_from_out(rh[i].z); o.w *= elu_grad_from_out(rh[i].w);
+                }
+                out[obase + c4 * plane] = o;
+                if (want_max) omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+              }
+            }
+          }
+        } else {
         float acc[2][16];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -776,6 +893,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
           atomicAdd(&g_tcq_epi[4], te4 - te3); atomicAdd(&g_tcq_epi[5], te5 - te4); atomicAdd(&g_tcq_epi[6], clock64() - te5);
         }
 #endif
+        }   // !LEAN
       }
       if (in.out_maxbits != nullptr) {                      // magnitudes of the written tensor, for its consumer's operand scale
 #pragma unroll
@@ -858,8 +976,8 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
                const uint32_t* maxbits, const float* wscale) {
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
-    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<true, TQ_PAIR_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM_PAIR));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<false, 2, TQ_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM_PAIR));
   }
   const int g_num_sms = device_sm_count();
   int W = 0, nstrips = 0;
@@ -886,20 +1004,20 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
     if (dev >= 0 && dev < OP3_MAX_DEVICES && max_pairs[dev] == 0) {
       cfg.gridDim = dim3(2 * (g_num_sms / 2));
       int nc = 0;
-      OP3_CHECK(cudaOccupancyMaxActiveClusters(&nc, conv5x5_tcq_kernel<true, TQ_PAIR_NEG>, &cfg));
+      OP3_CHECK(cudaOccupancyMaxActiveClusters(&nc, conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN>, &cfg));
       max_pairs[dev] = nc > 0 ? nc : 1;
     }
     int pairs = (dev >= 0 && dev < OP3_MAX_DEVICES) ? max_pairs[dev] : g_num_sms / 2;
     if (total < pairs) pairs = (int)total;
     cfg.gridDim = dim3(2 * pairs);
-    OP3_CHECK(cudaLaunchKernelEx(&cfg, conv5x5_tcq_kernel<true, TQ_PAIR_NEG>, in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
+    OP3_CHECK(cudaLaunchKernelEx(&cfg, conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN>, in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
                                  out_chunks, epi, ref, maxbits, wscale, W, nstrips));
     OP3_COUNT_LAUNCH();
     return OP3_OK;
   }
   const long long total = items * tiles_img;
   const int grid = total < g_num_sms ? (int)total : g_num_sms;
-  conv5x5_tcq_kernel<false, 2><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
+  conv5x5_tcq_kernel<false, 2, TQ_LEAN><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
                                                                out_chunks, epi, ref, maxbits, wscale, W, nstrips);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
