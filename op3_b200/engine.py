@@ -608,10 +608,25 @@ class Engine:
         dyn_scratch = None
         d_dec = torch.empty(N, DD, 4, **f32)
 
+        # gradient accumulators of every state of the schedule: ONE zero-filled slab (a fill kernel per tensor was 50 launches)
+        per_state = N * (R + 2 * Rs + 2 * LSTM)
+        n_states = len(tape.steps) + 1
+        slab = torch.zeros(n_states, per_state, **f32)
+        slab_next = [0]
+
         def grads_of(s):
             if s.dz is None:
-                s.dz, s.dl1, s.dl2 = torch.zeros(N, R, **f32), torch.zeros(N, Rs, **f32), torch.zeros(N, Rs, **f32)
-                s.dh, s.dc = torch.zeros(N, LSTM, **f32), torch.zeros(N, LSTM, **f32)
+                if slab_next[0] < n_states:
+                    row = slab[slab_next[0]]
+                    slab_next[0] += 1
+                else:                                        # a prior owner outside the schedule's own states
+                    row = torch.zeros(per_state, **f32)
+                o = 0
+                s.dz = row[o:o + N * R].view(N, R); o += N * R
+                s.dl1 = row[o:o + N * Rs].view(N, Rs); o += N * Rs
+                s.dl2 = row[o:o + N * Rs].view(N, Rs); o += N * Rs
+                s.dh = row[o:o + N * LSTM].view(N, LSTM); o += N * LSTM
+                s.dc = row[o:o + N * LSTM].view(N, LSTM)
             return s
 
         # decodes grouped by the state they decode
