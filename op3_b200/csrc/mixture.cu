@@ -364,6 +364,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+#ifdef OP3_MIX_TRACE
+__device__ unsigned long long g_mix_trace[16];      // per phase: summed cycles of thread 0 of every CTA; [15] = CTAs
+#define MIXT(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(&g_mix_trace[i], (unsigned long long)(_t - mt_prev)); mt_prev = _t; } } while (0)
+#else
+#define MIXT(i) do { } while (0)
+#endif
 // EXACT: K == KMAX, so every `k < K` slot predicate folds away at compile time (~10 % of the instructions at K = 4)
 template <int KMAX, bool EXACT>
 __global__ void __cluster_dims__(MIXF_CL, 1, 1) __launch_bounds__(MIXF_THREADS)
@@ -373,6 +379,10 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
                  const float* __restrict__ b2, const float* __restrict__ b3, int B, int K_in, int D, int emit, int Rs,
                  float beta, unsigned* __restrict__ sync) {
   const int K = EXACT ? KMAX : K_in;
+#ifdef OP3_MIX_TRACE
+  long long mt_prev = clock64();
+  if (threadIdx.x == 0) atomicAdd(&g_mix_trace[15], 1ull);
+#endif
   extern __shared__ __align__(128) unsigned char mixf_raw[];
   MixfSmem& sm = *reinterpret_cast<MixfSmem*>(mixf_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -391,31 +401,27 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
   if (tid == 0) {
     for (int it = 0; it < npix; ++it) mbar_init(reinterpret_cast<uint64_t*>(&sm.mbar[it]), 1);
     fence_mbar_init();
-    // one sub-chunk of MIXF_THREADS pixels per pass-1 iteration: compute starts when the first 1/npix of the bytes landed
+  }
+  __syncthreads();                                             // mbarriers initialised before anyone arms / polls them
+  // One sub-chunk of MIXF_THREADS pixels per pass-1 iteration (compute starts when the first 1/npix of the bytes landed).  The
+  // 3 + K bulk copies of every sub-chunk are issued by DIFFERENT lanes of warp 0 (one thread issuing all 28 of them took
+  // 4800 cycles before pass 1 could start), the byte counts are armed by warp 1.
+  if (warp == 1 && lane < npix) {
     const uint32_t sub = (uint32_t)MIXF_THREADS * (16u * K + 12u);
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
+                 :: "r"(smem_u32(&sm.mbar[lane])), "r"(sub) : "memory");
+  }
+  if (warp == 0) {
     const float* img = io.image + (size_t)b * io.image_bstride + pix0;
-    for (int it = 0; it < npix; ++it) {
+    const int per = 3 + K;
+    for (int e = lane; e < npix * per; e += 32) {
+      const int it = e / per, c = e - it * per, o = it * MIXF_THREADS;
       unsigned long long* bar = &sm.mbar[it];
-      const int o = it * MIXF_THREADS;
-      asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
-                   :: "r"(smem_u32(bar)), "r"(sub) : "memory");
-      for (int c = 0; c < 3; ++c) bulk_g2s(s_img + c * PX + o, img + (size_t)c * DD + o, MIXF_THREADS * 4, bar);
-      for (int k = 0; k < K; ++k)
-        bulk_g2s(s_dec + (size_t)k * PX + o, io.dec_out + ((size_t)(b * K + k) * DD + pix0 + o) * 4, MIXF_THREADS * 16, bar);
+      if (c < 3) bulk_g2s(s_img + c * PX + o, img + (size_t)c * DD + o, MIXF_THREADS * 4, bar);
+      else bulk_g2s(s_dec + (size_t)(c - 3) * PX + o, io.dec_out + ((size_t)(b * K + (c - 3)) * DD + pix0 + o) * 4, MIXF_THREADS * 16, bar);
     }
   }
-  // KL of this sample (rank 0 only) while the copies are in flight
-  double kl = 0.0;
-  if (rank == 0) {
-    for (int i = tid; i < K * Rs; i += MIXF_THREADS) {
-      size_t o = (size_t)b * K * Rs + i;
-      float sq_ = softplus_std(io.post_l2[o]), spv = softplus_std(io.prior_l2[o]);
-      float dm = io.post_l1[o] - io.prior_l1[o];
-      kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
-    }
-    kl = warp_sum_d(kl);
-  }
-  __syncthreads();                                             // mbarriers initialised before anyone polls them
+  MIXT(0);                                                     // prologue: barrier init, copy issue, KL
 
   // ---------------- pass 1: outputs + statistics
   Pixel<KMAX> px;
@@ -427,6 +433,7 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
   for (int it = 0; it < npix; ++it) {
     const int lp = it * MIXF_THREADS + tid, pix = pix0 + lp;
     mbar_wait(reinterpret_cast<uint64_t*>(&sm.mbar[it]), 0);
+    if (it == 0) MIXT(1);                                      // first staged sub-chunk has landed
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) px.v[k] = s_dec[(size_t)k * PX + lp];
@@ -479,6 +486,7 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
       accSq += q0 * q0 + q1 * q1 + q2 * q2;
     }
   }
+  MIXT(2);                                                     // pass 1
   const double n1 = 32.0 * npix, n3 = 96.0 * npix;
   if (emit) {
 #pragma unroll
@@ -512,18 +520,37 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
     for (int w = 0; w < MIXF_WARPS; ++w) s += sm.red[w][tid];
     sm.part[tid] = s;
   }
-  cluster.sync();                                              // every CTA's partials are visible cluster-wide
+  MIXT(3);                                                     // warp / CTA reduction of the statistics
+  cluster.barrier_arrive();                                    // this CTA's partials are written ...
+  // KL of this sample (rank 0 only), between arrive and wait: the other seven CTAs of the cluster do not wait for it
+  double kl = 0.0;
+  if (rank == 0) {
+    for (int i = tid; i < K * Rs; i += MIXF_THREADS) {
+      size_t o = (size_t)b * K * Rs + i;
+      float sq_ = softplus_std(io.post_l2[o]), spv = softplus_std(io.prior_l2[o]);
+      float dm = io.post_l1[o] - io.prior_l1[o];
+      kl += (double)(logf(spv / sq_) + (sq_ * sq_ + dm * dm) / (2.f * spv * spv) - 0.5f);
+    }
+    kl = warp_sum_d(kl);
+  }
+  cluster.barrier_wait();                                      // ... and every CTA's partials are visible cluster-wide
+  MIXT(4);                                                     // cluster barrier
 
   // ---------------- cluster-wide statistics (fixed rank order), loss scalars
   if (emit && tid < 3 * K + 1) {
     const int q = tid, k = q / 3, g = q % 3;
     const int qi = q == 3 * K ? 6 * K : 6 * k + 2 * g;
-    double s = 0.0, s2 = 0.0;
-#pragma unroll 1
+    // all 2 x MIXF_CL remote reads in flight at once (a distributed-shared-memory load costs ~700 cycles; one rank per loop
+    // iteration put 8 of them back to back on every CTA's critical path), then added in rank order: still deterministic
+    double ps[MIXF_CL], ps2[MIXF_CL];
+#pragma unroll
     for (int r = 0; r < MIXF_CL; ++r) {
       const double* rp = cluster.map_shared_rank(sm.part, r);
-      s += rp[qi]; s2 += rp[qi + 1];
+      ps[r] = rp[qi]; ps2[r] = rp[qi + 1];
     }
+    double s = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < MIXF_CL; ++r) { s += ps[r]; s2 += ps2[r]; }
     const double n = (q != 3 * K && g == 2) ? 3.0 * DD : (double)DD;
     const double mean = s / n;
     double var = (s2 - s * s / n) / (n - 1.0);
@@ -542,11 +569,14 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
       double klv = 0.0, cl = 0.0, sq = 0.0;
 #pragma unroll
       for (int w = 0; w < MIXF_WARPS; ++w) klv += sm.red[w][0];
-#pragma unroll 1
+      double pc[MIXF_CL], pq[MIXF_CL];
+#pragma unroll
       for (int r = 0; r < MIXF_CL; ++r) {
         const double* rp = cluster.map_shared_rank(sm.part, r);
-        cl += rp[6 * K + 2]; sq += rp[6 * K + 3];
+        pc[r] = rp[6 * K + 2]; pq[r] = rp[6 * K + 3];
       }
+#pragma unroll
+      for (int r = 0; r < MIXF_CL; ++r) { cl += pc[r]; sq += pq[r]; }
       double* samp = reinterpret_cast<double*>(io.stats + L.sample);
       samp[b * 3] = cl; samp[b * 3 + 1] = klv; samp[b * 3 + 2] = sq;
       __threadfence();
@@ -564,8 +594,10 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
     }
   }
   cluster.barrier_arrive();                                    // this CTA no longer reads remote shared memory
+  MIXT(5);                                                     // cluster-wide statistics, loss scalars
   if (emit) {
     __syncthreads();                                           // sm.ln
+    MIXT(6);
     // ---------------- pass 2: refinement inputs + gradient seed from the staged pixels
     const float ga0 = __ldg(g0), be0 = __ldg(b0), ga1 = __ldg(g1), be1 = __ldg(b1), ga2 = __ldg(g2), be2 = __ldg(b2);
     const float ga3x = __ldg(g3), ga3y = __ldg(g3 + 1), ga3z = __ldg(g3 + 2);
@@ -605,7 +637,9 @@ mix_fused_kernel(Op3MixtureIO io, const float* __restrict__ mse_image, long long
       reinterpret_cast<float4*>(io.smp)[(size_t)b * DD + pix] = make_float4(x0, x1, x2, (P - lP.x) * lP.y * ga1 + be1);
     }
   }
+  MIXT(7);                                                     // pass 2
   cluster.barrier_wait();                                      // nobody exits while a peer may still read its partials
+  MIXT(8);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -709,6 +743,14 @@ __global__ void __launch_bounds__(384) mix_bwd_reduce_kernel(const double* __res
 }  // namespace op3
 
 using namespace op3;
+
+#ifdef OP3_MIX_TRACE
+extern "C" int op3_debug_mix_trace(unsigned long long* out /*[16] host*/, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_mix_trace, sizeof(unsigned long long) * 16);
+  if (reset) { static unsigned long long z[16]; cudaMemcpyToSymbol(g_mix_trace, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 extern "C" size_t op3_mixture_stats_floats(const Op3Dims* d) {
   if (validate_dims(d) != OP3_OK) return 0;
