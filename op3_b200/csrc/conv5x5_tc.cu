@@ -20,6 +20,9 @@
 //   loaders).  3xTF32 ("parity mode"): a_hi*[w_hi;w_lo] is ONE MMA with N = 2*cout (the halves are summed in the
 //   epilogue), a_lo*w_hi a second one.  1xTF32 ("speed mode") issues a_hi*w_hi only.  Narrow-N MMAs are operand-fetch
 //   bound (~48 cycles for any N <= 64, measured), so the N = 2*cout stacking is free.
+#include <cuda.h>
+#include <cstdlib>
+#include <unordered_map>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(TqRoles<NEG>::THREADS, 1)
 conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
                    float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
                    const float4* __restrict__ ref, const uint32_t* __restrict__ maxbits, const float* __restrict__ wscale,
-                   int W, int nstrips) {
+                   int W, int nstrips, const __grid_constant__ CUtensorMap wmap, int use_tma) {
   // An "item" is one image (nstrips == 1, W == D) or one vertical strip of W output columns of an image (D = 128: two
   // strips of 64, so that 128 + 4 P rows still fit four chunks of the ring).  Whole images use pitch D + 2: the two
   // right-hand pad columns of a row double as the left-hand pad of the next (3 % padding rows instead of 6 %).  Strips carry
@@ -423,7 +426,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
   uint4* w_s = reinterpret_cast<uint4*>(smem_raw + TQ_A_BYTES);
   float* xch = reinterpret_cast<float*>(smem_raw + TQ_A_BYTES + W_BYTES);
   float* fixb = xch + NEG * TQ_XCH;                            // per epilogue warp: [4 target lanes][32] boundary sums
-  __shared__ uint64_t full_bar[TQ_NSLOT], empty_bar[TQ_NSLOT], acc_full[3], acc_empty[3];
+  __shared__ uint64_t full_bar[TQ_NSLOT], empty_bar[TQ_NSLOT], acc_full[3], acc_empty[3], w_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[32];
 
@@ -432,14 +435,17 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     // PAIR: the leader's full / acc_empty barriers collect the arrivals of BOTH CTAs (the peer's own copies stay unused)
     for (int s = 0; s < TQ_NSLOT; ++s) { mbar_init(&full_bar[s], (PAIR ? 2 : 1) * TQ_LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], (PAIR ? 2 : 1) * 128); }
+    mbar_init(&w_bar, 1);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
     if (PAIR) tmem_alloc2<512>(&tmem_base_s);
     else tmem_alloc<512>(&tmem_base_s);
   }
-  {   // resident weights: ordinary slab [K group][tap][k-chunk][64 rows: hi 0..31, lo 32..63] -> [K group][ky][hi/lo][k-chunk][kx*32 + co]
-    // (PAIR: only this CTA's half of the 160 stacked rows, [rank * 80, rank * 80 + 80))
+  if (PAIR || !use_tma) {
+    // resident weights: ordinary slab [K group][tap][k-chunk][64 rows: hi 0..31, lo 32..63] -> [K group][ky][hi/lo][k-chunk][kx*32 + co]
+    // (PAIR: only this CTA's half of the 160 stacked rows, [rank * 80, rank * 80 + 80)).  The single-CTA form fetches them with
+    // TMA tensor copies instead (issued by the MMA warp below).
     const uint4* wsrc = reinterpret_cast<const uint4*>(wt);
     for (int e = tid; e < ngroups * 25 * 2 * 64; e += TC_THREADS) {
       const int row64 = e & 63, kc = (e >> 6) & 1, tap = (e >> 7) % 25, cg = e / (128 * 25);
@@ -538,6 +544,23 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     // instructions (~25 cycles per MMA: the whole gap between the isolated and the in-situ MMA rate).
     if (!PAIR || rank == 0) {
       const bool leader = elect_one();
+      if (!PAIR && use_tma) {
+        // The slab is the contiguous array [K group][ky][kx][j = k-chunk*2 + hi/lo][32 co x 8 ci halves]: one box
+        // {256 halves, 1, 5 kx, 1, 1} per (K group, ky, j) is exactly the 160-row operand slab the MMAs take
+        // (tests/probes/probe_tma_weights.cu).  20 x ngroups cp.async.bulk.tensor copies by one thread replace ~1500
+        // instructions per thread of loads, index arithmetic and stores; loaders and epilogue warps never wait for them.
+        if (leader)
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
+                       :: "r"(smem_u32(&w_bar)), "r"((uint32_t)ngroups * 20u * (uint32_t)(TQ_NQ * 16)) : "memory");
+        for (int e = lane; e < ngroups * 20; e += 32) {        // one copy per lane and round: a single thread needs ~150 cycles per issue
+          const int cg = e / 20, ky = (e - cg * 20) >> 2, jj = e & 3;
+          const uint4* dst = w_s + ((((cg * 5 + ky) * 2 + (jj & 1)) * 2 + (jj >> 1)) * TQ_NQ);
+          asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                       :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(&wmap)), "r"(0), "r"(jj), "r"(0), "r"(ky), "r"(cg),
+                          "r"(smem_u32(&w_bar)) : "memory");
+        }
+        mbar_wait(&w_bar, 0);
+      }
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, TQ_NQ);
       const uint64_t ad = make_smem_desc(smem_u32(a_s), TQ_ROWS, 8);
@@ -971,6 +994,40 @@ bool tq_strips(int D, int* W, int* nstrips) {
   return false;
 }
 
+// Tensor map of a layer's fp16 weight slab for the quint-tap kernel's TMA prologue (see the kernel), cached per slab.
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool tq_weight_tmap(const float* wt, int ngroups, CUtensorMap* out) {
+  static TmapEncodeFn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (getenv("OP3_TCQ_NO_TMA") != nullptr) return false;          // A/B switch: the cooperative re-layout prologue
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<TmapEncodeFn>(fn);
+  }
+  if (encode == nullptr || (reinterpret_cast<uintptr_t>(wt) & 15u) != 0) return false;
+  static std::unordered_map<uint64_t, CUtensorMap> cache;           // key: slab address ^ K groups (host single-threaded like the other caches)
+  const uint64_t key = reinterpret_cast<uint64_t>(wt) ^ ((uint64_t)ngroups << 60);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap m;
+    const cuuint64_t gdim[5] = {256, 4, 5, 5, (cuuint64_t)ngroups};
+    const cuuint64_t gstr[4] = {512, 2048, 10240, 51200};            // bytes, dimensions 1..4
+    const cuuint32_t box[5] = {256, 1, 5, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<float*>(wt), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    it = cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  return true;
+}
+
 int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* wt, const float* bias, int cout_real,
                float4* out, int out_planes, int out_chunk0, int out_chunks, int epi, const float4* ref,
                const uint32_t* maxbits, const float* wscale) {
@@ -1010,15 +1067,18 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
     int pairs = (dev >= 0 && dev < OP3_MAX_DEVICES) ? max_pairs[dev] : g_num_sms / 2;
     if (total < pairs) pairs = (int)total;
     cfg.gridDim = dim3(2 * pairs);
+    CUtensorMap nomap{};
     OP3_CHECK(cudaLaunchKernelEx(&cfg, conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN>, in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
-                                 out_chunks, epi, ref, maxbits, wscale, W, nstrips));
+                                 out_chunks, epi, ref, maxbits, wscale, W, nstrips, nomap, 0));
     OP3_COUNT_LAUNCH();
     return OP3_OK;
   }
   const long long total = items * tiles_img;
   const int grid = total < g_num_sms ? (int)total : g_num_sms;
+  CUtensorMap wmap{};
+  const int use_tma = tq_weight_tmap(wt, (in.total_chunks + 3) / 4, &wmap) ? 1 : 0;
   conv5x5_tcq_kernel<false, 2, TQ_LEAN><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
-                                                               out_chunks, epi, ref, maxbits, wscale, W, nstrips);
+                                                               out_chunks, epi, ref, maxbits, wscale, W, nstrips, wmap, use_tma);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
