@@ -344,6 +344,9 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
 // fp16-split products feeding it) instead of expm1f, whose ~20 instructions per channel made the epilogue -- 32 channels x
 // 124 pixels per tile -- the kernel's bottleneck once the tensor core needed only 2400 cycles per tile.
 __device__ __forceinline__ float elu_tc(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+#ifdef OP3_TC_TRACE
+__device__ int g_tcq_dbg = 0;      // timing-only experiments (results are WRONG when set): 16 = loaders skip loads, conversion and stores
+#endif
 
 #ifndef OP3_TCQ_SMEM_A
 #define OP3_TCQ_TMEM_A 1      /* x_hi staged in TMEM once per kernel row (define OP3_TCQ_SMEM_A for the all-smem form) */
@@ -509,14 +512,19 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
           while (ix[u] >= P - 2) { ix[u] -= P; ++iy[u]; }
         }
       };
-      load_chunk(v);
+#ifdef OP3_TC_TRACE
+      const bool skip = (g_tcq_dbg & 16) != 0;
+#else
+      constexpr bool skip = false;
+#endif
+      if (!skip) load_chunk(v);
       for (int jc = 0; jc < T + 3; ++jc, ++c) {
         const int slot = c % TQ_NSLOT;
-        if (jc + 1 < T + 3) load_chunk(vn);
+        if (jc + 1 < T + 3 && !skip) load_chunk(vn);
         if (c >= TQ_NSLOT) mbar_wait_warp(&empty_bar[slot], ((c / TQ_NSLOT) - 1) & 1);
 #pragma unroll
         for (int u = 0; u < NR; ++u)
-          if (tact[u]) {
+          if (tact[u] && !skip) {
             uint4 hi, lo;
             f16_split2(v[u][0].x * sc, v[u][0].y * sc, hi.x, lo.x);
             f16_split2(v[u][0].z * sc, v[u][0].w * sc, hi.y, lo.y);
@@ -1093,6 +1101,7 @@ bool tc_quint_fits(int D, int total_chunks) {
 }
 
 #ifdef OP3_TC_TRACE
+extern "C" int op3_debug_tcq_flags(int flags) { cudaMemcpyToSymbol(g_tcq_dbg, &flags, sizeof(int)); return 0; }
 extern "C" int op3_debug_tcq_epi(unsigned long long* out /*[8] host*/, int reset) {
   if (out) cudaMemcpyFromSymbol(out, g_tcq_epi, sizeof(unsigned long long) * 8);
   if (reset) { static unsigned long long z[8]; cudaMemcpyToSymbol(g_tcq_epi, z, sizeof(z)); }

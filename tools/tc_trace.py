@@ -35,6 +35,10 @@ def main():
     out = torch.empty(N, 64 * 64, 4, device=dev)
     f = lib.op3_debug_tc_trace
     f.argtypes = [C.c_void_p, C.c_int]
+    if os.environ.get("TCQ_DBG"):
+        fl = lib.op3_debug_tcq_flags
+        fl.argtypes = [C.c_int]
+        fl(int(os.environ["TCQ_DBG"]))
     if os.environ.get("TCQ_PAIR"):
         lib.op3_set_tcq_pair(int(os.environ["TCQ_PAIR"]))
     for _ in range(3):
