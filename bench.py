@@ -532,6 +532,7 @@ def main():
             dist.destroy_process_group()
         return
     metric, unit, scaling = metric_of(cfg)
+    graphed = cfg["kind"] == "train" and use_graph
     hbm, bf16, bf16_sus, which = peaks()
     tf32_peak = bf16_sus / 2.0           # dense TF32 tensor-pipe peak ~ 1/2 of the measured (sustained) bf16 figure
     # the tensor-pipe peak of the mode's operand type (fp16 runs at the bf16 rate), and how many tensor products the mode
@@ -554,8 +555,12 @@ def main():
         "data": "synthetic", "config": config_dict(args.config), "precision": args.precision,
         "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-        "host_launches_per_step_ungraphed": launches_host, "clocks": clocks,
+        # kernels of this library that EXECUTE inside the timed region.  Under CUDA-graph replay the host issues only the
+        # graph launch + the optimizer's kernels (host_launches); the graph's kernel nodes are the same launches the
+        # uncaptured step issues, counted by the library's launch counter in the profiling pass
+        "gpu_launches": int(round(launches_host * args.steps)) if graphed else int(launches),
+        "gpu_launches_per_step": launches_host if graphed else launches / args.steps,
+        "host_launches": int(launches), "cuda_graph": bool(graphed), "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "%s (%s)" % (fam[dom], kind),
                      "achieved": achieved, "peak": mode_peak, "unit": "TFLOP/s", "frac": achieved / mode_peak,
                      "traffic": ncu_traffic(("conv_fwd", "conv_wgrad")[dom], args.precision),
