@@ -336,6 +336,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch / candidate count of the config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph")
+    ap.add_argument("--no-wgrad-overlap", action="store_true",
+                    help="conv weight gradients on the launch stream instead of the library's side stream (A/B)")
     ap.add_argument("--precision", default=os.environ.get("OP3_PRECISION", "f16x3"), choices=["fp32", "tf32x3", "tf32", "f16x3"],
                     help="arithmetic of the 5x5 convolutions (see op3_set_precision)")
     args = ap.parse_args()
@@ -416,6 +418,8 @@ def main():
         # scaled config (~85 GB per step) only one of them fits in HBM, and launch gaps are invisible at 1 s per step
         use_graph = (not args.no_graph) and cfg["D"] == 64
         trainer.use_cuda_graph = use_graph
+        model.engine.wgrad_overlap = not args.no_wgrad_overlap
+        extra["wgrad_overlap"] = bool(model.engine.wgrad_overlap)
         sched = np.array(cfg["schedule"], dtype=np.float64)
         lw = np.arange(1, len(sched) + 1)
         n_batches = 4
@@ -509,6 +513,7 @@ def main():
     # roofline numerators come from here, with every kernel launched from the host
     if cfg["kind"] == "train":
         trainer.use_cuda_graph = False
+        model.engine.wgrad_overlap = False     # per-family times are kernel durations: no two families share the SMs here
     lib.op3_profile_enable(1)
     n_prof = min(args.steps, 5)
     l1 = lib.op3_launch_count()
@@ -519,6 +524,7 @@ def main():
     lib.op3_profile_enable(0)
     if cfg["kind"] == "train":
         trainer.use_cuda_graph = use_graph
+        model.engine.wgrad_overlap = not args.no_wgrad_overlap
     # end to end: pinned host inputs in, result scalars out, every step
     for i in range(min(2, args.warmup)):
         step_e2e(i)

@@ -104,6 +104,15 @@ int op3_set_fused_mlp(int on);
  * tcgen05.mma.cta_group::2 stream (bit-identical results; its MMA stream is 27 % faster but the kernel is not, yet: its
  * loaders and epilogue are issue-bound).  Default 0 = the single-CTA form. */
 int op3_set_tcq_pair(int on);
+/* Weight-gradient lane.  1: the convolution weight-gradient kernels of op3_decoder_bwd / op3_refine_bwd are issued to a
+ * per-device side stream, ordered after the work already issued to the call's stream (event edge; under stream capture they
+ * become a parallel branch of the graph), so they fill the SMs that the small kernels of the dgrad chain leave idle.  The
+ * caller then owns the join: op3_wgrad_join(stream) makes `stream` wait for the lane, and must be called before any buffer
+ * handed to those calls (acts, d_out, scratch, pg) is overwritten, freed or read back, before op3_finalize_grads, and before a
+ * capture ends.  Gradients are bit-identical to the serial order (one FIFO lane per device).  Default 0: everything on the
+ * call's stream, no join needed.  The reference has no counterpart (autograd runs op3_model.py's backward on one stream). */
+int op3_set_wgrad_overlap(int on);
+int op3_wgrad_join(void* stream);
 
 /* Optional timing of kernel families with CUDA events on the launch stream (used by bench.py for the roofline
  * numbers).  Families: 0 = conv5x5 forward/dgrad, 1 = conv5x5 wgrad, 2 = mixture kernels, 3 = small GEMMs.

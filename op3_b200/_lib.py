@@ -65,6 +65,8 @@ SIGNATURES = {
     "op3_get_precision": (C.c_int, []),
     "op3_set_fused_mlp": (C.c_int, [C.c_int]),
     "op3_set_tcq_pair": (C.c_int, [C.c_int]),
+    "op3_set_wgrad_overlap": (C.c_int, [C.c_int]),
+    "op3_wgrad_join": (C.c_int, [C.c_void_p]),
     "op3_profile_enable": (C.c_int, [C.c_int]),
     "op3_profile_collect": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
     "op3_prepared_floats": (C.c_size_t, [_P(Op3Dims)]),

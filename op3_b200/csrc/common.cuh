@@ -53,6 +53,11 @@ bool fused_mlp_enabled();
 // quint-tap conv kernel as CTA pairs (tcgen05 cta_group::2); op3_set_tcq_pair(0) selects the single-CTA form
 bool tcq_pair_enabled();
 
+// weight-gradient lane (api.cu): the stream a conv weight-gradient launch of a backward call goes to -- `st` itself unless
+// op3_set_wgrad_overlap(1), then the per-device side stream, ordered after everything issued to `st` so far
+int wgrad_stream(cudaStream_t st, cudaStream_t* out);
+bool wgrad_overlap_enabled();
+
 // ---- small device helpers -------------------------------------------------------------------
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 // derivative of ELU(alpha=1) expressed through its OUTPUT a: a>0 -> 1, else a+1 (= e^x)
@@ -129,6 +134,7 @@ struct ConvSrc {          // one group of float4 channel-chunks of the (virtual)
   const float4* ptr;      // [n_idx][nchunks][D][D] float4
   int nchunks;
   int div;                // n_idx = (div > 0) ? n / div : 0   (div=1 per slot-image, K per sample, 0 constant)
+  int pitch;              // chunks per image in memory when only `nchunks` of them are read (0: = nchunks)
 };
 struct ConvInput {
   ConvSrc src[5];
@@ -141,7 +147,8 @@ struct ConvInput {
   const uint32_t* maxbits;
   uint32_t* out_maxbits;
 };
-enum { EPI_NONE = 0, EPI_ELU = 1, EPI_MUL_ELUGRAD = 2 };
+enum { EPI_NONE = 0, EPI_ELU = 1, EPI_MUL_ELUGRAD = 2,
+       EPI_ACCUM = 8, EPI_MAX2 = 16 };   // flags of the quint-tap kernel's second K pass (conv5x5_tc.cu)
 // out[n][cout/4][D][D] = epi( conv5x5_pad2(in, wt) + bias ); wt layout [25][cin_pad][cout] (cout fastest)
 int conv5x5_forward(cudaStream_t st, int N, int D, const ConvInput& in, int cout, const float* wt, const float* bias,
                     float4* out, int epi, const float4* elu_ref);

@@ -390,6 +390,11 @@ constexpr int TQ_SMEM_PAIR = TQ_A_BYTES + TQ_W_BYTES / 2 + TQ_PAIR_NEG * TQ_XCH 
 #ifndef OP3_TQ_IDLE
 #define OP3_TQ_IDLE 1
 #endif
+// out += v as one 16-byte reduction (REDG.E.ADD.F32x4): no return value, no register or latency cost for the issuing warp
+__device__ __forceinline__ void red_add_f4(float4* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <int NEG> struct TqRoles {
   static constexpr bool HAS_IDLE = OP3_TQ_IDLE != 0;
   static constexpr int EPI = 4 * NEG, MMA = EPI, IDLE = HAS_IDLE ? MMA + 4 : 1000, LOAD0 = MMA + 1, NLOAD = OP3_TQ_NLOAD;   // IDLE: the loader-range warp on the issuer's scheduler
@@ -397,12 +402,15 @@ template <int NEG> struct TqRoles {
   static constexpr int THREADS = (LOAD0 + NLOAD + (HAS_IDLE ? 1 : 0)) * 32;
   static constexpr int SMEM_X = NEG * TQ_XCH * 4 + EPI * 128 * 4;                              // exchange buffers + per-warp fix-up rows
 };
-template <bool PAIR, int NEG, bool LEAN>
+template <bool PAIR, int NEG, bool LEAN, bool STRIPS, bool ACCUM>
 __global__ void __launch_bounds__(TqRoles<NEG>::THREADS, 1)
 conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, const float* __restrict__ bias, int cout_real,
                    float4* __restrict__ out, int out_planes, int out_chunk0, int out_chunks, int epi,
                    const float4* __restrict__ ref, const uint32_t* __restrict__ maxbits, const float* __restrict__ wscale,
-                   int W, int nstrips, const __grid_constant__ CUtensorMap wmap, int use_tma) {
+                   int W_arg, int nstrips_arg, const __grid_constant__ CUtensorMap wmap, int use_tma) {
+  // STRIPS = false is the whole-image instance (every 64 x 64 configuration): W = D, one item per image and x0 = 0 are
+  // compile-time facts there -- as runtime values they cost the loaders and the epilogue ~10 % (registers, index arithmetic)
+  const int W = STRIPS ? W_arg : D, nstrips = STRIPS ? nstrips_arg : 1;
   // An "item" is one image (nstrips == 1, W == D) or one vertical strip of W output columns of an image (D = 128: two
   // strips of 64, so that 128 + 4 P rows still fit four chunks of the ring).  Whole images use pitch D + 2: the two
   // right-hand pad columns of a row double as the left-hand pad of the next (3 % padding rows instead of 6 %).  Strips carry
@@ -678,6 +686,12 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
     const size_t plane = (size_t)D * D;
     float* xb = xch + grp * TQ_XCH;
     const bool want_max = in.out_maxbits != nullptr;
+    // EPI_ACCUM: this launch is the second K pass of a contraction over more than 32 channels -- its results are ADDED to what
+    // the first pass stored (one fire-and-forget 16-byte reduction per float4: each element has exactly one writer, so the sum
+    // is deterministic).  EPI_MAX2: record twice the magnitudes, so that the two passes' maxima bound the magnitude of the sum.
+    const int epi_b = epi & 3;
+    constexpr bool accum = ACCUM;                          // (a separate instance: as a runtime flag it cost the main path ~5 %)
+    const float max_mul = (epi & EPI_MAX2) ? 2.f : 1.f;
     const float m1 = lane < 31 ? 1.f : 0.f, m2 = lane < 30 ? 1.f : 0.f, m3 = lane < 29 ? 1.f : 0.f, m4 = lane < 28 ? 1.f : 0.f;
     int j = 0;
     for (int g = g0; g < g1;) {
@@ -758,7 +772,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
               else mbar_arrive(&acc_empty[slot]);
             }
             float4 rh[4];                                    // dgrad: activation outputs whose ELU' multiplies this half
-            if (epi == EPI_MUL_ELUGRAD) {
+            if (epi_b == EPI_MUL_ELUGRAD) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 rh[i] = (valid && 4 * half + i < out_chunks) ? __ldg(&ref[obase + (4 * half + i) * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -796,13 +810,13 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
                 const float4 bb = *reinterpret_cast<const float4*>(&s_bias[16 * half + 4 * i]);
                 float4 o = make_float4(fmaf(acc[4 * i], inv_scale, bb.x), fmaf(acc[4 * i + 1], inv_scale, bb.y),
                                        fmaf(acc[4 * i + 2], inv_scale, bb.z), fmaf(acc[4 * i + 3], inv_scale, bb.w));
-                if (epi == EPI_ELU) {
+                if (epi_b == EPI_ELU) {
                   o.x = elu_tc(o.x); o.y = elu_tc(o.y); o.z = elu_tc(o.z); o.w = elu_tc(o.w);
-                } else if (epi == EPI_MUL_ELUGRAD) {
+                } else if (epi_b == EPI_MUL_ELUGRAD) {
                   o.x *= elu_grad_from_out(rh[i].x); o.y *= elu_grad_from_out(rh[i].y);
                   o.z *= elu_grad_from_out(rh[i].z); o.w *= elu_grad_from_out(rh[i].w);
                 }
-                out[obase + c4 * plane] = o;
+                if (accum) red_add_f4(&out[obase + c4 * plane], o); else out[obase + c4 * plane] = o;
                 if (want_max) omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
               }
             }
@@ -853,7 +867,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         // dgrad: the activation outputs whose ELU' multiplies the result -- requested only now (the tap-shift temporaries are
         // dead), their latency hides behind the group barrier and the boundary fix-up
         float4 ra[8];
-        if (epi == EPI_MUL_ELUGRAD) {
+        if (epi_b == EPI_MUL_ELUGRAD) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) ra[i] = (valid && i < out_chunks) ? __ldg(&ref[obase + i * plane]) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
@@ -903,13 +917,13 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
               const float4 bb = *reinterpret_cast<const float4*>(&s_bias[16 * half + 4 * i]);
               float4 o = make_float4(fmaf(acc[half][4 * i], inv_scale, bb.x), fmaf(acc[half][4 * i + 1], inv_scale, bb.y),
                                      fmaf(acc[half][4 * i + 2], inv_scale, bb.z), fmaf(acc[half][4 * i + 3], inv_scale, bb.w));
-              if (epi == EPI_ELU) {
+              if (epi_b == EPI_ELU) {
                 o.x = elu_tc(o.x); o.y = elu_tc(o.y); o.z = elu_tc(o.z); o.w = elu_tc(o.w);
-              } else if (epi == EPI_MUL_ELUGRAD) {
+              } else if (epi_b == EPI_MUL_ELUGRAD) {
                 o.x *= elu_grad_from_out(ra[c4].x); o.y *= elu_grad_from_out(ra[c4].y);
                 o.z *= elu_grad_from_out(ra[c4].z); o.w *= elu_grad_from_out(ra[c4].w);
               }
-              out[obase + c4 * plane] = o;
+              if (accum) red_add_f4(&out[obase + c4 * plane], o); else out[obase + c4 * plane] = o;
               if (want_max) omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
             }
           }
@@ -927,6 +941,7 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         }   // !LEAN
       }
       if (in.out_maxbits != nullptr) {                      // magnitudes of the written tensor, for its consumer's operand scale
+        omax *= max_mul;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
         if (lane == 0 && __float_as_uint(omax) > __ldcg(&in.out_maxbits[n])) atomicMax(&in.out_maxbits[n], __float_as_uint(omax));
@@ -1041,8 +1056,10 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
                const uint32_t* maxbits, const float* wscale) {
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<false, 2, TQ_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
-    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM_PAIR));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<false, 2, TQ_LEAN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<false, 2, TQ_LEAN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<false, 2, TQ_LEAN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM));
+    OP3_CHECK(cudaFuncSetAttribute(conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM_PAIR));
   }
   const int g_num_sms = device_sm_count();
   int W = 0, nstrips = 0;
@@ -1050,7 +1067,7 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
   const int P = nstrips == 1 ? D + TQ_PAD : W + 4;
   const int tiles_img = (D * P + TQ_TS - 1) / TQ_TS;
   const long long items = (long long)N * nstrips;
-  if (tcq_pair_enabled() && items % 2 == 0 && items >= 2) {
+  if (tcq_pair_enabled() && items % 2 == 0 && items >= 2 && !(epi & EPI_ACCUM)) {
     // CTA pairs (cta_group::2): one cluster of two CTAs per TPC, each pair owns a contiguous range of item-pair tiles
     const long long total = items / 2 * tiles_img;
     cudaLaunchConfig_t cfg{};
@@ -1069,14 +1086,14 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
     if (dev >= 0 && dev < OP3_MAX_DEVICES && max_pairs[dev] == 0) {
       cfg.gridDim = dim3(2 * (g_num_sms / 2));
       int nc = 0;
-      OP3_CHECK(cudaOccupancyMaxActiveClusters(&nc, conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN>, &cfg));
+      OP3_CHECK(cudaOccupancyMaxActiveClusters(&nc, conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN, true, false>, &cfg));
       max_pairs[dev] = nc > 0 ? nc : 1;
     }
     int pairs = (dev >= 0 && dev < OP3_MAX_DEVICES) ? max_pairs[dev] : g_num_sms / 2;
     if (total < pairs) pairs = (int)total;
     cfg.gridDim = dim3(2 * pairs);
     CUtensorMap nomap{};
-    OP3_CHECK(cudaLaunchKernelEx(&cfg, conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN>, in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
+    OP3_CHECK(cudaLaunchKernelEx(&cfg, conv5x5_tcq_kernel<true, TQ_PAIR_NEG, TQ_LEAN, true, false>, in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
                                  out_chunks, epi, ref, maxbits, wscale, W, nstrips, nomap, 0));
     OP3_COUNT_LAUNCH();
     return OP3_OK;
@@ -1085,8 +1102,16 @@ int launch_tcq(cudaStream_t st, int N, int D, const ConvInput& in, const float* 
   const int grid = total < g_num_sms ? (int)total : g_num_sms;
   CUtensorMap wmap{};
   const int use_tma = tq_weight_tmap(wt, (in.total_chunks + 3) / 4, &wmap) ? 1 : 0;
-  conv5x5_tcq_kernel<false, 2, TQ_LEAN><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0,
-                                                               out_chunks, epi, ref, maxbits, wscale, W, nstrips, wmap, use_tma);
+  if (epi & EPI_ACCUM) {
+    OP3_REQUIRE(nstrips == 1, "conv5x5_tcq: the accumulating pass is built for whole images only (D=%d)", D);
+    conv5x5_tcq_kernel<false, 2, TQ_LEAN, false, true><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(
+        in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0, out_chunks, epi, ref, maxbits, wscale, W, nstrips, wmap, use_tma);
+  } else if (nstrips == 1)
+    conv5x5_tcq_kernel<false, 2, TQ_LEAN, false, false><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(
+        in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0, out_chunks, epi, ref, maxbits, wscale, W, nstrips, wmap, use_tma);
+  else
+    conv5x5_tcq_kernel<false, 2, TQ_LEAN, true, false><<<grid, TqRoles<2>::THREADS, TQ_SMEM, st>>>(
+        in, N, D, wt, bias, cout_real, out, out_planes, out_chunk0, out_chunks, epi, ref, maxbits, wscale, W, nstrips, wmap, use_tma);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   return OP3_OK;
@@ -1160,6 +1185,22 @@ int conv5x5_tc_forward(cudaStream_t st, int precision, int N, int D, const ConvI
     if (nout == 16 && !quint)
       return launch_tc<16, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
     if (nout == 16) return launch_tcq(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);
+    int tq_w = 0, tq_ns = 0;
+    if (nout == 32 && in.total_chunks == 16 && in.nsrc == 1 && epi != EPI_ELU && tq_strips(D, &tq_w, &tq_ns) && tq_ns == 1) {
+      // 64 input channels (dgrad of the refinement net's third conv): two K passes of 32 channels on the quint-tap kernel, whose
+      // resident weights and activation ring hold two 16-channel K groups.  Pass 1 stores, pass 2 adds (EPI_ACCUM); both apply the
+      // epilogue factor, which distributes over the sum ((a + b) * ELU' = a * ELU' + b * ELU').
+      ConvInput lo = in, hi = in;
+      lo.src[0].nchunks = hi.src[0].nchunks = 8;
+      lo.src[0].pitch = hi.src[0].pitch = in.src[0].pitch ? in.src[0].pitch : 16;
+      hi.src[0].ptr = in.src[0].ptr + (size_t)8 * D * D;
+      lo.total_chunks = hi.total_chunks = 8;
+      lo.real_cin = hi.real_cin = 0;
+      const size_t kgroup = (size_t)25 * 2 * 64 * 4;      // floats per 16-channel K group of the fp16 slab
+      OP3_TRY(launch_tcq(st, N, D, lo, wt, bias, cout, out, planes, 0, planes, epi | EPI_MAX2, elu_ref, maxbits, wt + slab - 4));
+      return launch_tcq(st, N, D, hi, wt + 2 * kgroup, nullptr, cout, out, planes, 0, planes, epi | EPI_ACCUM | EPI_MAX2, elu_ref, maxbits,
+                        wt + slab - 4);
+    }
     if (nout == 32)
       return quint ? launch_tcq(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4)
                    : launch_tc<32, 2>(st, N, D, in, wt, bias, cout, out, planes, 0, planes, epi, elu_ref, maxbits, wt + slab - 4);

@@ -161,7 +161,9 @@ extern "C" size_t op3_decoder_acts_floats(const Op3Dims* d, int N) {
 
 extern "C" size_t op3_decoder_scratch_floats(const Op3Dims* d, int N) {
   if (validate_dims(d) != OP3_OK) return 0;
-  return 2 * (size_t)N * 32 * d->D * d->D + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) +
+  // four gradient planes: each layer's dPre keeps its own buffer, so a weight-gradient kernel that runs late on the
+  // weight-gradient lane (op3_set_wgrad_overlap) never sees its operand overwritten by a later dgrad
+  return 4 * (size_t)N * 32 * d->D * d->D + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3) +
          conv5x5_wgrad_scratch_floats(32, 32) + tc_scratch_floats(N);
 }
 
@@ -207,8 +209,9 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
   const int R = d->Rd + d->Rs, D = d->D;
   DecActs A = dec_acts(d, N, const_cast<float*>(acts));
   const size_t plane = (size_t)N * 32 * D * D;
-  float4* gbuf[2] = {reinterpret_cast<float4*>(scratch), reinterpret_cast<float4*>(scratch + plane)};
-  float* dT = scratch + 2 * plane;
+  float4* gbuf[4];
+  for (int i = 0; i < 4; ++i) gbuf[i] = reinterpret_cast<float4*>(scratch + i * plane);
+  float* dT = scratch + 4 * plane;
   float* wscr = dT + (((size_t)N * NCLS * 32 + 3) & ~(size_t)3);
   float* tcs = wscr + conv5x5_wgrad_scratch_floats(32, 32);
 
@@ -226,9 +229,11 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
     if (pg) {
       ConvInput xin = single_src(A.a[i], 8);
       if (f16) xin.maxbits = tc_slot(atcs, N, 1 + i);
-      OP3_TRY(conv5x5_wgrad_auto(st, N, D, xin, cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i], gmax));
+      cudaStream_t sw = st;
+      OP3_TRY(wgrad_stream(st, &sw));
+      OP3_TRY(conv5x5_wgrad_auto(sw, N, D, xin, cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i], gmax));
     }
-    float4* gn = gbuf[i & 1];
+    float4* gn = gbuf[i];
     // dgrad: conv over g with flipped/transposed weights, times ELU'(a[i]) -> dPre of the layer below
     ConvInput gin = single_src(g, gch);
     if (f16) { gin.maxbits = gmax; gin.out_maxbits = tc_slot(tcs, N, 1 + i); }

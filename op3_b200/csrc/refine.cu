@@ -747,11 +747,17 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
     gi2.maxbits = m2; gi2.out_maxbits = tc_slot(tcs, N, 3);
     gi1.maxbits = m1;
   }
-  OP3_TRY(conv5x5_wgrad_auto(st, N, D, x2, Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2], m3));
+  // weight gradients go to the weight-gradient lane (common.cuh: `st` itself unless op3_set_wgrad_overlap(1)); g3, g2, g1 are
+  // separate buffers and nothing on `st` writes what they read
+  cudaStream_t sw = st;
+  OP3_TRY(wgrad_stream(st, &sw));
+  OP3_TRY(conv5x5_wgrad_auto(sw, N, D, x2, Rs, g3, wscr, pg + L.ref_wf[2], pg + L.ref_bf[2], m3));
   OP3_TRY(conv5x5_auto(st, N, D, gi3, 32, prep + L.ref_wd[2], prep + L.ref_td[2], nullptr, g2, EPI_MUL_ELUGRAD, A.r2, tcs));
-  OP3_TRY(conv5x5_wgrad_auto(st, N, D, x1, 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1], m2));
+  OP3_TRY(wgrad_stream(st, &sw));
+  OP3_TRY(conv5x5_wgrad_auto(sw, N, D, x1, 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1], m2));
   OP3_TRY(conv5x5_auto(st, N, D, gi2, 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1, tcs));
-  OP3_TRY(conv5x5_wgrad_auto(st, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0], m1));
+  OP3_TRY(wgrad_stream(st, &sw));
+  OP3_TRY(conv5x5_wgrad_auto(sw, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0], m1));
   OP3_TRY(conv5x5_auto(st, N, D, gi1, REF_CIN_PAD, prep + L.ref_wd[0], prep + L.ref_td[0], nullptr,
                        reinterpret_cast<float4*>(d_in), EPI_NONE, nullptr, tcs));
   return OP3_OK;

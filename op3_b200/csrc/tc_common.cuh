@@ -235,7 +235,7 @@ __device__ __forceinline__ const float4* tc_src_chunk_ptr(const ConvInput& in, i
       int nc = in.src[s].nchunks;
       if (c < base + nc) {
         int idx = in.src[s].div > 0 ? n / in.src[s].div : 0;
-        return in.src[s].ptr + ((size_t)idx * nc + (c - base)) * D * D;
+        return in.src[s].ptr + ((size_t)idx * (in.src[s].pitch ? in.src[s].pitch : nc) + (c - base)) * D * D;
       }
       base += nc;
     }

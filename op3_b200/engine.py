@@ -581,10 +581,25 @@ class Engine:
     def backward(self, tape, g_total, g_kle, g_clog):
         """Accumulate d(g_total*total + g_kle*kle + g_clog*clog)/d params into a fresh flat gradient buffer and
         return it (same layout as flat_params())."""
-        with torch.cuda.device(self.flat_params().device):
-            return self._backward(tape, g_total, g_kle, g_clog)
+        dev = self.flat_params().device
+        # conv weight gradients on the library's weight-gradient lane (include/op3_b200.h, op3_set_wgrad_overlap): they fill
+        # the SMs the small kernels of the dgrad chain leave idle.  Joined once per state below (d_dec and the scratch
+        # buffers are reused from one state to the next) and before the gradients are finalised; the *_No_Sharing networks
+        # reuse one scratch buffer for K calls per state and keep the serial order.
+        overlap = bool(self.wgrad_overlap) and not (self.ns_dec or self.ns_ref)
+        with torch.cuda.device(dev):
+            if not overlap:
+                return self._backward(tape, g_total, g_kle, g_clog, False)
+            check(self.lib.op3_set_wgrad_overlap(1), "set_wgrad_overlap")
+            try:
+                return self._backward(tape, g_total, g_kle, g_clog, True)
+            finally:
+                self.lib.op3_wgrad_join(torch.cuda.current_stream(dev).cuda_stream)
+                self.lib.op3_set_wgrad_overlap(0)
 
-    def _backward(self, tape, g_total, g_kle, g_clog):
+    wgrad_overlap = True
+
+    def _backward(self, tape, g_total, g_kle, g_clog, overlap=False):
         m, lib = self.model, self.lib
         d, B = tape.dims, tape.B
         K, D, Rd, Rs = m.K, m.image_size, m.det_size, m.sto_size
@@ -640,6 +655,8 @@ class Engine:
             w_clog = (g_total + g_clog) * w
             w_kl = (g_total * float(m.beta) + g_kle) * w / B
             d_in = d_in_for.pop(id(dc), None) if dc is not None else None
+            if overlap:
+                check(lib.op3_wgrad_join(st), "wgrad_join")
             if dc is not None and (w_clog != 0.0 or d_in is not None):
                 check(lib.op3_mixture_bwd(C.byref(d), C.byref(dc.io), w_clog, ptr(d_in), ptr(d_dec), C.byref(gs), None, st),
                       "mixture_bwd")
@@ -721,6 +738,8 @@ class Engine:
             gview("initial_lambdas2", Rs).add_(s0.dl2.sum(0))
             if Rd:
                 gview("inital_deter_state", Rd).add_(s0.dz[:, :Rd].sum(0))
+        if overlap:
+            check(lib.op3_wgrad_join(st), "wgrad_join")
         for k in range(len(pgs)):        # per weight set; the shared networks' accumulators live in set 0 only
             check(lib.op3_finalize_grads(C.byref(d), ptr(pgs[k]), C.byref(gss[k]), st), "finalize_grads")
         s0.dz = s0.dl1 = s0.dl2 = s0.dh = s0.dc = None

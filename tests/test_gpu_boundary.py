@@ -155,3 +155,36 @@ def test_cuda_graph_train_step_is_bit_identical_to_eager():
     assert v_graph == v_eager, "losses differ:\n%r\n%r" % (v_graph, v_eager)
     for k in p_eager:
         assert torch.equal(p_eager[k], p_graph[k]), k
+
+
+def test_wgrad_lane_is_bit_identical_to_serial():
+    """Engine.wgrad_overlap (op3_set_wgrad_overlap / op3_wgrad_join): the conv weight-gradient kernels of the backward pass run on
+    the library's side stream next to the dgrad chain.  Same accumulation order per parameter, so three optimizer steps must
+    give the same losses and weights bit for bit as the serial order -- any operand overwritten early would show up here."""
+    import op3_b200
+    from op3_b200.engine import Engine
+    from op3_b200.torch.op3_modules.op3_trainer import OP3Trainer, TrainingScheduler
+    B, K, T = 16, 4, 3
+    sched, lw = np.array([0., 0., 1., 0., 1., 0.]), np.arange(1, 7)
+    batches = [(orc.synth_frames(B, T, seed=70 + i).cuda(), orc.synth_actions(B, T, seed=90 + i).cuda()) for i in range(3)]
+
+    def run(overlap):
+        m, _ = build_model(4, K, seed=0)
+        m.deterministic_sampling = True
+        m.engine.wgrad_overlap = overlap
+        tr = OP3Trainer(None, None, m, TrainingScheduler(2, "curriculum", T, T), B, lr=3e-4)
+        vals = [[float(v) for v in tr.train_step(*batches[i], sched, lw)] for i in range(3)]
+        return vals, {k: v.detach().clone() for k, v in m.named_parameters()}
+
+    assert Engine.wgrad_overlap is True, "the lane is the default"
+    for prec in ("f16x3", "fp32"):
+        op3_b200.set_precision(prec)
+        try:
+            v_ser, p_ser = run(False)
+            v_lane, p_lane = run(True)
+        finally:
+            op3_b200.set_precision("fp32")
+        assert v_lane == v_ser, "%s: losses differ:\n%r\n%r" % (prec, v_lane, v_ser)
+        for k in p_ser:
+            assert torch.equal(p_ser[k], p_lane[k]), "%s: %s" % (prec, k)
+    assert op3_b200._lib.load().op3_wgrad_join(torch.cuda.current_stream().cuda_stream) == 0      # nothing pending: a no-op
