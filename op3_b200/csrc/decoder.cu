@@ -226,18 +226,21 @@ extern "C" int op3_decoder_bwd(const Op3Dims* d, int N, const float* prep, const
   int gch = 1;  // chunks of g
   for (int i = 3; i >= 0; --i) {  // conv layer i+2, input a[i], output gradient g (dPre of that layer)
     const int cout = i == 3 ? 4 : 32;
-    if (pg) {
-      ConvInput xin = single_src(A.a[i], 8);
-      if (f16) xin.maxbits = tc_slot(atcs, N, 1 + i);
-      cudaStream_t sw = st;
-      OP3_TRY(wgrad_stream(st, &sw));
-      OP3_TRY(conv5x5_wgrad_auto(sw, N, D, xin, cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i], gmax));
-    }
     float4* gn = gbuf[i];
     // dgrad: conv over g with flipped/transposed weights, times ELU'(a[i]) -> dPre of the layer below
     ConvInput gin = single_src(g, gch);
     if (f16) { gin.maxbits = gmax; gin.out_maxbits = tc_slot(tcs, N, 1 + i); }
     OP3_TRY(conv5x5_auto(st, N, D, gin, 32, prep + L.dec_wd[i], prep + L.dec_td[i], nullptr, gn, EPI_MUL_ELUGRAD, A.a[i], tcs));
+    if (pg) {
+      ConvInput xin = single_src(A.a[i], 8);
+      if (f16) xin.maxbits = tc_slot(atcs, N, 1 + i);
+      // d_out carries no recorded maxima: the dgrad call above reduced them into slot 0 of tcs (conv5x5_tc_forward), and no
+      // later call of this function touches that slot -- the weight gradient reuses them instead of reducing d_out again
+      const uint32_t* wmax = (f16 && gmax == nullptr) ? tc_slot(tcs, N, 0) : gmax;
+      cudaStream_t sw = st;
+      OP3_TRY(wgrad_stream(st, &sw));
+      OP3_TRY(conv5x5_wgrad_auto(sw, N, D, xin, cout, g, wscr, pg + L.dec_wf[i], pg + L.dec_bf[i], wmax));
+    }
     g = gn;
     gmax = f16 ? gin.out_maxbits : nullptr;
     gch = 8;

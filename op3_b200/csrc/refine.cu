@@ -757,7 +757,9 @@ extern "C" int op3_refine_bwd(const Op3Dims* d, const Op3Params* p, const float*
   OP3_TRY(conv5x5_wgrad_auto(sw, N, D, x1, 32, g2, wscr, pg + L.ref_wf[1], pg + L.ref_bf[1], m2));
   OP3_TRY(conv5x5_auto(st, N, D, gi2, 32, prep + L.ref_wd[1], prep + L.ref_td[1], nullptr, g1, EPI_MUL_ELUGRAD, A.r1, tcs));
   OP3_TRY(wgrad_stream(st, &sw));
-  OP3_TRY(conv5x5_wgrad_auto(sw, N, D, refine_l1_input(d, io, prep, L), 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0], m1));
+  ConvInput x0 = refine_l1_input(d, io, prep, L);
+  if (f16) x0.maxbits = tc_slot(atcs, N, 0);     // reduced by the forward pass's first conv call into slot 0 of the acts' scratch
+  OP3_TRY(conv5x5_wgrad_auto(sw, N, D, x0, 32, g1, wscr, pg + L.ref_wf[0], pg + L.ref_bf[0], m1));
   OP3_TRY(conv5x5_auto(st, N, D, gi1, REF_CIN_PAD, prep + L.ref_wd[0], prep + L.ref_td[0], nullptr,
                        reinterpret_cast<float4*>(d_in), EPI_NONE, nullptr, tcs));
   return OP3_OK;
