@@ -666,6 +666,8 @@ __device__ unsigned long long g_ring_trace[256][8];   // issuer: operand wait, l
 #ifndef OP3_RING_SMEM_A
 #define OP3_RING_TMEM_A 1     /* X block staged in TMEM with tcgen05.cp (define OP3_RING_SMEM_A for the smem-A form) */
 #endif
+__host__ __device__ inline int ring_vb0(int P) { return (2 * P) / HG_BP; }                         // leading all-halo blocks of an item
+__host__ __device__ inline int ring_live_blocks(int D, int P) { return ((D + 2) * P + HG_BP - 1) / HG_BP - ring_vb0(P); }
 constexpr int RB_RING = 56;                  // G chunks in the ring (+ 1 guard slot = copy of slot 0 for wrapped K pairs)
 constexpr int RB_PRE = 5;                    // refill steps per item: 5 blocks = 40 chunks >= 4*P/8 = 36 (D = 64)
 constexpr int RB_LOADERS = 2 * 4 * 32;       // two groups (even / odd steps) of 2 X warps + 2 G warps
@@ -690,7 +692,11 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
   // two strips of 64 -- the G ring holds 4 rows of pitch W + 8).  The X window of a strip reads its real neighbour columns.
   const int P = W + 8;                                     // multiple of 8
   const int QN = (D + 4) * P;                              // padded-linear input pixels per item
-  const int NBLK = (QN + HG_BP - 1) / HG_BP;
+  // Blocks whose X pixels are all halo rows (zeros) do no work at all: the first VB0 blocks of an item (rows 0, 1) only feed
+  // G into the ring, which the refill steps of the first live block do anyway, and the blocks behind row D + 1 are dropped.
+  // D = 64: 73 live blocks (2 .. 74) of the 77 that cover the padded rows.
+  const int VB0 = ring_vb0(P);
+  const int NBLK = ring_live_blocks(D, P);                 // live blocks per item; block index vb = VB0 + live index
   // Each CTA owns a contiguous range [g0, g1) of the global block sequence (image-major), balanced to one block; an
   // "item" is one image's share of that range.  Only the first item of a CTA can start inside an image.
   const long long total_blocks = (long long)N * nstrips * NBLK;
@@ -728,8 +734,8 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
   float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // step sequence of this CTA: for item = blockIdx.x, += gridDim.x: vb = b0 - RB_PRE .. b1 - 1  (vb < b0: ring refill only)
-  auto item_b0 = [&](int item) { int b = g0 - item * NBLK; return b > 0 ? b : 0; };
-  auto item_b1 = [&](int item) { int e = g1 - item * NBLK; return e < NBLK ? e : NBLK; };
+  auto item_b0 = [&](int item) { int b = g0 - item * NBLK; return (b > 0 ? b : 0) + VB0; };
+  auto item_b1 = [&](int item) { int e = g1 - item * NBLK; return (e < NBLK ? e : NBLK) + VB0; };
   auto advance = [&](int& item, int& vb) {                 // next step; item >= n_items afterwards means "no more steps"
     if (++vb >= item_b1(item)) {
       item += 1;
@@ -864,7 +870,10 @@ conv5x5_wgrad_ring_kernel(ConvInput in, int N, int D, const float4* __restrict__
         const unsigned long long tc0 = clock64();
 #endif
         if (act) {
-          if (vb >= item_b0(item)) {                       // refill chunks belong to the previous range's sum
+          // refill chunks belong to the previous range's sum -- except the G chunks of the leading halo blocks, which only
+          // ever pass through the refill of the range that starts the item
+          const int b0i = item_b0(item);
+          if (vb >= b0i || (b0i == VB0 && vb >= 0)) {
 #pragma unroll
             for (int e = 4; e < 12; ++e) {
               bias_acc.x += gv[e].x; bias_acc.y += gv[e].y; bias_acc.z += gv[e].z; bias_acc.w += gv[e].w;
@@ -1169,7 +1178,7 @@ int launch_wgrad_ring(cudaStream_t st, int N, int D, const ConvInput& in, const 
   const int g_wg_sms = device_sm_count() > 148 ? 148 : device_sm_count();   // scratch is sized for 148 slabs
   int W = 0, nstrips = 0;
   OP3_REQUIRE(ring_strips(D, &W, &nstrips), "conv5x5_wgrad_ring: D=%d has no strip decomposition", D);
-  const int P = W + 8, NBLK = ((D + 4) * P + HG_BP - 1) / HG_BP;
+  const int P = W + 8, NBLK = ring_live_blocks(D, P);
   const long long total_blocks = (long long)N * nstrips * NBLK;
   const int grid = total_blocks < g_wg_sms ? (int)total_blocks : g_wg_sms;
   conv5x5_wgrad_ring_kernel<<<grid, RB_THREADS, RB_SMEM, st>>>(in, N, D, dpre, g_planes, g_chunk0, g_chunks, cout_total,

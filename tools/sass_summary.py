@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "op3_b200", "libop3_b200.so")
 KEYS = ["UTCHMMA", "UTCQMMA", "UTCMMA", "UTCCP", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "HMMA", "MMA.",
-        "SYNCS", "UCGABAR", "SHFL", "MUFU", "FFMA", "LDS", "STS", "LDG", "STG", "BAR.SYNC", "ELECT"]
+        "SYNCS", "UCGABAR", "SHFL", "MUFU", "FFMA", "LDS", "STS", "LDG", "STG", "REDG", "BAR.SYNC", "ELECT"]
 
 
 def main():
