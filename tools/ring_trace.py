@@ -25,9 +25,10 @@ def main():
                    sto_repsize=64, det_repsize=64, K=4, extra_args=dict(beta=1e-2, deterministic_sampling=False))
     model = create_model_v2(variant, 64, 64, 4).to(dev)
     trainer = OP3Trainer(None, None, model, TrainingScheduler(4, "curriculum", 5, 5), 64, lr=3e-4)
-    fr, ac = bench.synth_batch(64, 1)
+    cfg = bench.CONFIGS["c2"]
+    fr, ac = bench.synth_batch(cfg, 64, 1)
     fr, ac = fr.to(dev).float() / 255.0, ac.to(dev)
-    sched, lw = np.array(bench.SCHEDULE, dtype=np.float64), np.arange(1, 10)
+    sched, lw = np.array(cfg["schedule"], dtype=np.float64), np.arange(1, 10)
     for _ in range(2):
         trainer.train_step(fr, ac, sched, lw)
     torch.cuda.synchronize()
