@@ -173,7 +173,7 @@ constexpr int LR = PITCH(128), L2R = PITCH(256), LSE = PITCH(160), L32 = PITCH(3
 constexpr int DYN_FWD_SMEM_FLOATS = GEMM_SMEM_FLOATS + 16 * (LR + L2R + LSE + LSE + LR + L32 + L2R + LR + L32 + 2 + LR);
 constexpr int DYN_BWD_SMEM_FLOATS = GEMM_SMEM_FLOATS + 16 * (L64 + L2R + LR + LR + LSE + L32 + L32 + LR + L2R + LSE + LR);
 
-__global__ void __launch_bounds__(FT) dyn_fwd_fused_kernel(const Op3Dims d, const __grid_constant__ Op3Params p, const DynActs A,
+__global__ void __launch_bounds__(FT, 1) dyn_fwd_fused_kernel(const Op3Dims d, const __grid_constant__ Op3Params p, const DynActs A,
                                                            const float* __restrict__ z, const float* __restrict__ actions,
                                                            float* __restrict__ out_z, float* __restrict__ l1_out,
                                                            float* __restrict__ l2_out, int S, int tc) {
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(FT) dyn_fwd_fused_kernel(const Op3Dims d, cons
 
 // Backward of the chain above for the same samples: every pre-activation gradient is written to the gradient twin G of its
 // activation buffer (the batched weight-gradient launch that follows contracts them over ALL rows), dz is written.
-__global__ void __launch_bounds__(FT) dyn_bwd_fused_kernel(const Op3Dims d, const __grid_constant__ Op3Params p, const DynActs A,
+__global__ void __launch_bounds__(FT, 1) dyn_bwd_fused_kernel(const Op3Dims d, const __grid_constant__ Op3Params p, const DynActs A,
                                                            const DynActs G, const float* __restrict__ d_out_z,
                                                            const float* __restrict__ d_l1, const float* __restrict__ d_l2,
                                                            float* __restrict__ dz, int S, int tc) {

@@ -5,7 +5,7 @@
 // chains of layers no wider than 512: launched layer by layer they are pure launch latency (a training step of the pickplace
 // variant spent 370 launches and 5 ms on them).  Here ONE CTA owns a tile of up to 16 rows (for the dynamics: every slot and
 // every ordered slot pair of the same samples) and walks the whole chain with the activations in shared memory; only the
-// weights stream in (L2 -> shared memory, cp.async, 4-stage ring of 64 x 32 tiles) and only what the backward pass or the
+// weights stream in (L2 -> shared memory, cp.async, 4-stage ring of 128 x 32 tiles) and only what the backward pass or the
 // caller needs is written out.  Two arithmetic paths behind one interface: fp32 FMA (exact mode; its inner loop is bound by the
 // shared-memory reads of the activation panel, 1 LDS.128 per 4 FMAs) and warp-level tensor-core MMAs with 3xTF32 operand
 // splitting (every other mode; fp32-grade like the convolutions of those modes, 6 scalar LDS per 3 MMAs).
@@ -16,12 +16,16 @@
 namespace op3 {
 namespace fused {
 
-constexpr int FT = 256;                 // threads per CTA: 64 output columns x 4 contraction groups
+#ifndef OP3_FUSED_WARPS
+#define OP3_FUSED_WARPS 16              /* warps per CTA (8 or 16): the chains are latency-bound, a warp owns 8 output columns */
+#endif
+constexpr int FT = 32 * OP3_FUSED_WARPS; // threads per CTA: TN output columns x 4 contraction groups
 constexpr int RTM = 16;                 // rows of one activation panel
-constexpr int TN = 64, TK = 32;         // weight tile: 64 output columns x 32 contraction steps
+constexpr int TN = 8 * OP3_FUSED_WARPS, TK = 32;   // weight tile: TN output columns x 32 contraction steps
 constexpr int PNT = TK + 4;             // pitch of a [column][k] tile (float4 reads, conflict-free over 8 lanes)
-constexpr int PNN = TN + 8;             // pitch of a [k][column] tile (72 = 8 mod 32: conflict-free mma B fragments)
-constexpr int WTILE = TN * PNT;         // 2304 floats = TK * PNN
+constexpr int PNN = TN + 8;             // pitch of a [k][column] tile (8 mod 32: conflict-free mma B fragments)
+constexpr int WTILE = TN * PNT > TK * PNN ? TN * PNT : TK * PNN;
+static_assert(FT == 4 * TN && PNN % 32 == 8, "thread maps below: 4 contraction groups of TN threads, two 16-byte chunks per thread and tile");
 constexpr int NST = 4;                  // tiles in flight
 constexpr int GEMM_SMEM_FLOATS = NST * WTILE + 4 * RTM * TN;     // weight ring + cross-group reduction buffer
 
@@ -66,15 +70,15 @@ template <bool NN, int RT>
 __device__ __noinline__ void cta_gemm_rt(const float* Xs, int ldx, int rows, const float* __restrict__ W, int ldw, int kdim,
                                          int ncols, float* wt, const Epi ep) {
   static_assert((NST & (NST - 1)) == 0, "NST must be a power of two");
-  const int tid = threadIdx.x, n = tid & 63, kq = tid >> 6;
+  const int tid = threadIdx.x, n = tid % TN, kq = tid / TN;
   float* red = wt + NST * WTILE;
   const int nkt = (kdim + TK - 1) / TK, nnt = (ncols + TN - 1) / TN, total = nkt * nnt;
   // every thread copies two 16-byte chunks per tile: (row crow, crow + rstep) x 4 consecutive elements at ccol
-  const int crow = NN ? (tid >> 4) : (tid >> 3);
-  const int ccol = NN ? (tid & 15) * 4 : (tid & 7) * 4;
-  constexpr int rstep = NN ? 16 : 32;
+  const int crow = NN ? tid / (TN / 4) : (tid >> 3);
+  const int ccol = NN ? (tid % (TN / 4)) * 4 : (tid & 7) * 4;
+  constexpr int rstep = NN ? 4 * FT / TN : FT / 8;
   const int soff = NN ? crow * PNN + ccol : crow * PNT + ccol;
-  constexpr int sstep = NN ? 16 * PNN : 32 * PNT;
+  constexpr int sstep = NN ? rstep * PNN : rstep * PNT;
   int pt = 0, pn0 = 0, pk0 = 0;                              // prefetch cursor: tile index, its first column and first k
   auto issue = [&]() {
     if (pt < total) {
@@ -159,7 +163,7 @@ __device__ __noinline__ void cta_gemm_rt(const float* Xs, int ldx, int rows, con
     for (int r = 0; r < RT; ++r) red[(kq * RT + r) * TN + n] = acc[r];
     __syncthreads();
     for (int e = tid; e < rows * TN; e += FT) {
-      const int r = e >> 6, i = e & 63, c = nt * TN + i;
+      const int r = e / TN, i = e % TN, c = nt * TN + i;
       if (c < ncols) {
         float v = ((red[(0 * RT + r) * TN + i] + red[(1 * RT + r) * TN + i]) + red[(2 * RT + r) * TN + i]) +
                   red[(3 * RT + r) * TN + i];
@@ -200,7 +204,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// Same contract as cta_gemm_rt on the tensor cores: warp w owns columns 8w .. 8w+7 of the 64-column tile and all 16 panel
+// Same contract as cta_gemm_rt on the tensor cores: warp w owns columns 8w .. 8w+7 of the TN-column tile and all 16 panel
 // rows (one m16n8k8 accumulator, no cross-warp reduction).  Operands are split x = hi + lo with hi = rn_tf32(x), lo =
 // rn_tf32(x - hi) and the three products lo*hi + hi*lo + hi*hi accumulate in fp32 (3xTF32: ~1e-6 relative, like the tf32x3
 // convolutions).  ldx = 4 mod 32 keeps the A-fragment loads conflict-free.
@@ -209,11 +213,11 @@ __device__ __noinline__ void cta_gemm_mma(const float* Xs, int ldx, int rows, co
                                           int ncols, float* wt, const Epi ep) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
   const int nkt = (kdim + TK - 1) / TK, nnt = (ncols + TN - 1) / TN, total = nkt * nnt;
-  const int crow = NN ? (tid >> 4) : (tid >> 3);
-  const int ccol = NN ? (tid & 15) * 4 : (tid & 7) * 4;
-  constexpr int rstep = NN ? 16 : 32;
+  const int crow = NN ? tid / (TN / 4) : (tid >> 3);
+  const int ccol = NN ? (tid % (TN / 4)) * 4 : (tid & 7) * 4;
+  constexpr int rstep = NN ? 4 * FT / TN : FT / 8;
   const int soff = NN ? crow * PNN + ccol : crow * PNT + ccol;
-  constexpr int sstep = NN ? 16 * PNN : 32 * PNT;
+  constexpr int sstep = NN ? rstep * PNN : rstep * PNT;
   int pt = 0, pn0 = 0, pk0 = 0;
   auto issue = [&]() {
     if (pt < total) {

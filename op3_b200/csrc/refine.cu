@@ -277,7 +277,7 @@ constexpr int REF_FWD_SMEM_FLOATS = GEMM_SMEM_FLOATS + 16 * (LPO + LXW + LHH + L
 constexpr int REF_BWD_SMEM_FLOATS = GEMM_SMEM_FLOATS + 16 * (LPO + LHH + LG + LXW);
 
 // extra == nullptr: columns [128, 448) of X are built from the latent state (op3_refine_fwd); else copied from extra [N][320]
-__global__ void __launch_bounds__(FT) ref_head_fwd_kernel(int N, int R, int Rd, const __grid_constant__ Op3Params p,
+__global__ void __launch_bounds__(FT, 1) ref_head_fwd_kernel(int N, int R, int Rd, const __grid_constant__ Op3Params p,
                                                           const __grid_constant__ Op3RefineIO io, float w_kl,
                                                           const float* __restrict__ extra, const float* __restrict__ pooled,
                                                           float* __restrict__ X, float* __restrict__ gates,
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(FT) ref_head_fwd_kernel(int N, int R, int Rd, 
 
 // Backward of the head for a row tile.  Writes dgates and dX (columns [0,128) already multiplied by ELU' of the FC output:
 // the operands of the batched weight-gradient launch), dpool; adds the direct paths into dl1, dl2, dz_acc, dh, dc.
-__global__ void __launch_bounds__(FT) ref_head_bwd_kernel(int N, int R, int Rd, const __grid_constant__ Op3Params p,
+__global__ void __launch_bounds__(FT, 1) ref_head_bwd_kernel(int N, int R, int Rd, const __grid_constant__ Op3Params p,
                                                           const float* __restrict__ gates, const float* __restrict__ Xa,
                                                           const float* __restrict__ c_prev, const float* __restrict__ d_l1n,
                                                           const float* __restrict__ d_l2n, const float* __restrict__ d_h,
