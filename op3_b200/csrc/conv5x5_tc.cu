@@ -134,10 +134,10 @@ conv5x5_tc_kernel(ConvInput in, int N, int D, int G, const float* __restrict__ w
 #pragma unroll
                 for (int kc = 0; kc < 2; ++kc) {
                   uint4 hi, lo;
-                  f16_split2(v[u][2 * kc].x * sc, v[u][2 * kc].y * sc, hi.x, lo.x);
-                  f16_split2(v[u][2 * kc].z * sc, v[u][2 * kc].w * sc, hi.y, lo.y);
-                  f16_split2(v[u][2 * kc + 1].x * sc, v[u][2 * kc + 1].y * sc, hi.z, lo.z);
-                  f16_split2(v[u][2 * kc + 1].z * sc, v[u][2 * kc + 1].w * sc, hi.w, lo.w);
+                  f16_split2_scaled(v[u][2 * kc].x, v[u][2 * kc].y, sc, hi.x, lo.x);
+                  f16_split2_scaled(v[u][2 * kc].z, v[u][2 * kc].w, sc, hi.y, lo.y);
+                  f16_split2_scaled(v[u][2 * kc + 1].x, v[u][2 * kc + 1].y, sc, hi.z, lo.z);
+                  f16_split2_scaled(v[u][2 * kc + 1].z, v[u][2 * kc + 1].w, sc, hi.w, lo.w);
                   a_hi16[kc * PH + h] = hi;
                   a_lo16[kc * PH + h] = lo;
                 }
@@ -534,10 +534,10 @@ conv5x5_tcq_kernel(ConvInput in, int N, int D, const float* __restrict__ wt, con
         for (int u = 0; u < NR; ++u)
           if (tact[u] && !skip) {
             uint4 hi, lo;
-            f16_split2(v[u][0].x * sc, v[u][0].y * sc, hi.x, lo.x);
-            f16_split2(v[u][0].z * sc, v[u][0].w * sc, hi.y, lo.y);
-            f16_split2(v[u][1].x * sc, v[u][1].y * sc, hi.z, lo.z);
-            f16_split2(v[u][1].z * sc, v[u][1].w * sc, hi.w, lo.w);
+            f16_split2_scaled(v[u][0].x, v[u][0].y, sc, hi.x, lo.x);
+            f16_split2_scaled(v[u][0].z, v[u][0].w, sc, hi.y, lo.y);
+            f16_split2_scaled(v[u][1].x, v[u][1].y, sc, hi.z, lo.z);
+            f16_split2_scaled(v[u][1].z, v[u][1].w, sc, hi.w, lo.w);
             const int row = slot * TQ_TS + ti[u];
             uint4* ph = reinterpret_cast<uint4*>(a_s + (size_t)tk[u] * TQ_PLANE);
             uint4* pl = reinterpret_cast<uint4*>(a_s + (size_t)(4 + tk[u]) * TQ_PLANE);

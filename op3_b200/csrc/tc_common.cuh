@@ -164,6 +164,22 @@ __device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint3
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// f16_split2(a * sc, b * sc, ...) with the scale and the residual as packed fp32 pairs (FMUL2 / FADD2: 6 instead of 8
+// instructions per pair when a and b sit in an aligned register pair, e.g. the .x/.y or .z/.w of a loaded float4); same
+// roundings, bit-identical results
+__device__ __forceinline__ void f16_split2_scaled(float a, float b, float sc, uint32_t& hi, uint32_t& lo) {
+  float sa, sb;
+  asm("{\n\t.reg .b64 p, s, r;\n\tmov.b64 p, {%2, %3};\n\tmov.b64 s, {%4, %4};\n\tmul.rn.f32x2 r, p, s;\n\tmov.b64 {%0, %1}, r;\n\t}"
+      : "=f"(sa), "=f"(sb) : "f"(a), "f"(b), "f"(sc));
+  const __half2 h = __floats2half2_rn(sa, sb);
+  const float2 hf = __half22float2(h);
+  float ra, rb;
+  asm("{\n\t.reg .b64 p, q, r;\n\tmov.b64 p, {%2, %3};\n\tmov.b64 q, {%4, %5};\n\tsub.rn.f32x2 r, p, q;\n\tmov.b64 {%0, %1}, r;\n\t}"
+      : "=f"(ra), "=f"(rb) : "f"(sa), "f"(sb), "f"(hf.x), "f"(hf.y));
+  const __half2 l = __floats2half2_rn(ra, rb);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
