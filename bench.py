@@ -434,9 +434,23 @@ def main():
             fr, ac = resident[i % n_batches]
             return trainer.train_step(fr, ac, sched, lw)
 
+        from op3_b200.torch.op3_modules.op3_trainer import ScalarReadback
+        readback = ScalarReadback(dev, 4, trainer.stat_lag)
+        e2e_rows = []
+
         def step_e2e(i):
+            # the loop body of OP3Trainer.train_epoch: every step copies its batch from pinned host memory, and every step's
+            # four scalars travel back to the host -- read one step later (stat_lag = 1), while the next step runs
             fr, ac = host[i % n_batches]
             frd, acd = trainer.prepare_tensors((fr, ac))      # pinned uint8 -> H2D as bytes -> op3_prepare_frames (/255)
+            vals = trainer.train_step(frd, acd, sched, lw)
+            e2e_rows.extend(readback.push(vals))
+            return vals
+
+        def step_e2e_sync(i):
+            # the reference's own loop: loss.item() after every batch (op3_trainer.py:203-213) -- the GPU waits for the host
+            fr, ac = host[i % n_batches]
+            frd, acd = trainer.prepare_tensors((fr, ac))
             vals = trainer.train_step(frd, acd, sched, lw)
             out4.copy_(torch.stack(vals), non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
@@ -529,6 +543,11 @@ def main():
     for i in range(min(2, args.warmup)):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_sync = None
+    if cfg["kind"] == "train":
+        e2e_rows.extend(readback.drain())
+        assert len(e2e_rows) == args.steps + min(2, args.warmup) and all(np.isfinite(r).all() for r in e2e_rows), "e2e read-back"
+        ms_e2e_sync = timed(step_e2e_sync, args.steps)
 
     units = units_per_step * args.steps
     value = units / (ms_total * 1e-3)
@@ -559,8 +578,13 @@ def main():
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split on tcgen05)", "tf32": "tf32",
                                        "f16x3": "f32 (fp16 hi/lo operand split on tcgen05, fp32 accumulate)"}[args.precision],
         "data": "synthetic", "config": config_dict(args.config), "precision": args.precision,
-        "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e": dict({"value": e2e_value, "unit": unit, "ms_per_step": ms_e2e / args.steps,
+                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                    **({"readback": "every step's scalars copied to pinned host memory and read one step later "
+                                    "(OP3Trainer.train_epoch, stat_lag=1)",
+                        "sync_value": units / (ms_e2e_sync * 1e-3), "sync_ms_per_step": ms_e2e_sync / args.steps,
+                        "sync_readback": "blocking read after every step (the reference's loss.item())"}
+                       if ms_e2e_sync is not None else {})),
         # kernels of this library that EXECUTE inside the timed region.  Under CUDA-graph replay the host issues only the
         # graph launch + the optimizer's kernels (host_launches); the graph's kernel nodes are the same launches the
         # uncaptured step issues, counted by the library's launch counter in the profiling pass

@@ -143,6 +143,41 @@ def frames_to_float(frames_u8):
     return out
 
 
+class ScalarReadback:
+    """Per-step scalars on the host without stalling the step loop.
+
+    The reference's train_epoch reads the loss with .item() after every batch (op3_trainer.py:203-213): the GPU then idles
+    while the host prepares and launches the next step.  Here every step's scalars are copied into a pinned ring
+    (non_blocking, one event per row) and the host picks a row up when its event has completed -- at the latest `lag` steps
+    later, i.e. while the next step is already running.  lag = 0 is the reference's blocking read."""
+
+    def __init__(self, device, n=4, lag=1, slots=8):
+        self.ring = torch.empty(max(slots, lag + 2), n, dtype=torch.float32).pin_memory()
+        self.events = [torch.cuda.Event() for _ in range(self.ring.shape[0])]
+        self.device, self.lag, self.pending, self.k = device, int(lag), [], 0
+
+    def push(self, scalars):
+        """Queue one step's scalars (device tensors); returns the rows (lists of floats) that became readable, in step order."""
+        slot = self.k % self.ring.shape[0]
+        self.k += 1
+        self.ring[slot].copy_(torch.stack([s.detach().reshape(()) for s in scalars]), non_blocking=True)
+        self.events[slot].record(torch.cuda.current_stream(self.device))
+        self.pending.append(slot)
+        out = []
+        while len(self.pending) > self.lag:
+            out.append(self._read(self.pending.pop(0)))
+        return out
+
+    def drain(self):
+        out = [self._read(s) for s in self.pending]
+        self.pending = []
+        return out
+
+    def _read(self, slot):
+        self.events[slot].synchronize()
+        return self.ring[slot].tolist()
+
+
 class OP3Trainer:
     def __init__(self, train_dataset, test_dataset, model, scheduler_class, batch_size, lr=1e-3):
         self.batch_size = batch_size
@@ -242,6 +277,8 @@ class OP3Trainer:
         vals = ent["scalars"].clone()             # the graph's own buffer is overwritten by the next replay
         return vals[0], vals[1], vals[2], vals[3]
 
+    stat_lag = 1     # train_epoch reads a step's scalars this many steps later (0 = blocking read every step, like the reference)
+
     def train_step(self, true_images, actions, schedule, loss_schedule):
         """One optimisation step (op3_trainer.py:166-197).  Returns the four logged scalars as device tensors.
 
@@ -273,16 +310,23 @@ class OP3Trainer:
             self.save_model(name)
         self.model.train()
         losses, log_probs, kles, mses, timings = [], [], [], [], []
+        rb = None
+
+        def log(rows):
+            for vals in rows:
+                losses.append(vals[0]); log_probs.append(vals[1]); kles.append(vals[2]); mses.append(vals[3])
         for batch_idx, tensors in enumerate(self.train_dataset.dataloader):
             true_images, actions = self.prepare_tensors(tensors)
             schedule = self.scheduler_class.get_schedule(epoch, is_train=True)
             loss_schedule = self.scheduler_class.get_loss_schedule(schedule)
             t0 = time.time()
-            loss, clog, kle, mse = self.train_step(true_images, actions, schedule, loss_schedule)
-            vals = torch.stack([loss, clog, kle, mse]).tolist()       # one device->host sync per step
-            t1 = time.time()
-            timings.append(t1 - t0)
-            losses.append(vals[0]); log_probs.append(vals[1]); kles.append(vals[2]); mses.append(vals[3])
+            scalars = self.train_step(true_images, actions, schedule, loss_schedule)
+            if rb is None:
+                rb = ScalarReadback(scalars[0].device, 4, self.stat_lag)
+            log(rb.push(scalars))                  # stat_lag = 1: step i's scalars are read while step i + 1 runs
+            timings.append(time.time() - t0)
+        if rb is not None:
+            log(rb.drain())
         return OrderedDict([
             ("train/epoch", epoch), ("train/Log Prob", np.mean(log_probs)), ("train/KL", np.mean(kles)),
             ("train/loss", np.mean(losses)), ("train/mse", np.mean(mses)), ("train/time_step", float(np.sum(timings))),

@@ -188,3 +188,34 @@ def test_wgrad_lane_is_bit_identical_to_serial():
         for k in p_ser:
             assert torch.equal(p_ser[k], p_lane[k]), "%s: %s" % (prec, k)
     assert op3_b200._lib.load().op3_wgrad_join(torch.cuda.current_stream().cuda_stream) == 0      # nothing pending: a no-op
+
+
+def test_train_epoch_lagged_readback_equals_blocking(tmp_path):
+    """OP3Trainer.stat_lag: train_epoch copies every step's scalars to pinned memory and reads them one step later (the GPU no
+    longer idles while the host prepares the next step).  Same epoch statistics as the blocking read of the reference."""
+    from torch.utils.data.dataset import TensorDataset
+    from op3_b200.torch.data_management.dataset import BlocksDataset
+    from op3_b200.torch.op3_modules.op3_trainer import OP3Trainer, TrainingScheduler, ScalarReadback
+    torch.manual_seed(0)
+    feats = torch.randint(0, 256, (12, 5, 3, 64, 64)).float()
+    actions = torch.randn(12, 5, 6)
+
+    def run(lag):
+        train = BlocksDataset(TensorDataset(feats, actions), batchsize=4, shuffle=False)
+        train.action_dim = 4
+        m, _ = build_model(4, 3, seed=0)
+        m.deterministic_sampling = True
+        t = OP3Trainer(train, train, m, TrainingScheduler(seed_steps=2, schedule_type="curriculum", max_T=5, T=3), batch_size=4, lr=3e-4)
+        t.stat_lag = lag
+        return t.train_epoch(1)
+
+    a, b = run(0), run(1)
+    for k in ("train/loss", "train/Log Prob", "train/KL", "train/mse"):
+        assert a[k] == b[k] and np.isfinite(a[k]), (k, a[k], b[k])
+    rb = ScalarReadback(torch.device("cuda", 0), 2, lag=1, slots=3)          # ring wrap-around, order, drain
+    rows = []
+    for i in range(7):
+        rows += rb.push([torch.tensor(float(i), device="cuda"), torch.tensor(float(-i), device="cuda")])
+        assert len(rows) == i
+    rows += rb.drain()
+    assert rows == [[float(i), float(-i)] for i in range(7)]
