@@ -14,7 +14,10 @@ __device__ __forceinline__ int border_class(int v, int D) { return v < 2 ? v : (
 // One thread owns one float4 position of the coordinate map and streams EXP_NG images through it (the position's border
 // class and map value are computed once).  maxbits (optional): per-image largest magnitude of a1 for the fp16 conv mode
 // (zeroed by the caller).
+// FAST (fp16 conv mode): ELU through ex2.approx like the tensor-core conv epilogues of that mode (conv5x5_tc.cu, elu_tc) --
+// with expm1f the kernel is bound by its ~120 instructions per float4 (45 us for 134 MB), not by the store bandwidth.
 constexpr int EXP_NG = 8;
+template <bool FAST>
 __global__ void __launch_bounds__(256) dec_l1_expand_kernel(const float* __restrict__ T, const float4* __restrict__ cmap,
                                                             int N, int D, float4* __restrict__ a1, uint32_t* __restrict__ maxbits) {
   const int n0 = blockIdx.y * EXP_NG;
@@ -37,7 +40,8 @@ __global__ void __launch_bounds__(256) dec_l1_expand_kernel(const float* __restr
     if (n >= N) { if ((threadIdx.x & 31) == 0) s_mx[g][threadIdx.x >> 5] = 0.f; continue; }
     if (live) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(T + (size_t)n * (NCLS * 32) + cls * 32 + c4 * 4));
-      const float4 v = make_float4(elu_f(t.x + m.x), elu_f(t.y + m.y), elu_f(t.z + m.z), elu_f(t.w + m.w));
+      auto elu = [](float x) { return FAST ? (x > 0.f ? x : __expf(x) - 1.f) : elu_f(x); };
+      const float4 v = make_float4(elu(t.x + m.x), elu(t.y + m.y), elu(t.z + m.z), elu(t.w + m.w));
       a1[(size_t)n * tot + i] = v;
       mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
     }
@@ -68,28 +72,54 @@ __global__ void __launch_bounds__(256) dec_l1_class_reduce_kernel(const float4* 
   for (int i = lane; i < NCLS; i += 32) wacc[w][i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   const float4* src = g1 + ((size_t)n * 8 + c4) * D * D;
-  for (int y = w; y < D; y += 8) {
-    int cy = border_class(y, D);
-    float4 mid = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int x = lane; x < D; x += 32) {
-      float4 v = src[(size_t)y * D + x];
-      int cx = border_class(x, D);
-      if (cx == 2) {
-        mid.x += v.x; mid.y += v.y; mid.z += v.z; mid.w += v.w;
-      } else {  // exactly one lane owns each border column of this row
-        float4 a = wacc[w][cy * 5 + cx];
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        wacc[w][cy * 5 + cx] = a;
+  // interior columns: per-lane partial sums run over all rows of one row class and are reduced across the warp once per class
+  // (a warp meets at most three classes), not once per row -- the kernel was bound by those 20 shuffles per row
+  float4 mid = make_float4(0.f, 0.f, 0.f, 0.f);
+  int mid_cy = -1;
+  auto flush = [&]() {
+    if (mid_cy >= 0) {
+      mid.x = warp_sum(mid.x); mid.y = warp_sum(mid.y); mid.z = warp_sum(mid.z); mid.w = warp_sum(mid.w);
+      if (lane == 0) {
+        float4 a = wacc[w][mid_cy * 5 + 2];
+        a.x += mid.x; a.y += mid.y; a.z += mid.z; a.w += mid.w;
+        wacc[w][mid_cy * 5 + 2] = a;
       }
+      __syncwarp();
     }
-    mid.x = warp_sum(mid.x); mid.y = warp_sum(mid.y); mid.z = warp_sum(mid.z); mid.w = warp_sum(mid.w);
-    if (lane == 0) {
-      float4 a = wacc[w][cy * 5 + 2];
-      a.x += mid.x; a.y += mid.y; a.z += mid.z; a.w += mid.w;
-      wacc[w][cy * 5 + 2] = a;
+    mid = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto add = [&](int cy, int x, const float4& v) {
+    const int cx = border_class(x, D);
+    if (cx == 2) {
+      mid.x += v.x; mid.y += v.y; mid.z += v.z; mid.w += v.w;
+    } else {  // exactly one lane owns each border column of a row
+      float4 a = wacc[w][cy * 5 + cx];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      wacc[w][cy * 5 + cx] = a;
     }
-    __syncwarp();
+  };
+  if (D == 64) {           // the warp's eight rows x two float4 per lane: all sixteen loads in flight before the first use
+    float4 v[8][2];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      v[r][0] = src[(size_t)(w + 8 * r) * 64 + lane];
+      v[r][1] = src[(size_t)(w + 8 * r) * 64 + lane + 32];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int cy = border_class(w + 8 * r, 64);
+      if (cy != mid_cy) { flush(); mid_cy = cy; }
+      add(cy, lane, v[r][0]);
+      add(cy, lane + 32, v[r][1]);
+    }
+  } else {
+    for (int y = w; y < D; y += 8) {
+      const int cy = border_class(y, D);
+      if (cy != mid_cy) { flush(); mid_cy = cy; }
+      for (int x = lane; x < D; x += 32) add(cy, x, src[(size_t)y * D + x]);
+    }
   }
+  flush();
   __syncthreads();
   if (threadIdx.x < NCLS) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -181,8 +211,12 @@ extern "C" int op3_decoder_fwd(const Op3Dims* d, int N, const float* prep, const
   // fp16 mode: slots 1..4 of tcs keep the per-image maxima of a1..a4 (written by their producers, reused by backward)
   const bool f16 = op3_get_precision() == OP3_PREC_F16X3;
   if (f16) OP3_CHECK(cudaMemsetAsync(tcs, 0, tc_scratch_floats(N) * sizeof(float), st));
-  dec_l1_expand_kernel<<<dim3(ceil_div(8 * D * D, 256), ceil_div(N, EXP_NG)), 256, 0, st>>>(
-      A.T, reinterpret_cast<const float4*>(prep + L.cmap), N, D, A.a[0], f16 ? tc_slot(tcs, N, 1) : nullptr);
+  if (f16)
+    dec_l1_expand_kernel<true><<<dim3(ceil_div(8 * D * D, 256), ceil_div(N, EXP_NG)), 256, 0, st>>>(
+        A.T, reinterpret_cast<const float4*>(prep + L.cmap), N, D, A.a[0], tc_slot(tcs, N, 1));
+  else
+    dec_l1_expand_kernel<false><<<dim3(ceil_div(8 * D * D, 256), ceil_div(N, EXP_NG)), 256, 0, st>>>(
+        A.T, reinterpret_cast<const float4*>(prep + L.cmap), N, D, A.a[0], nullptr);
   OP3_COUNT_LAUNCH();
   OP3_LAUNCH_CHECK();
   // layers 2-4 are the implicit-GEMM hot spot (M = N*D*D pixels, N = 32, K = 800); layer 5 has 4 outputs
